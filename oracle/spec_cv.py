@@ -1,0 +1,160 @@
+"""TEST INFRASTRUCTURE ONLY -- integer restatement of the three OpenCV primitives the
+reference's v2 degradations delegate to (parity pinned: checked bit-exact against the
+real `cv2` of this image, 4.13.0, in tests/test_oracle_cv.py; the reference pins
+opencv-python 4.8.0.76 -- requirements.txt:42).
+
+  * cv2.GaussianBlur(block, (5, 5), sigmaX=1.0)        elvis.py:2190, utils.py:1209, presley.py:989
+  * cv2.resize(block, (s, s), interpolation=INTER_AREA)   elvis.py:2161, utils.py:1160, presley.py:982
+  * cv2.resize(small, (bs, bs), interpolation=INTER_LINEAR) elvis.py:2163, utils.py:1161, presley.py:983
+
+All functions take single-channel uint8 blocks shaped (..., h, w) -- leading axes are a
+batch of independent blocks (cv2 treats channels independently for these three
+operations) -- and return uint8.  The CUDA kernels in
+elvis_b200/csrc/degrade.cu mirror these formulas; the coefficient tables they consume
+are produced by elvis_b200/_tables.py with the same arithmetic as `linear_coeffs` /
+`area_table` below (two independent implementations, compared in the tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+GAUSS5_SIGMA1_Q8 = np.array([14, 62, 104, 62, 14], dtype=np.int64)  # sums to 256
+
+
+def _reflect101(i: int, n: int) -> int:
+    """cv2.BORDER_REFLECT_101 index map (gfedcb|abcdefgh|gfedcba)."""
+    if n == 1:
+        return 0
+    while i < 0 or i >= n:
+        if i < 0:
+            i = -i
+        if i >= n:
+            i = 2 * (n - 1) - i
+    return i
+
+
+def gaussian_blur5(block: np.ndarray) -> np.ndarray:
+    """One round of the 5x5 sigma=1 blur on an isolated block (border at the block edge).
+
+    Fixed-point separable filter: horizontal pass exact in 8.8, vertical pass exact in
+    16.16, one final rounding (acc + 2^15) >> 16.
+    """
+    h, w = block.shape[-2:]
+    src = block.astype(np.int64)
+    cols = np.array([[_reflect101(x + d, w) for d in (-2, -1, 0, 1, 2)] for x in range(w)])
+    rows = np.array([[_reflect101(y + d, h) for d in (-2, -1, 0, 1, 2)] for y in range(h)])
+    hp = (src[..., :, cols] * GAUSS5_SIGMA1_Q8).sum(axis=-1)                     # (..., h, w)
+    vp = (hp[..., rows, :] * GAUSS5_SIGMA1_Q8[:, None]).sum(axis=-2)
+    return ((vp + 32768) >> 16).astype(np.uint8)
+
+
+def gaussian_blur5_rounds(block: np.ndarray, rounds: int) -> np.ndarray:
+    out = block
+    for _ in range(int(rounds)):
+        out = gaussian_blur5(out)
+    return out
+
+
+# ----------------------------------------------------------------------------- INTER_AREA
+def area_table(ssize: int, dsize: int):
+    """Per-axis overlap table of cv2's generic area resize: list of (si, di, alpha) with
+    alpha a float32 weight.  scale = ssize/dsize (double); for each dst cell the source
+    span [dx*scale, (dx+1)*scale) is split into a leading partial cell, whole cells and
+    a trailing partial cell; weights are divided by min(scale, ssize - fsx1)."""
+    scale = float(ssize) / float(dsize)
+    tab = []
+    for dx in range(dsize):
+        fsx1 = dx * scale
+        fsx2 = fsx1 + scale
+        cell = min(scale, ssize - fsx1)
+        sx1 = int(np.ceil(fsx1))
+        sx2 = int(np.floor(fsx2))
+        sx2 = min(sx2, ssize - 1)
+        sx1 = min(sx1, sx2)
+        if sx1 - fsx1 > 1e-3:
+            tab.append((sx1 - 1, dx, np.float32((sx1 - fsx1) / cell)))
+        for sx in range(sx1, sx2):
+            tab.append((sx, dx, np.float32(1.0 / cell)))
+        if fsx2 - sx2 > 1e-3:
+            tab.append((sx2, dx, np.float32(min(min(fsx2 - sx2, 1.0), cell) / cell)))
+    return tab
+
+
+def resize_area(block: np.ndarray, dsize: int) -> np.ndarray:
+    """cv2.resize(block, (dsize, dsize), interpolation=cv2.INTER_AREA) for a square block."""
+    ssize = block.shape[-1]
+    assert block.shape[-2] == block.shape[-1]
+    lead = block.shape[:-2]
+    if dsize == ssize:
+        return block.copy()
+    if ssize % dsize == 0:
+        f = ssize // dsize
+        s = block.astype(np.int64).reshape(lead + (dsize, f, dsize, f)).sum(axis=(-3, -1))
+        if f == 2:
+            return ((s + 2) >> 2).astype(np.uint8)
+        # integer factor > 2: sum * float32(1/area), round half to even
+        scale = np.float32(1.0) / np.float32(f * f)
+        return np.rint(s.astype(np.float32) * scale).astype(np.uint8)
+    # generic fractional scale: float32 accumulation in table order, rows then columns
+    tab = area_table(ssize, dsize)
+    buf = np.zeros(lead + (ssize, dsize), dtype=np.float32)
+    srcf = block.astype(np.float32)
+    for (si, di, a) in tab:
+        buf[..., :, di] = buf[..., :, di] + srcf[..., :, si] * a
+    out = np.zeros(lead + (dsize, dsize), dtype=np.float32)
+    for (si, di, b) in tab:
+        out[..., di, :] = out[..., di, :] + buf[..., si, :] * b
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------- INTER_LINEAR
+def linear_coeffs(ssize: int, dsize: int, horizontal: bool):
+    """Source index pairs and 11-bit coefficients of cv2's u8 bilinear resize.
+
+    Returns (i0, i1, c0, c1): for dst index d, value = S[i0[d]]*c0[d] + S[i1[d]]*c1[d].
+    Horizontal taps are clamped *with* their weights (f forced to 0 at the borders);
+    vertical taps only have their row indices clamped (weights kept).
+    """
+    scale = float(ssize) / float(dsize)
+    i0 = np.zeros(dsize, np.int32)
+    i1 = np.zeros(dsize, np.int32)
+    c0 = np.zeros(dsize, np.int32)
+    c1 = np.zeros(dsize, np.int32)
+    for d in range(dsize):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        s = int(np.floor(f))
+        f = np.float32(f - np.float32(s))
+        if horizontal:
+            if s < 0:
+                s, f = 0, np.float32(0)
+            if s >= ssize - 1:
+                s, f = ssize - 1, np.float32(0)
+            i0[d] = s
+            i1[d] = min(s + 1, ssize - 1)
+        else:
+            i0[d] = min(max(s, 0), ssize - 1)
+            i1[d] = min(max(s + 1, 0), ssize - 1)
+        c0[d] = int(np.rint(np.float32(np.float32(1.0) - f) * np.float32(2048)))
+        c1[d] = int(np.rint(f * np.float32(2048)))
+    return i0, i1, c0, c1
+
+
+def resize_linear(small: np.ndarray, dsize: int) -> np.ndarray:
+    """cv2.resize(small, (dsize, dsize), interpolation=cv2.INTER_LINEAR) for square u8."""
+    ssize = small.shape[-1]
+    assert small.shape[-2] == small.shape[-1]
+    if ssize == dsize:
+        return small.copy()
+    s = small.astype(np.int64)
+    hi0, hi1, a0, a1 = linear_coeffs(ssize, dsize, horizontal=True)
+    vi0, vi1, b0, b1 = linear_coeffs(ssize, dsize, horizontal=False)
+    rows = s[..., :, hi0] * a0 + s[..., :, hi1] * a1                     # (..., ssize, dsize) 19-bit
+    r0 = rows[..., vi0, :] >> 4
+    r1 = rows[..., vi1, :] >> 4
+    out = (((b0[:, None] * r0) >> 16) + ((b1[:, None] * r1) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def down_up(block: np.ndarray, small: int) -> np.ndarray:
+    """AREA down to small x small then LINEAR up to the block size (elvis.py:2160-2163)."""
+    return resize_linear(resize_area(block, small), block.shape[-1])

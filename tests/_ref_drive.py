@@ -1,0 +1,62 @@
+"""Drive the unmodified reference `calculate_removability_scores` (elvis.py:968-1224) with
+its two external tools faked, so that its in-tree tail (elvis.py:1160-1220) can be used as
+a checker.  EVCA (`python -m evca.main`, elvis.py:1014-1031) is replaced by a function
+that writes the caller's SC/TC as the CSVs the tail reads; UFO (elvis.py:1109-1113) by a
+function that writes the caller's foreground masks as PNGs.  Build-container only."""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+import types
+from unittest import mock
+
+import numpy as np
+
+from oracle import ref_import
+
+
+def run_reference_removability(sc, tc, fg_masks, alpha, beta, block_size):
+    """sc, tc: (T, By, Bx) float64.  fg_masks: None or (T, By, Bx) uint8 (0 = background),
+    written at block resolution so the reference's NEAREST resize is the identity."""
+    import cv2
+    E = ref_import.load("elvis")
+    T, By, Bx = sc.shape
+    width, height = Bx * block_size, By * block_size
+    with tempfile.TemporaryDirectory() as tmp:
+        pkg_dir = os.path.join(tmp, "evca")
+        os.makedirs(pkg_dir)
+        frames_dir = os.path.join(tmp, "frames")
+        os.makedirs(frames_dir)
+        for i in range(T):
+            open(os.path.join(frames_dir, f"{i + 1:05d}.png"), "wb").close()
+        raw = os.path.join(tmp, "raw.yuv")
+        open(raw, "wb").close()
+        fake_evca = types.ModuleType("evca")
+        fake_evca.__file__ = os.path.join(pkg_dir, "__init__.py")
+
+        def fake_run(cmd, *a, **k):
+            for name, arr in (("evca_SC_blocks.csv", sc), ("evca_TC_blocks.csv", tc)):
+                table = arr.reshape(T, By * Bx).T        # rows = blocks, cols = frames
+                with open(os.path.join(pkg_dir, name), "w") as f:
+                    f.write(",".join(f"f{i}" for i in range(T)) + "\n")
+                    for row in table:
+                        f.write(",".join(repr(float(v)) for v in row) + "\n")
+            return types.SimpleNamespace(returncode=0, stdout="", stderr="")
+
+        def fake_ufo(device, model, datapath, save_root, *a):
+            if fg_masks is None:
+                return
+            for i in range(T):
+                cv2.imwrite(os.path.join(save_root[0], f"{i + 1:05d}.png"), fg_masks[i])
+
+        fake_ufo_pkg = types.ModuleType("ufo")
+        fake_ufo_pkg.__file__ = os.path.join(tmp, "ufo", "__init__.py")
+        fake_ufo_test = types.ModuleType("ufo.test")
+        fake_ufo_test.debug_test = fake_ufo
+        with mock.patch.dict(sys.modules, {"evca": fake_evca, "ufo": fake_ufo_pkg, "ufo.test": fake_ufo_test}), \
+                mock.patch.object(E.subprocess, "run", fake_run), \
+                mock.patch("builtins.print", lambda *a, **k: None):
+            out = E.calculate_removability_scores(raw, frames_dir, width, height, block_size,
+                                                  alpha=alpha, working_dir=tmp, smoothing_beta=beta)
+    return np.asarray(out)
