@@ -1,0 +1,95 @@
+"""Host-side coefficient tables for elvis_degrade_downsample (layout documented in
+csrc/degrade.cu).  The arithmetic follows OpenCV's resize setup code for 8-bit images:
+the bilinear taps are float32 positions quantised to 11 bits, the fractional INTER_AREA
+weights are float32 overlaps.  tests/test_tables.py compares these against the
+independent restatement in oracle/spec_cv.py."""
+from __future__ import annotations
+
+import math
+from functools import lru_cache
+
+import numpy as np
+
+KIND_COPY, KIND_2X2, KIND_INT, KIND_FRAC = 0, 1, 2, 3
+
+
+def level_stride(pb: int) -> int:
+    return 8 + (pb + 1) + 4 * pb + 8 * pb
+
+
+def _linear_taps(ssize: int, dsize: int, horizontal: bool):
+    d = np.arange(dsize, dtype=np.float64)
+    pos = ((d + 0.5) * (ssize / dsize) - 0.5).astype(np.float32)
+    base = np.floor(pos).astype(np.int64)
+    frac = (pos - base.astype(np.float32)).astype(np.float32)
+    if horizontal:   # taps AND weights collapse at the borders
+        lo = base < 0
+        hi = base >= ssize - 1
+        frac = np.where(lo | hi, np.float32(0), frac)
+        base = np.where(lo, 0, np.where(hi, ssize - 1, base))
+        i0, i1 = base, np.minimum(base + 1, ssize - 1)
+    else:            # only the row indices are clamped
+        i0, i1 = np.clip(base, 0, ssize - 1), np.clip(base + 1, 0, ssize - 1)
+    c0 = np.rint((np.float32(1) - frac) * np.float32(2048)).astype(np.int32)
+    c1 = np.rint(frac * np.float32(2048)).astype(np.int32)
+    return i0.astype(np.int32), i1.astype(np.int32), c0, c1
+
+
+def _area_entries(ssize: int, dsize: int):
+    """(start[dsize+1], src_index[], alpha float32[]) of the fractional area kernel."""
+    scale = ssize / dsize
+    start, src, alpha = [0], [], []
+    for d in range(dsize):
+        a, b = d * scale, d * scale + scale
+        cell = min(scale, ssize - a)
+        first, last = math.ceil(a), min(math.floor(b), ssize - 1)
+        first = min(first, last)
+        if first - a > 1e-3:
+            src.append(first - 1)
+            alpha.append((first - a) / cell)
+        for s in range(first, last):
+            src.append(s)
+            alpha.append(1.0 / cell)
+        if b - last > 1e-3:
+            src.append(last)
+            alpha.append(min(min(b - last, 1.0), cell) / cell)
+        start.append(len(src))
+    return np.array(start, np.int32), np.array(src, np.int32), np.array(alpha, np.float32)
+
+
+@lru_cache(maxsize=64)
+def build(pb: int, small_sizes: tuple) -> np.ndarray:
+    """int32 blob with one entry per level; small_sizes[level] is the side the block is
+    reduced to (== pb: the level copies the block)."""
+    stride = level_stride(pb)
+    blob = np.zeros((len(small_sizes), stride), np.int32)
+    for lv, small in enumerate(small_sizes):
+        small = int(small)
+        e = blob[lv]
+        e[0] = small
+        if small >= pb:
+            e[1] = KIND_COPY
+            continue
+        if pb % small == 0:
+            f = pb // small
+            e[1] = KIND_2X2 if f == 2 else KIND_INT
+            e[2] = f
+            e[3] = np.array([np.float32(1.0) / np.float32(f * f)], np.float32).view(np.int32)[0]
+        else:
+            e[1] = KIND_FRAC
+            start, src, alpha = _area_entries(pb, small)
+            assert len(src) <= 2 * pb
+            e[4] = len(src)
+            e[8:8 + small + 1] = start
+            ent = e[8 + pb + 1: 8 + pb + 1 + 4 * pb].reshape(2 * pb, 2)
+            ent[:len(src), 0] = src
+            ent[:len(src), 1] = alpha.view(np.int32)
+        off = 8 + pb + 1 + 4 * pb
+        for horizontal in (True, False):
+            i0, i1, c0, c1 = _linear_taps(small, pb, horizontal)
+            e[off:off + pb] = i0
+            e[off + pb:off + 2 * pb] = i1
+            e[off + 2 * pb:off + 3 * pb] = c0
+            e[off + 3 * pb:off + 4 * pb] = c1
+            off += 4 * pb
+    return blob.reshape(-1)

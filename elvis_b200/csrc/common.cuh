@@ -1,0 +1,55 @@
+// Shared host/device helpers for the elvis_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/elvis_b200.h"
+
+namespace elvis {
+
+extern thread_local int g_last_cuda_error;
+
+inline int cuda_fail(cudaError_t e) {
+    g_last_cuda_error = (int)e;
+    return ELVIS_ERR_CUDA;
+}
+
+// Launch check: catches configuration errors at enqueue time without synchronising.
+#define ELVIS_CHECK_LAUNCH()                                   \
+    do {                                                       \
+        cudaError_t e__ = cudaGetLastError();                  \
+        if (e__ != cudaSuccess) return ::elvis::cuda_fail(e__); \
+    } while (0)
+
+inline cudaStream_t as_stream(elvis_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline bool aligned_to(const void* p, int64_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// Largest power-of-two vector width (bytes, <= 16) usable for rows of `row_bytes` payload
+// addressed as base + frame*frame_stride + row*row_stride + k*unit.
+inline int vector_unit(const elvis_plane* p, int64_t row_bytes) {
+    int u = 16;
+    while (u > 1) {
+        if (aligned_to(p->data, u) && p->frame_stride % u == 0 && p->row_stride % u == 0 && row_bytes % u == 0)
+            return u;
+        u >>= 1;
+    }
+    return 1;
+}
+
+inline int plane_ok(const elvis_plane* p) {
+    return p && p->data && p->height > 0 && p->width > 0 && p->channels >= 1 && p->row_stride >= (int64_t)p->width * p->channels;
+}
+
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+
+// streaming 128/64/32-bit accesses: no L1 allocation (every byte is touched once)
+template <typename V> __device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
+template <typename V> __device__ __forceinline__ void st_stream(V* p, V v) { __stcs(p, v); }
+
+// float(2^23 + b) for byte K of w: byte_perm builds the bit pattern 0x4B0000bb directly, so a
+// u8 -> fp32 conversion is one PRMT (and the 2^23 bias cancels in differences).
+template <int K> __device__ __forceinline__ float byte_as_biased_float(uint32_t w) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 + K));
+}
+
+}  // namespace elvis

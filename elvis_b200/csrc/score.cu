@@ -1,0 +1,268 @@
+// a1: per-block spatial (SC) and temporal (TC) DCT-energy features -- the arithmetic the
+// reference delegates to the external EVCA package (elvis.py:1014-1031, presley.py:202).
+// Spec: oracle/spec_scoring.py.
+//
+// Mapping.  One thread owns one 8x8 luma tile and walks it through a run of consecutive
+// frames; the tile never leaves registers, so there is no shared-memory staging and no
+// transposition.  A warp covers R x (32/R) tiles (R = block_size / 8), i.e. one block row of
+// 32/R^2 blocks, so that every row load of the warp is R fully used 128-byte lines and the
+// per-block sum is an R*R-lane xor-shuffle reduction.
+//
+// Temporal streaming.  DCT is linear, so C_t = C_{t-1} + DCT(Y_t - Y_{t-1}).  Each frame costs
+// ONE 8x8 transform (of the exact integer frame difference): its weighted magnitude is TC, and
+// the running sum of the differences is C_t, whose weighted magnitude is SC.  Transforming the
+// small integer difference keeps TC accurate to fp32 rounding of *its own* magnitude
+// (|C_t| - |C_{t-1}| computed from two large fp32 coefficients would not).  Every luma byte is
+// read from HBM once per chunk of frames; a chunk primes its accumulator with one extra
+// transform of the frame before it.
+#include "common.cuh"
+#include "dct8.cuh"
+
+namespace elvis {
+
+struct ScoreParams {
+    const uint8_t* y;
+    const uint8_t* halo;
+    int64_t frame_stride, row_stride;
+    int32_t T, By, Bx, tiles_x, chunk_len, n_chunks;
+    float* sc;
+    float* tc;
+    unsigned* mm;   // {sc_min, sc_max, tc_min, tc_max} as float bits (all values are >= +0)
+    int32_t mm_begin, mm_end;
+    float inv_area;
+};
+
+namespace {
+
+__device__ constexpr float kW[8][8] = {
+#include "score_weights.inc"
+};
+
+constexpr int kScoreThreads = 128;
+
+template <bool ALIGNED>
+__device__ __forceinline__ void load_tile(uint2 (&dst)[8], const uint8_t* p, int64_t row_stride, bool valid) {
+    if (!valid) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) dst[r] = make_uint2(0u, 0u);
+        return;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint8_t* q = p + r * row_stride;
+        if (ALIGNED) {
+            dst[r] = __ldcs(reinterpret_cast<const uint2*>(q));
+        } else {
+            uint32_t lo = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24);
+            uint32_t hi = q[4] | (q[5] << 8) | (q[6] << 16) | ((uint32_t)q[7] << 24);
+            dst[r] = make_uint2(lo, hi);
+        }
+    }
+}
+
+template <int R, bool ALIGNED>
+__global__ void __launch_bounds__(kScoreThreads, 2) score_kernel(const ScoreParams p) {
+    constexpr int TW = 32 / R;   // tiles per warp-tile row
+    const int lane = threadIdx.x & 31;
+    const int unit = blockIdx.x * (kScoreThreads / 32) + (threadIdx.x >> 5);
+    const int per_chunk = p.By * p.tiles_x;
+    if (unit >= per_chunk * p.n_chunks) return;
+    const int chunk = unit / per_chunk;
+    const int rem = unit - chunk * per_chunk;
+    const int by = rem / p.tiles_x;
+    const int tx = rem - by * p.tiles_x;
+
+    const int tr = lane / TW, tcx = lane % TW;
+    const int tile_col = tx * TW + tcx;
+    const bool valid = tile_col < p.Bx * R;
+    const bool leader = valid && tr == 0 && (tcx % R) == 0;
+    const int bxi = tile_col / R;
+    const int64_t tile_off = (int64_t)(by * R + tr) * 8 * p.row_stride + (int64_t)tile_col * 8;
+
+    const int t0 = chunk * p.chunk_len;
+    const int t1 = min(p.T, t0 + p.chunk_len);
+    const bool has_prev = (t0 > 0) || (p.halo != nullptr);
+    const int t_start = has_prev ? t0 - 1 : t0;
+
+    auto frame_ptr = [&](int t) -> const uint8_t* {
+        return (t < 0 ? p.halo : p.y + (int64_t)t * p.frame_stride) + tile_off;
+    };
+
+    float acc[8][8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int v = 0; v < 8; ++v) acc[u][v] = 0.f;
+
+    uint2 cur[8], prv[8], nxt[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) prv[r] = make_uint2(0u, 0u);
+    load_tile<ALIGNED>(cur, frame_ptr(t_start), p.row_stride, valid);
+
+    float smin = __int_as_float(0x7f800000), smax = 0.f, tmin = __int_as_float(0x7f800000), tmax = 0.f;
+
+    for (int t = t_start; t < t1; ++t) {
+        if (t + 1 < t1) load_tile<ALIGNED>(nxt, frame_ptr(t + 1), p.row_stride, valid);
+
+        float x[8][8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            x[r][0] = byte_as_biased_float<0>(cur[r].x) - byte_as_biased_float<0>(prv[r].x);
+            x[r][1] = byte_as_biased_float<1>(cur[r].x) - byte_as_biased_float<1>(prv[r].x);
+            x[r][2] = byte_as_biased_float<2>(cur[r].x) - byte_as_biased_float<2>(prv[r].x);
+            x[r][3] = byte_as_biased_float<3>(cur[r].x) - byte_as_biased_float<3>(prv[r].x);
+            x[r][4] = byte_as_biased_float<0>(cur[r].y) - byte_as_biased_float<0>(prv[r].y);
+            x[r][5] = byte_as_biased_float<1>(cur[r].y) - byte_as_biased_float<1>(prv[r].y);
+            x[r][6] = byte_as_biased_float<2>(cur[r].y) - byte_as_biased_float<2>(prv[r].y);
+            x[r][7] = byte_as_biased_float<3>(cur[r].y) - byte_as_biased_float<3>(prv[r].y);
+        }
+        fdct8x8(x);   // x[u][v]: u = vertical frequency, v = horizontal frequency (AAN-scaled)
+
+        // per-row partial sums keep 16 independent FMA chains in flight; fixed order => deterministic
+        float s_part[8], d_part[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            float s = 0.f, d = 0.f;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                if (u == 0 && v == 0) continue;   // DC carries no texture energy
+                acc[u][v] += x[u][v];
+                s = fmaf(fabsf(acc[u][v]), kW[u][v], s);
+                d = fmaf(fabsf(x[u][v]), kW[u][v], d);
+            }
+            s_part[u] = s;
+            d_part[u] = d;
+        }
+        float s = ((s_part[0] + s_part[1]) + (s_part[2] + s_part[3])) + ((s_part[4] + s_part[5]) + (s_part[6] + s_part[7]));
+        float d = ((d_part[0] + d_part[1]) + (d_part[2] + d_part[3])) + ((d_part[4] + d_part[5]) + (d_part[6] + d_part[7]));
+
+        // sum the block's R x R tiles
+#pragma unroll
+        for (int m = 1; m < R; m <<= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, m);
+            d += __shfl_xor_sync(0xffffffffu, d, m);
+        }
+#pragma unroll
+        for (int m = TW; m < 32; m <<= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, m);
+            d += __shfl_xor_sync(0xffffffffu, d, m);
+        }
+
+        if (t >= t0 && leader) {
+            const float scv = s * p.inv_area;
+            const float tcv = (t == 0 && p.halo == nullptr) ? 0.f : d * p.inv_area;
+            const int64_t o = ((int64_t)t * p.By + by) * p.Bx + bxi;
+            p.sc[o] = scv;
+            p.tc[o] = tcv;
+            if (t >= p.mm_begin && t < p.mm_end) {
+                smin = fminf(smin, scv);
+                smax = fmaxf(smax, scv);
+                tmin = fminf(tmin, tcv);
+                tmax = fmaxf(tmax, tcv);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            prv[r] = cur[r];
+            cur[r] = nxt[r];
+        }
+    }
+
+    if (p.mm != nullptr) {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, m));
+            smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, m));
+            tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, m));
+            tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, m));
+        }
+        if (lane == 0) {
+            // non-negative floats order like their bit patterns
+            atomicMin(p.mm + 0, __float_as_uint(smin));
+            atomicMax(p.mm + 1, __float_as_uint(smax));
+            atomicMin(p.mm + 2, __float_as_uint(tmin));
+            atomicMax(p.mm + 3, __float_as_uint(tmax));
+        }
+    }
+}
+
+__global__ void score_minmax_init(unsigned* mm) {
+    if (threadIdx.x < 4) mm[threadIdx.x] = (threadIdx.x & 1) ? 0u : 0x7f800000u;
+}
+
+template <int R>
+int launch_score(const ScoreParams& p, bool aligned, cudaStream_t st) {
+    const int units = p.By * p.tiles_x * p.n_chunks;
+    const int grid = (units + (kScoreThreads / 32) - 1) / (kScoreThreads / 32);
+    if (aligned)
+        score_kernel<R, true><<<grid, kScoreThreads, 0, st>>>(p);
+    else
+        score_kernel<R, false><<<grid, kScoreThreads, 0, st>>>(p);
+    ELVIS_CHECK_LAUNCH();
+    return ELVIS_OK;
+}
+
+}  // namespace
+
+// chunking heuristic: enough (tile-group x chunk) units for >= 16 waves of resident warps, but
+// chunks no shorter than 16 frames (each chunk pays one extra priming transform).
+static int pick_chunks(int T, int tile_groups, int override_len) {
+    if (override_len > 0) return (T + override_len - 1) / override_len;
+    const int resident_warps = kNumSMs * 2 * (kScoreThreads / 32);
+    const long target = 16L * resident_warps;
+    long n = (target + tile_groups - 1) / tile_groups;
+    const long max_chunks = (T + 15) / 16;
+    if (n > max_chunks) n = max_chunks;
+    if (n < 1) n = 1;
+    return (int)n;
+}
+
+}  // namespace elvis
+
+extern "C" int elvis_score_sc_tc(const elvis_plane* y, int32_t n_frames, const uint8_t* prev_halo,
+                                 int32_t block_size, int32_t dct_size, float* sc, float* tc,
+                                 float* minmax, int32_t mm_begin, int32_t mm_end, elvis_stream_t stream) {
+    using namespace elvis;
+    if (!plane_ok(y) || !sc || !tc || n_frames <= 0) return ELVIS_ERR_INVALID_ARG;
+    if (y->channels != 1) return ELVIS_ERR_UNSUPPORTED;
+    if (dct_size != 8) return ELVIS_ERR_UNSUPPORTED;
+    if (block_size != 8 && block_size != 16 && block_size != 32) return ELVIS_ERR_UNSUPPORTED;
+    const int By = y->height / block_size, Bx = y->width / block_size;
+    if (By <= 0 || Bx <= 0) return ELVIS_ERR_SHAPE;
+    const int R = block_size / 8;
+    const int TW = 32 / R;
+
+    ScoreParams p;
+    p.y = static_cast<const uint8_t*>(y->data);
+    p.halo = prev_halo;
+    p.frame_stride = y->frame_stride;
+    p.row_stride = y->row_stride;
+    p.T = n_frames;
+    p.By = By;
+    p.Bx = Bx;
+    p.tiles_x = (Bx * R + TW - 1) / TW;
+    int override_len = 0;
+    if (const char* e = getenv("ELVIS_SCORE_CHUNK")) override_len = atoi(e);
+    p.n_chunks = pick_chunks(n_frames, By * p.tiles_x, override_len);
+    p.chunk_len = (n_frames + p.n_chunks - 1) / p.n_chunks;
+    p.n_chunks = (n_frames + p.chunk_len - 1) / p.chunk_len;
+    p.sc = sc;
+    p.tc = tc;
+    p.mm = reinterpret_cast<unsigned*>(minmax);
+    p.mm_begin = mm_begin;
+    p.mm_end = mm_end;
+    p.inv_area = 1.0f / (float)(block_size * block_size);
+
+    cudaStream_t st = as_stream(stream);
+    if (minmax) {
+        score_minmax_init<<<1, 32, 0, st>>>(p.mm);
+        ELVIS_CHECK_LAUNCH();
+    }
+    const bool aligned = aligned_to(p.y, 8) && p.frame_stride % 8 == 0 && p.row_stride % 8 == 0 &&
+                         (prev_halo == nullptr || aligned_to(prev_halo, 8));
+    switch (R) {
+        case 1: return launch_score<1>(p, aligned, st);
+        case 2: return launch_score<2>(p, aligned, st);
+        default: return launch_score<4>(p, aligned, st);
+    }
+}

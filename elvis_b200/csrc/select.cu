@@ -1,0 +1,176 @@
+// a4 / a6: per block-row top-k removal mask, and a13: side-channel bit packers.
+//
+// One CTA sorts one (frame, block-row) of scores: a shared-memory bitonic network over
+// (order-preserving 64-bit key, column) pairs.  The comparator is the strict total order
+// "key, then column", which realises the tie rule of the oracle (lowest column first ==
+// np.argmin's rule, utils.py:721, and the stable reading of np.argsort(-row),
+// elvis.py:1401).  The first k entries of the sorted row are the removed blocks.
+#include "common.cuh"
+
+namespace elvis {
+namespace {
+
+// IEEE double -> uint64 whose unsigned order equals the float order (-0 == +0, NaN last)
+__device__ __forceinline__ unsigned long long sortable_key(double v) {
+    v = __dadd_rn(v, 0.0);   // -0.0 -> +0.0 so that signed zeros tie like they compare
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+
+constexpr int select_threads(int n) { return n / 2 > 512 ? 512 : (n / 2 < 32 ? 32 : n / 2); }
+
+template <int N>   // N = padded row length (power of two)
+__global__ void __launch_bounds__(select_threads(N)) select_rows_kernel(
+        const double* __restrict__ scores, int by, int bx, const int32_t* __restrict__ k_per_row, int k_uniform,
+        int polarity, uint8_t* __restrict__ mask) {
+    __shared__ unsigned long long s_key[N];
+    __shared__ uint16_t s_col[N];
+    const int64_t row = blockIdx.x;
+    const int k = k_per_row ? k_per_row[row % by] : k_uniform;
+    const double* src = scores + row * bx;
+    uint8_t* dst = mask + row * bx;
+    if (k <= 0 || k >= bx) {   // nothing or everything removed: no ranking needed
+        for (int i = threadIdx.x; i < bx; i += blockDim.x) dst[i] = k >= bx ? 1 : 0;
+        return;
+    }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        unsigned long long key = ~0ULL;
+        if (i < bx) {
+            const double v = src[i];
+            // NaN ranks last in either polarity (np.argsort's rule), but ahead of the padding
+            key = (v != v) ? ~0ULL - 1 : sortable_key(polarity == ELVIS_REMOVE_HIGH ? -v : v);
+        }
+        s_key[i] = key;
+        s_col[i] = (uint16_t)i;
+    }
+    __syncthreads();
+    for (int size = 2; size <= N; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < N / 2; t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool ascending = (lo & size) == 0;
+                const unsigned long long ka = s_key[lo], kb = s_key[hi];
+                const uint16_t ca = s_col[lo], cb = s_col[hi];
+                const bool a_after_b = ka > kb || (ka == kb && ca > cb);
+                if (a_after_b == ascending) {
+                    s_key[lo] = kb;
+                    s_key[hi] = ka;
+                    s_col[lo] = cb;
+                    s_col[hi] = ca;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const int c = s_col[i];
+        if (c < bx) dst[c] = i < k ? 1 : 0;
+    }
+}
+
+// np.packbits over a flat array: bit 7 of byte j is value 8j
+__global__ void __launch_bounds__(256) pack_bits_kernel(const uint8_t* __restrict__ m, int64_t n, uint8_t* __restrict__ out) {
+    const int64_t nbytes = (n + 7) / 8;
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < nbytes; j += (int64_t)gridDim.x * 256) {
+        unsigned b = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int64_t i = j * 8 + q;
+            if (i < n && m[i]) b |= 0x80u >> q;
+        }
+        out[j] = (uint8_t)b;
+    }
+}
+
+__global__ void __launch_bounds__(256) unpack_bits_kernel(const uint8_t* __restrict__ p, int64_t n, uint8_t* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+        out[i] = (p[i >> 3] >> (7 - (i & 7))) & 1;
+}
+
+__global__ void __launch_bounds__(256) pack2_kernel(const int32_t* __restrict__ lv, int64_t rows, int bx, uint8_t* __restrict__ out) {
+    const int pb = (bx + 3) / 4;
+    const int64_t total = rows * pb;
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < total; j += (int64_t)gridDim.x * 256) {
+        const int64_t r = j / pb;
+        const int c = (int)(j - r * pb) * 4;
+        unsigned b = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (c + q < bx) b |= ((unsigned)lv[r * bx + c + q] & 3u) << (2 * q);
+        out[j] = (uint8_t)b;
+    }
+}
+
+__global__ void __launch_bounds__(256) unpack2_kernel(const uint8_t* __restrict__ p, int64_t rows, int bx, int32_t* __restrict__ out) {
+    const int pb = (bx + 3) / 4;
+    const int64_t total = rows * bx;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int64_t r = i / bx;
+        const int c = (int)(i - r * bx);
+        out[i] = (p[r * pb + (c >> 2)] >> (2 * (c & 3))) & 3;
+    }
+}
+
+inline int grid_for(int64_t n) {
+    int64_t g = (n + 255) / 256;
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+template <int N>
+int launch_select(const double* scores, int64_t rows, int by, int bx, const int32_t* kpr, int ku, int pol, uint8_t* mask, cudaStream_t st) {
+    select_rows_kernel<N><<<(unsigned)rows, select_threads(N), 0, st>>>(scores, by, bx, kpr, ku, pol, mask);
+    ELVIS_CHECK_LAUNCH();
+    return ELVIS_OK;
+}
+
+}  // namespace
+}  // namespace elvis
+
+using namespace elvis;
+
+extern "C" int elvis_select_rows(const double* scores, int32_t n_frames, int32_t by, int32_t bx,
+                                 const int32_t* k_per_row, int32_t k_uniform, int32_t polarity,
+                                 uint8_t* mask, elvis_stream_t stream) {
+    if (!scores || !mask || n_frames <= 0 || by <= 0 || bx <= 0) return ELVIS_ERR_INVALID_ARG;
+    if (polarity != ELVIS_REMOVE_HIGH && polarity != ELVIS_REMOVE_LOW) return ELVIS_ERR_INVALID_ARG;
+    if (bx > 4096) return ELVIS_ERR_UNSUPPORTED;
+    const int64_t rows = (int64_t)n_frames * by;
+    cudaStream_t st = as_stream(stream);
+    if (bx <= 64) return launch_select<64>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+    if (bx <= 128) return launch_select<128>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+    if (bx <= 256) return launch_select<256>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+    if (bx <= 512) return launch_select<512>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+    if (bx <= 1024) return launch_select<1024>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+    if (bx <= 2048) return launch_select<2048>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+    return launch_select<4096>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+}
+
+extern "C" int elvis_pack_mask_bits(const uint8_t* mask, int64_t n, uint8_t* packed, elvis_stream_t stream) {
+    if (!mask || !packed || n <= 0) return ELVIS_ERR_INVALID_ARG;
+    pack_bits_kernel<<<grid_for((n + 7) / 8), 256, 0, as_stream(stream)>>>(mask, n, packed);
+    ELVIS_CHECK_LAUNCH();
+    return ELVIS_OK;
+}
+
+extern "C" int elvis_unpack_mask_bits(const uint8_t* packed, int64_t n, uint8_t* mask, elvis_stream_t stream) {
+    if (!mask || !packed || n <= 0) return ELVIS_ERR_INVALID_ARG;
+    unpack_bits_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(packed, n, mask);
+    ELVIS_CHECK_LAUNCH();
+    return ELVIS_OK;
+}
+
+extern "C" int elvis_pack_levels_2bit(const int32_t* levels, int64_t rows, int32_t bx, uint8_t* packed, elvis_stream_t stream) {
+    if (!levels || !packed || rows <= 0 || bx <= 0) return ELVIS_ERR_INVALID_ARG;
+    pack2_kernel<<<grid_for(rows * ((bx + 3) / 4)), 256, 0, as_stream(stream)>>>(levels, rows, bx, packed);
+    ELVIS_CHECK_LAUNCH();
+    return ELVIS_OK;
+}
+
+extern "C" int elvis_unpack_levels_2bit(const uint8_t* packed, int64_t rows, int32_t bx, int32_t* levels, elvis_stream_t stream) {
+    if (!levels || !packed || rows <= 0 || bx <= 0) return ELVIS_ERR_INVALID_ARG;
+    unpack2_kernel<<<grid_for(rows * bx), 256, 0, as_stream(stream)>>>(packed, rows, bx, levels);
+    ELVIS_CHECK_LAUNCH();
+    return ELVIS_OK;
+}

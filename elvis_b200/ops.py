@@ -1,0 +1,324 @@
+"""Device-level operators: CUDA uint8/float tensors in, CUDA tensors out, one C-ABI call
+each, enqueued on torch's current stream.  torch is used for memory and streams only.
+
+Clip layouts
+  planar plane : (T, H, W) uint8           -- Y, U or V of a YUV clip
+  packed clip  : (T, H, W, C) uint8        -- the reference's BGR/RGB frames (C = 3)
+  block maps   : (T, By, Bx)               -- scores float64, masks uint8, levels int32
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, _tables
+from ._lib import (F32, F64, LEVELS_INVERTED_BINS, LEVELS_INVERTED_ROUND, LEVELS_ROUND, REMOVE_HIGH,
+                   REMOVE_LOW, Plane, call)
+
+__all__ = ["score_sc_tc", "minmax", "combine_removability", "normalize_", "importance_scores", "select_rows",
+           "shrink", "stretch", "levels_from_scores", "degrade_blur", "degrade_downsample", "dct_dampen",
+           "pack_mask_bits", "unpack_mask_bits", "pack_levels_2bit", "unpack_levels_2bit",
+           "REMOVE_HIGH", "REMOVE_LOW", "LEVELS_ROUND", "LEVELS_INVERTED_ROUND", "LEVELS_INVERTED_BINS"]
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: torch.Tensor | None) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _check_cuda(t: torch.Tensor, dtype, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor (elvis_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def plane_of(clip: torch.Tensor, name: str = "clip") -> Plane:
+    """struct elvis_plane of a (T, H, W) or (T, H, W, C) uint8 CUDA tensor; rows may be
+    strided (a cropped view), pixels of a row must be dense."""
+    _check_cuda(clip, torch.uint8, name)
+    if clip.dim() == 3:
+        ch, (sf, sr, sx) = 1, clip.stride()
+        ok = sx == 1 or clip.shape[2] == 1
+    elif clip.dim() == 4:
+        ch = clip.shape[3]
+        sf, sr, sx, sc = clip.stride()
+        ok = (sc == 1 or ch == 1) and (sx == ch or clip.shape[2] == 1)
+    else:
+        raise ValueError(f"{name} must be (T, H, W) or (T, H, W, C)")
+    if not ok:
+        raise ValueError(f"{name}: pixels of a row must be contiguous")
+    return Plane(clip.data_ptr(), sf, sr, clip.shape[1], clip.shape[2], ch, 0)
+
+
+def _float_dtype(t: torch.Tensor, name: str) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float64:
+        return F64
+    raise TypeError(f"{name} must be float32 or float64")
+
+
+# ------------------------------------------------------------------------------ a1
+def score_sc_tc(y: torch.Tensor, block_size: int, prev_halo: torch.Tensor | None = None, dct_size: int = 8,
+                minmax_range: tuple | None = None):
+    """SC/TC of a (T, H, W) luma clip -> (sc, tc, minmax): float32 (T, By, Bx) each and a
+    float32[4] {sc_min, sc_max, tc_min, tc_max} over frames minmax_range (default: all)."""
+    pl = plane_of(y, "y")
+    if y.dim() != 3:
+        raise ValueError("y must be (T, H, W)")
+    T, H, W = y.shape
+    by, bx = H // block_size, W // block_size
+    if prev_halo is not None:
+        _check_cuda(prev_halo, torch.uint8, "prev_halo")
+        if prev_halo.shape != y.shape[1:] or prev_halo.stride() != y.stride()[1:]:
+            prev_halo = _match_halo(prev_halo, y)
+    sc = torch.empty((T, by, bx), dtype=torch.float32, device=y.device)
+    tc = torch.empty_like(sc)
+    mm = torch.empty(4, dtype=torch.float32, device=y.device)
+    lo, hi = (0, T) if minmax_range is None else minmax_range
+    call("elvis_score_sc_tc", C.byref(pl), T, _ptr(prev_halo), block_size, dct_size, _ptr(sc), _ptr(tc), _ptr(mm),
+         lo, hi, _stream())
+    return sc, tc, mm
+
+
+def _match_halo(halo: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    if halo.shape != y.shape[1:]:
+        raise ValueError("prev_halo must have the shape of one luma frame")
+    buf = torch.empty_strided(y.shape[1:], y.stride()[1:], dtype=torch.uint8, device=y.device)
+    buf.copy_(halo)
+    return buf
+
+
+def minmax(x: torch.Tensor) -> torch.Tensor:
+    if not x.is_contiguous():
+        raise ValueError("minmax needs a contiguous tensor")
+    out = torch.empty(2, dtype=torch.float64, device=x.device)
+    call("elvis_minmax", _ptr(x), _float_dtype(x, "x"), x.numel(), _ptr(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------ a2
+def combine_removability(sc: torch.Tensor, tc: torch.Tensor, norm: torch.Tensor, alpha: float, beta: float,
+                         background: torch.Tensor | None = None, t_begin: int = 0, t_count: int | None = None,
+                         is_first: bool = True, is_last: bool = True, clip_frames: int | None = None):
+    """Un-normalised smoothed removability of frames [t_begin, t_begin + t_count) plus its
+    {min, max} (float64[2]).  clip_frames = length of the whole clip (for the reference's
+    `shape[0] >= 2` smoothing condition); defaults to the local length."""
+    dt = _float_dtype(sc, "sc")
+    if tc.dtype != sc.dtype or norm.dtype != sc.dtype:
+        raise TypeError("sc, tc and norm must share a dtype")
+    if not (sc.is_contiguous() and tc.is_contiguous()) or sc.shape != tc.shape or sc.dim() != 3:
+        raise ValueError("sc and tc must be contiguous (T, By, Bx)")
+    t_ext, by, bx = sc.shape
+    t_count = t_ext - t_begin if t_count is None else t_count
+    clip_frames = t_ext if clip_frames is None else clip_frames
+    if background is not None:
+        _check_cuda(background, torch.uint8, "background")
+        if background.shape != sc.shape or not background.is_contiguous():
+            raise ValueError("background must be contiguous (T, By, Bx) uint8")
+    out = torch.empty((t_count, by, bx), dtype=torch.float64, device=sc.device)
+    mm = torch.empty(2, dtype=torch.float64, device=sc.device)
+    smooth = int(beta < 1 and clip_frames >= 2)
+    call("elvis_combine_removability", _ptr(sc), _ptr(tc), dt, _ptr(norm), t_ext, by, bx, t_begin, t_count,
+         int(is_first), int(is_last), _ptr(background), float(alpha), float(beta), smooth, _ptr(out), _ptr(mm), _stream())
+    return out, mm
+
+
+def normalize_(x: torch.Tensor, mm: torch.Tensor) -> torch.Tensor:
+    _check_cuda(x, torch.float64, "x")
+    _check_cuda(mm, torch.float64, "minmax")
+    if not x.is_contiguous():
+        raise ValueError("x must be contiguous")
+    call("elvis_normalize", _ptr(x), x.numel(), _ptr(mm), _stream())
+    return x
+
+
+# ------------------------------------------------------------------------------ a3
+def importance_scores(sc: torch.Tensor, tc: torch.Tensor, foreground: torch.Tensor | None, alpha: float, beta: float,
+                      t_begin: int = 0, t_count: int | None = None, is_first: bool = True, is_last: bool = True):
+    dt = _float_dtype(sc, "sc")
+    if tc.dtype != sc.dtype or (foreground is not None and foreground.dtype != sc.dtype):
+        raise TypeError("sc, tc and foreground must share a dtype")
+    if not (sc.is_contiguous() and tc.is_contiguous()) or sc.shape != tc.shape or sc.dim() != 3:
+        raise ValueError("sc and tc must be contiguous (T, By, Bx)")
+    if foreground is not None and (foreground.shape != sc.shape or not foreground.is_contiguous()):
+        raise ValueError("foreground must be contiguous (T, By, Bx)")
+    t_ext, by, bx = sc.shape
+    t_count = t_ext - t_begin if t_count is None else t_count
+    out = torch.empty((t_count, by, bx), dtype=torch.float64, device=sc.device)
+    call("elvis_importance_scores", _ptr(sc), _ptr(tc), _ptr(foreground), dt, t_ext, by, bx, t_begin, t_count,
+         int(is_first), int(is_last), float(alpha), float(beta), _ptr(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------ a4-a7
+def select_rows(scores: torch.Tensor, k, polarity: int = REMOVE_HIGH) -> torch.Tensor:
+    """(T, By, Bx) float64 -> uint8 mask, 1 = removed.  k: int, or int32 CUDA tensor (By,)."""
+    _check_cuda(scores, torch.float64, "scores")
+    if scores.dim() != 3 or not scores.is_contiguous():
+        raise ValueError("scores must be contiguous (T, By, Bx)")
+    T, by, bx = scores.shape
+    mask = torch.empty((T, by, bx), dtype=torch.uint8, device=scores.device)
+    if isinstance(k, torch.Tensor):
+        _check_cuda(k, torch.int32, "k")
+        if k.shape != (by,) or not k.is_contiguous():
+            raise ValueError("per-row k must be a contiguous (By,) tensor")
+        call("elvis_select_rows", _ptr(scores), T, by, bx, _ptr(k), 0, polarity, _ptr(mask), _stream())
+    else:
+        call("elvis_select_rows", _ptr(scores), T, by, bx, _ptr(None), int(k), polarity, _ptr(mask), _stream())
+    return mask
+
+
+def _mask_arg(mask: torch.Tensor) -> torch.Tensor:
+    _check_cuda(mask, torch.uint8, "mask")
+    if mask.dim() != 3 or not mask.is_contiguous():
+        raise ValueError("mask must be contiguous (T, By, Bx) uint8")
+    return mask
+
+
+def shrink(clip: torch.Tensor, mask: torch.Tensor, block_px: int, out_bx: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Left-compact the blocks with mask == 0.  clip: (T, H, W[, C]); returns
+    (T, By*block_px, out_bx*block_px[, C])."""
+    mask = _mask_arg(mask)
+    T, by, bx = mask.shape
+    if clip.shape[0] != T:
+        raise ValueError("clip and mask disagree on the frame count")
+    if clip.shape[1] % block_px or clip.shape[2] % block_px:
+        raise ValueError("Image dimensions must be divisible by block_size.")   # elvis.py:1376
+    shape = (T, by * block_px, out_bx * block_px) + tuple(clip.shape[3:])
+    if out is None:
+        out = torch.empty(shape, dtype=torch.uint8, device=clip.device)
+    elif tuple(out.shape) != shape:
+        raise ValueError(f"out must be {shape}")
+    if out_bx == 0 or out.numel() == 0:
+        return out
+    src, dst = plane_of(clip), plane_of(out, "out")
+    call("elvis_shrink", C.byref(src), C.byref(dst), T, block_px, by, bx, out_bx, _ptr(mask), _stream())
+    return out
+
+
+def stretch(shrunk: torch.Tensor, mask: torch.Tensor, block_px: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Inverse of shrink: (T, By*block_px, sbx*block_px[, C]) -> (T, By*block_px, Bx*block_px[, C])."""
+    mask = _mask_arg(mask)
+    T, by, bx = mask.shape
+    if shrunk.shape[0] != T:
+        raise ValueError("clip and mask disagree on the frame count")
+    if shrunk.shape[1] % block_px or shrunk.shape[2] % block_px:
+        raise ValueError("Image dimensions must be divisible by block_size.")
+    sbx = shrunk.shape[2] // block_px
+    shape = (T, by * block_px, bx * block_px) + tuple(shrunk.shape[3:])
+    if out is None:
+        out = torch.empty(shape, dtype=torch.uint8, device=shrunk.device)
+    elif tuple(out.shape) != shape:
+        raise ValueError(f"out must be {shape}")
+    if sbx == 0:   # every block was removed: the canvas stays black
+        return out.zero_()
+    src, dst = plane_of(shrunk), plane_of(out, "out")
+    call("elvis_stretch", C.byref(src), C.byref(dst), T, block_px, by, bx, sbx, _ptr(mask), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------ a8-a12, a14
+def levels_from_scores(scores: torch.Tensor, rule: int, param: int) -> torch.Tensor:
+    _check_cuda(scores, torch.float64, "scores")
+    if not scores.is_contiguous():
+        raise ValueError("scores must be contiguous")
+    out = torch.empty(scores.shape, dtype=torch.int32, device=scores.device)
+    call("elvis_levels_from_scores", _ptr(scores), scores.numel(), rule, int(param), _ptr(out), _stream())
+    return out
+
+
+def _degrade_args(clip: torch.Tensor, block_map: torch.Tensor, block_px: int, dtype, out):
+    _check_cuda(block_map, dtype, "block map")
+    if block_map.dim() != 3 or not block_map.is_contiguous() or block_map.shape[0] != clip.shape[0]:
+        raise ValueError("block map must be contiguous (T, By, Bx)")
+    T, by, bx = block_map.shape
+    if by != clip.shape[1] // block_px or bx != clip.shape[2] // block_px:
+        raise ValueError("block map does not match the clip's block grid")
+    if out is None:
+        out = torch.empty_like(clip, memory_format=torch.contiguous_format)
+    return T, by, bx, out
+
+
+def degrade_blur(clip: torch.Tensor, rounds: torch.Tensor, block_px: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    T, by, bx, out = _degrade_args(clip, rounds, block_px, torch.int32, out)
+    src, dst = plane_of(clip), plane_of(out, "out")
+    call("elvis_degrade_blur", C.byref(src), C.byref(dst), T, block_px, by, bx, _ptr(rounds), _stream())
+    return out
+
+
+_table_cache: dict = {}
+
+
+def _device_tables(block_px: int, small_sizes: tuple, device) -> torch.Tensor:
+    key = (block_px, small_sizes, str(device))
+    t = _table_cache.get(key)
+    if t is None:
+        t = torch.from_numpy(_tables.build(block_px, small_sizes).copy()).to(device)
+        _table_cache[key] = t
+    return t
+
+
+def degrade_downsample(clip: torch.Tensor, levels: torch.Tensor, block_px: int, small_sizes,
+                       out: torch.Tensor | None = None) -> torch.Tensor:
+    """small_sizes[level] = side the block is reduced to before being scaled back."""
+    T, by, bx, out = _degrade_args(clip, levels, block_px, torch.int32, out)
+    small_sizes = tuple(int(s) for s in small_sizes)
+    tab = _device_tables(block_px, small_sizes, clip.device)
+    src, dst = plane_of(clip), plane_of(out, "out")
+    call("elvis_degrade_downsample", C.byref(src), C.byref(dst), T, block_px, by, bx, _ptr(levels), _ptr(tab),
+         len(small_sizes), _stream())
+    return out
+
+
+def dct_dampen(clip: torch.Tensor, strength: torch.Tensor, block_px: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    T, by, bx, out = _degrade_args(clip, strength, block_px, torch.float32, out)
+    src, dst = plane_of(clip), plane_of(out, "out")
+    call("elvis_dct_dampen", C.byref(src), C.byref(dst), T, block_px, by, bx, _ptr(strength), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------ a13
+def pack_mask_bits(mask: torch.Tensor) -> torch.Tensor:
+    _check_cuda(mask, torch.uint8, "mask")
+    m = mask.contiguous()
+    out = torch.empty((m.numel() + 7) // 8, dtype=torch.uint8, device=m.device)
+    call("elvis_pack_mask_bits", _ptr(m), m.numel(), _ptr(out), _stream())
+    return out
+
+
+def unpack_mask_bits(packed: torch.Tensor, shape) -> torch.Tensor:
+    _check_cuda(packed, torch.uint8, "packed")
+    n = int(np.prod(shape))
+    if packed.numel() * 8 < n:
+        raise ValueError("packed buffer too small")
+    out = torch.empty(tuple(shape), dtype=torch.uint8, device=packed.device)
+    call("elvis_unpack_mask_bits", _ptr(packed.contiguous()), n, _ptr(out), _stream())
+    return out
+
+
+def pack_levels_2bit(levels: torch.Tensor) -> torch.Tensor:
+    _check_cuda(levels, torch.int32, "levels")
+    lv = levels.contiguous()
+    bx = lv.shape[-1]
+    rows = lv.numel() // bx
+    out = torch.empty(tuple(lv.shape[:-1]) + ((bx + 3) // 4,), dtype=torch.uint8, device=lv.device)
+    call("elvis_pack_levels_2bit", _ptr(lv), rows, bx, _ptr(out), _stream())
+    return out
+
+
+def unpack_levels_2bit(packed: torch.Tensor, bx: int) -> torch.Tensor:
+    _check_cuda(packed, torch.uint8, "packed")
+    p = packed.contiguous()
+    if p.shape[-1] != (bx + 3) // 4:
+        raise ValueError("packed rows must hold ceil(bx/4) bytes")
+    rows = p.numel() // p.shape[-1]
+    out = torch.empty(tuple(p.shape[:-1]) + (bx,), dtype=torch.int32, device=p.device)
+    call("elvis_unpack_levels_2bit", _ptr(p), rows, bx, _ptr(out), _stream())
+    return out

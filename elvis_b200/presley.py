@@ -1,0 +1,135 @@
+"""Drop-in mirrors of the hot-path functions of the reference's `presley.py`: the batch
+shrink/stretch wrappers (presley.py:761-827), the generic adaptive degradation
+(presley.py:968-1039) and an `analyze_frames` stand-in for the external EVCA call
+(presley.py:202).  The batch functions move the whole clip to the GPU once."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Callable, List, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from . import utils as _utils
+from .elvis import _to_dev
+
+
+# ------------------------------------------------------------------ EVCA stand-in
+@dataclass
+class EVCAConfig:
+    block_size: int = 16
+    dct_size: int = 8
+
+
+@dataclass
+class Complexities:
+    SC: np.ndarray
+    TC: np.ndarray
+
+
+def rgb_to_luma(frames: torch.Tensor) -> torch.Tensor:
+    """(T, H, W, 3) uint8 RGB -> (T, H, W) uint8 BT.601 luma, cv2.COLOR_RGB2GRAY's fixed-point
+    rule (R*4899 + G*9617 + B*1868 + 8192) >> 14."""
+    f = frames.to(torch.int32)
+    y = (f[..., 0] * 4899 + f[..., 1] * 9617 + f[..., 2] * 1868 + 8192) >> 14
+    return y.to(torch.uint8)
+
+
+def analyze_frames(frames: np.ndarray, config: EVCAConfig) -> Complexities:
+    """Stand-in for `evca.analyze_frames(np.array(frames), EVCAConfig(block_size=bs))`
+    (presley.py:202): per-block SC/TC of the clip's luma, float64 (T, By, Bx)."""
+    f = _to_dev(np.asarray(frames), np.uint8)
+    y = f if f.dim() == 3 else rgb_to_luma(f)
+    sc, tc, _ = ops.score_sc_tc(y.contiguous(), config.block_size, dct_size=config.dct_size)
+    return Complexities(sc.double().cpu().numpy(), tc.double().cpu().numpy())
+
+
+calculate_importance_scores = _utils.calculate_importance_scores   # presley.py:129-152 == utils.py:665-688
+shrink_frame_row_only = _utils.shrink_frame_row_only               # presley.py:713-757 == utils.py:692-736
+
+
+# ------------------------------------------------------------------ batch shrink / stretch
+def shrink_video_frames(frames: List[np.ndarray], importance_scores: List[np.ndarray], block_size: int,
+                        shrink_amount: float, method: Callable = shrink_frame_row_only) -> Tuple[List[np.ndarray], List[Any]]:
+    """presley.py:761-784.  With the row-only method the whole clip is processed in one
+    batch on the GPU; any other callable is applied frame by frame like the reference."""
+    if method is not shrink_frame_row_only or len(frames) == 0:
+        out = [method(f, s, block_size, shrink_amount) for f, s in zip(frames, importance_scores)]
+        return [o[0] for o in out], [o[1] for o in out]
+    clip = _to_dev(np.stack(frames), np.uint8)
+    h, w = clip.shape[1:3]
+    by, bx = h // block_size, w // block_size
+    k, out_bx = _utils.row_only_plan(by, bx, shrink_amount)
+    scores = _to_dev(np.stack([np.asarray(s, np.float64)[:by, :bx] for s in importance_scores]))
+    mask = ops.select_rows(scores, _to_dev(k), ops.REMOVE_LOW)
+    shrunk = ops.shrink(clip[:, :by * block_size, :bx * block_size], mask, block_size, out_bx).cpu().numpy()
+    mask_h = mask.cpu().numpy().astype(bool)
+    return [shrunk[i] for i in range(len(frames))], [mask_h[i] for i in range(len(frames))]
+
+
+def stretch_video_frames(shrunken_frames: List[np.ndarray], removal_masks: List[np.ndarray], block_size: int) -> List[np.ndarray]:
+    """presley.py:787-827 (row-major refill == per-row refill because every row of a
+    row-only shrink keeps the same number of blocks)."""
+    if len(shrunken_frames) == 0:
+        return []
+    masks = _to_dev(np.stack([np.asarray(m) != 0 for m in removal_masks]), np.uint8)
+    clip = _to_dev(np.stack(shrunken_frames), np.uint8)
+    sby, sbx = clip.shape[1] // block_size, clip.shape[2] // block_size
+    if sbx == 0:
+        by, bx = masks.shape[1:]
+        z = np.zeros((by * block_size, bx * block_size) + tuple(clip.shape[3:]), np.uint8)
+        return [z.copy() for _ in shrunken_frames]
+    out = ops.stretch(clip[:, :sby * block_size, :sbx * block_size], masks, block_size).cpu().numpy()
+    return [out[i] for i in range(len(shrunken_frames))]
+
+
+# ------------------------------------------------------------------ adaptive degradation
+def generate_degradation_map(importance: np.ndarray, max_value: int) -> np.ndarray:
+    """presley.py:968-975."""
+    imp = _to_dev(np.asarray(importance), np.float64)
+    return ops.levels_from_scores(imp, ops.LEVELS_INVERTED_ROUND, max_value).cpu().numpy()
+
+
+def downscale_block(block: np.ndarray, scale: int) -> np.ndarray:
+    """presley.py:978-983 (one block = a one-block frame)."""
+    bs = block.shape[0]
+    lv = torch.ones((1, 1, 1), dtype=torch.int32, device="cuda")
+    out = ops.degrade_downsample(_to_dev(block)[None], lv, bs, [bs, max(1, bs // int(scale))])
+    return out[0].cpu().numpy()
+
+
+def blur_block(block: np.ndarray, rounds: int) -> np.ndarray:
+    """presley.py:986-990."""
+    bs = block.shape[0]
+    r = torch.full((1, 1, 1), int(rounds), dtype=torch.int32, device="cuda")
+    return ops.degrade_blur(_to_dev(block)[None], r, bs)[0].cpu().numpy()
+
+
+def _degrade_clip(clip: torch.Tensor, levels: torch.Tensor, block_size: int, method: Callable) -> torch.Tensor:
+    if method is downscale_block:
+        top = max(1, int(levels.max().item()))
+        smalls = [block_size] + [max(1, block_size // s) for s in range(1, top + 1)]
+        return ops.degrade_downsample(clip, levels, block_size, smalls)
+    if method is blur_block:
+        return ops.degrade_blur(clip, levels, block_size)
+    raise TypeError("method must be elvis_b200.presley.downscale_block or blur_block")
+
+
+def degrade_frame(frame: np.ndarray, degradation_map: np.ndarray, block_size: int, method: Callable) -> np.ndarray:
+    """presley.py:993-1013."""
+    lv = _to_dev(np.asarray(degradation_map), np.int32)[None]
+    return _degrade_clip(_to_dev(frame)[None], lv, block_size, method)[0].cpu().numpy()
+
+
+def degrade_video_adaptive(frames: List[np.ndarray], importance_scores: List[np.ndarray], block_size: int,
+                           max_value: int, method: Callable) -> Tuple[List[np.ndarray], List[np.ndarray]]:
+    """presley.py:1016-1039, the whole clip in one batch."""
+    if len(frames) == 0:
+        return [], []
+    clip = _to_dev(np.stack(frames), np.uint8)
+    imp = _to_dev(np.stack(importance_scores), np.float64)
+    levels = ops.levels_from_scores(imp, ops.LEVELS_INVERTED_ROUND, max_value)
+    out = _degrade_clip(clip, levels, block_size, method).cpu().numpy()
+    lv = levels.cpu().numpy()
+    return [out[i] for i in range(len(frames))], [lv[i] for i in range(len(frames))]

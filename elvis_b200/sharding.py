@@ -1,0 +1,119 @@
+"""Frame sharding across the GPUs of one box.
+
+Frames are independent for shrink / stretch / degrade; scoring couples frame t with t-1
+(TC) and t+1 (the blend uses TC[t+1], elvis.py:1180) and smoothing couples t with t-1
+(elvis.py:1210-1213).  Each rank therefore owns a contiguous frame range (the split of the
+reference's chunk_for_devices, elvis.py:264-278) and needs ONE luma frame of halo on each
+side, exchanged with torch.distributed send/recv (NCCL over NVLink on the GPU box, gloo in
+the CPU tests).  The elvis-mode global normalisations need two tiny all-reduces
+({sc,tc} min/max and the final min/max); the utils per-frame mode needs none.
+
+Everything here is device-agnostic plumbing; the arithmetic is injected (`kernels`), which is
+elvis_b200.ops in production and an oracle-backed stand-in in tests/test_sharding_gloo.py.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def frame_range(n_frames: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous split: base = T // G frames each, the first T % G ranks get one extra."""
+    base, extra = divmod(n_frames, world)
+    a = rank * base + min(rank, extra)
+    return a, a + base + (1 if rank < extra else 0)
+
+
+class HaloClip:
+    """A rank's luma frames with one halo slot on each side, so that received halos land in
+    place and the scoring kernel sees one contiguous extended clip (no concatenation copy).
+
+        buf[0]            Y[a-1]   (valid iff rank > 0)
+        buf[1 : n+1]      Y[a:b]   (owned)
+        buf[n+1]          Y[b]     (valid iff rank < world-1)
+    """
+
+    def __init__(self, n_local: int, height: int, width: int, device, pin: bool = False):
+        self.n = n_local
+        self.buf = torch.empty((n_local + 2, height, width), dtype=torch.uint8, device=device)
+
+    @property
+    def owned(self) -> torch.Tensor:
+        return self.buf[1:self.n + 1]
+
+    def extended(self, rank: int, world: int) -> Tuple[torch.Tensor, int]:
+        """(frames the kernels should see, index of the first owned frame inside them)."""
+        lo = 0 if rank > 0 else 1
+        hi = self.n + 2 if rank < world - 1 else self.n + 1
+        return self.buf[lo:hi], 1 - lo
+
+
+def exchange_halo(clip: HaloClip, rank: int, world: int, group=None) -> None:
+    """Send my first/last owned frame to the previous/next rank and receive theirs into the
+    halo slots.  One batched isend/irecv group => a single NCCL group call."""
+    if world == 1 or clip.n == 0:
+        return
+    ops = []
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, clip.buf[1], rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, clip.buf[0], rank - 1, group))
+    if rank < world - 1:
+        ops.append(dist.P2POp(dist.isend, clip.buf[clip.n], rank + 1, group))
+        ops.append(dist.P2POp(dist.irecv, clip.buf[clip.n + 1], rank + 1, group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+
+
+def allreduce_minmax(mm: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """In-place exact all-reduce of interleaved {min, max, min, max, ...}: one MAX reduction
+    of {-min, max, ...}."""
+    if world == 1:
+        return mm
+    sign = torch.ones_like(mm)
+    sign[0::2] = -1
+    v = mm * sign
+    dist.all_reduce(v, op=dist.ReduceOp.MAX, group=group)
+    mm.copy_(v * sign)
+    return mm
+
+
+def sharded_removability(clip: HaloClip, n_frames_total: int, block_size: int, alpha: float, beta: float,
+                         rank: int, world: int, background: Optional[torch.Tensor] = None, kernels=None,
+                         group=None) -> torch.Tensor:
+    """elvis-mode removability (elvis.py:1160-1220) of the owned frames -> (n, By, Bx) float64.
+    background: optional uint8 (n+2, By, Bx) laid out like clip.buf (halo slots filled by the
+    caller when it has the neighbours' masks; only slot 0 is ever read)."""
+    if kernels is None:
+        from . import ops as kernels
+    exchange_halo(clip, rank, world, group)
+    ext, first = clip.extended(rank, world)
+    sc, tc, norm = kernels.score_sc_tc(ext, block_size, minmax_range=(first, first + clip.n))
+    allreduce_minmax(norm, world, group)
+    bg = None
+    if background is not None:
+        lo = 1 - first
+        bg = background[lo:lo + ext.shape[0]].contiguous()
+    r, mm = kernels.combine_removability(sc, tc, norm, alpha, beta, bg, t_begin=first, t_count=clip.n,
+                                         is_first=(rank == 0), is_last=(rank == world - 1),
+                                         clip_frames=n_frames_total)
+    allreduce_minmax(mm, world, group)
+    return kernels.normalize_(r, mm)
+
+
+def sharded_importance(clip: HaloClip, block_size: int, alpha: float, beta: float, rank: int, world: int,
+                       foreground: Optional[torch.Tensor] = None, kernels=None, group=None) -> torch.Tensor:
+    """utils-mode importance (utils.py:665-688) of the owned frames: per-frame normalisation,
+    so the halo exchange is the only communication."""
+    if kernels is None:
+        from . import ops as kernels
+    exchange_halo(clip, rank, world, group)
+    ext, first = clip.extended(rank, world)
+    sc, tc, _ = kernels.score_sc_tc(ext, block_size)
+    fg = None
+    if foreground is not None:
+        lo = 1 - first
+        fg = foreground[lo:lo + ext.shape[0]].to(sc.dtype).contiguous()
+    return kernels.importance_scores(sc, tc, fg, alpha, beta, t_begin=first, t_count=clip.n,
+                                     is_first=(rank == 0), is_last=(rank == world - 1))

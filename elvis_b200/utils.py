@@ -1,0 +1,93 @@
+"""Drop-in mirrors of the hot-path functions of the reference's `utils.py` (PRESLEY-era
+API): importance scoring, row-only shrink/stretch and the adaptive degradations.  Same
+signatures and return values as the reference; the work runs on the sm_100a kernels."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from .elvis import _packed_clip, _to_dev
+
+
+def calculate_importance_scores(frames, block_size: int, alpha: float, beta: float, complexities,
+                                foreground_masks: np.ndarray) -> List[np.ndarray]:
+    """utils.py:665-688.  complexities: object with .SC/.TC (T, By, Bx) -- EVCA's result or
+    elvis_b200.presley.analyze_frames'.  `frames` and `block_size` are unused, as in the
+    reference."""
+    sc = _to_dev(np.asarray(complexities.SC), np.float64)
+    tc = _to_dev(np.asarray(complexities.TC), np.float64)
+    fg = _to_dev(np.asarray(foreground_masks), np.float64)
+    imp = ops.importance_scores(sc, tc, fg, alpha, beta).cpu().numpy()
+    return [imp[i] for i in range(len(imp))]
+
+
+def row_only_plan(blocks_y: int, blocks_x: int, shrink_amount: float):
+    """Pass structure of utils.py:711-735 -> (k per block row (By,) int32, output width in
+    blocks).  A pass removes one block from every row in row order until
+    int(By*Bx*shrink) are gone; the width drops once per pass, also after a partial one."""
+    target = int(blocks_y * blocks_x * shrink_amount)
+    passes = 0
+    k = np.zeros(blocks_y, np.int32)
+    removed = 0
+    while removed < target and blocks_x - passes > 1:
+        n = min(blocks_y, target - removed)
+        k[:n] += 1
+        removed += n
+        passes += 1
+    return k, blocks_x - passes
+
+
+def shrink_frame_row_only(frame: np.ndarray, importance: np.ndarray, block_size: int,
+                          shrink_amount: float) -> Tuple[np.ndarray, np.ndarray]:
+    """utils.py:692-736 -> (shrunken, removal_mask bool, True = removed)."""
+    h, w = frame.shape[:2]
+    by, bx = h // block_size, w // block_size
+    k, out_bx = row_only_plan(by, bx, shrink_amount)
+    scores = _to_dev(np.asarray(importance, np.float64)[:by, :bx])[None]
+    mask = ops.select_rows(scores, _to_dev(k), ops.REMOVE_LOW)
+    clip = _packed_clip(frame)[:, :by * block_size, :bx * block_size]      # utils.py:707 crop
+    shrunk = ops.shrink(clip, mask, block_size, out_bx)
+    return shrunk[0].cpu().numpy(), mask[0].cpu().numpy().astype(bool)
+
+
+def stretch_frame_row_only(shrunk_frame: np.ndarray, removal_mask: np.ndarray, block_size: int) -> np.ndarray:
+    """utils.py:739-759."""
+    mask = _to_dev(np.asarray(removal_mask) != 0, np.uint8)[None]
+    by, bx = mask.shape[1:]
+    sby, sbx = shrunk_frame.shape[0] // block_size, shrunk_frame.shape[1] // block_size
+    if sbx == 0:
+        return np.zeros((by * block_size, bx * block_size) + shrunk_frame.shape[2:], shrunk_frame.dtype)
+    clip = _packed_clip(shrunk_frame)[:, :sby * block_size, :sbx * block_size]
+    return ops.stretch(clip, mask, block_size)[0].cpu().numpy()
+
+
+def _block_importance(importance: np.ndarray, by: int, bx: int) -> np.ndarray:
+    importance = np.asarray(importance)
+    if importance.shape != (by, bx):   # utils.py:1127-1128 (host-side map resize, rarely taken)
+        import cv2
+        importance = cv2.resize(importance, (bx, by), interpolation=cv2.INTER_LINEAR)
+    return importance
+
+
+def degrade_adaptive_downsample(frame: np.ndarray, importance: np.ndarray, block_size: int,
+                                max_scale: int = 4) -> Tuple[np.ndarray, np.ndarray]:
+    """utils.py:1101-1168 -> (frame, degradation_map int32 with values {0, 2, ..., max_scale})."""
+    by, bx = frame.shape[0] // block_size, frame.shape[1] // block_size
+    imp = _to_dev(_block_importance(importance, by, bx), np.float64)[None]
+    levels = ops.levels_from_scores(imp, ops.LEVELS_INVERTED_BINS, max_scale)
+    smalls = [block_size, block_size] + [max(1, block_size // s) for s in range(2, max_scale + 1)]
+    out = ops.degrade_downsample(_packed_clip(frame), levels, block_size, smalls)
+    return out[0].cpu().numpy(), levels[0].cpu().numpy()
+
+
+def degrade_adaptive_blur(frame: np.ndarray, importance: np.ndarray, block_size: int,
+                          max_rounds: int = 10) -> Tuple[np.ndarray, np.ndarray]:
+    """utils.py:1171-1217."""
+    by, bx = frame.shape[0] // block_size, frame.shape[1] // block_size
+    imp = _to_dev(_block_importance(importance, by, bx), np.float64)[None]
+    rounds = ops.levels_from_scores(imp, ops.LEVELS_INVERTED_ROUND, max_rounds)
+    out = ops.degrade_blur(_packed_clip(frame), rounds, block_size)
+    return out[0].cpu().numpy(), rounds[0].cpu().numpy()

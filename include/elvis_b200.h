@@ -1,0 +1,184 @@
+/*
+ * elvis_b200 -- C ABI of the B200 (sm_100a) implementation of the ELVIS / PRESLEY
+ * pre-/post-processing hot path.
+ *
+ * The reference (emanuele-artioli/elvis) is pure Python and has no FFI layer; its boundary
+ * for this path is a set of Python function signatures in elvis.py / utils.py /
+ * presley.py.  Each entry point below names the reference function (file:line under
+ * /root/reference) whose arithmetic it replaces; elvis_b200/{elvis,utils,presley}.py keep
+ * the reference's Python signatures and call these through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name starts with `host_`;
+ *   - nothing here allocates, frees or synchronises; all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = the legacy default stream);
+ *   - all entry points are re-entrant (no global mutable state);
+ *   - the return value is ELVIS_OK (0) or a negative ELVIS_ERR_* code; for ELVIS_ERR_CUDA
+ *     the failing cudaError_t is returned by elvis_last_cuda_error() (thread local);
+ *   - clips are batched: leading dimension T (frames); the reference's per-frame calls are
+ *     the T = 1 case;
+ *   - block maps (scores, masks, levels) are dense row-major (T, By, Bx).
+ */
+#ifndef ELVIS_B200_H
+#define ELVIS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ELVIS_B200_ABI_VERSION 1
+
+#define ELVIS_OK               0
+#define ELVIS_ERR_INVALID_ARG (-1)   /* NULL pointer, non-positive size, out-of-range parameter   */
+#define ELVIS_ERR_UNSUPPORTED (-2)   /* a size/configuration this build has no kernel for          */
+#define ELVIS_ERR_CUDA        (-3)   /* a CUDA runtime call failed; see elvis_last_cuda_error()    */
+#define ELVIS_ERR_SHAPE       (-4)   /* dimensions not divisible by the block size (elvis.py:1376) */
+
+#if defined(__GNUC__)
+#define ELVIS_API __attribute__((visibility("default")))
+#else
+#define ELVIS_API
+#endif
+
+typedef void* elvis_stream_t;
+
+/* One 8-bit image plane of a clip.  Planar YUV 4:2:0 is three of these (Y with the full
+ * block size, U and V with half of it); the reference's packed H x W x 3 BGR/RGB frames
+ * (elvis.py:4341, presley.py:184) are one plane with channels = 3. */
+typedef struct elvis_plane {
+    void*   data;          /* device pointer to frame 0, row 0                       */
+    int64_t frame_stride;  /* bytes between consecutive frames                       */
+    int64_t row_stride;    /* bytes between consecutive pixel rows                   */
+    int32_t height;        /* pixel rows                                             */
+    int32_t width;         /* pixels per row                                         */
+    int32_t channels;      /* interleaved bytes per pixel: 1 (planar) or 3 (packed)  */
+    int32_t reserved;
+} elvis_plane;
+
+/* element type selector for block-level float inputs */
+#define ELVIS_F32 0
+#define ELVIS_F64 1
+
+/* which end of the ranking is removed (SURVEY.md appendix "Score polarity") */
+#define ELVIS_REMOVE_HIGH 0          /* elvis.py:1401  argsort(-row)[:k]            */
+#define ELVIS_REMOVE_LOW  1          /* utils.py:721   k successive argmin passes   */
+
+/* level-map rules */
+#define ELVIS_LEVELS_ROUND          0  /* rint(score * param)                     elvis.py:2146, 2176      */
+#define ELVIS_LEVELS_INVERTED_ROUND 1  /* clip(rint((1-imp)*param), 0, param)     utils.py:1196-1197, presley.py:968-975 */
+#define ELVIS_LEVELS_INVERTED_BINS  2  /* b = clip(floor((1-imp)*param), 0, param-1); b ? b+1 : 0   utils.py:1138-1148 */
+
+ELVIS_API int         elvis_abi_version(void);
+ELVIS_API const char* elvis_error_string(int code);
+ELVIS_API int         elvis_last_cuda_error(void);
+
+/* ---- a1: per-block SC / TC features (replaces the external EVCA call, elvis.py:1014-1031,
+ * presley.py:202; arithmetic defined by oracle/spec_scoring.py -- parity unpinned).
+ * y: luma plane, channels must be 1; only the top-left (By*bs) x (Bx*bs) region is read,
+ * By = height / bs, Bx = width / bs.  prev_halo: one luma frame (same row_stride) that
+ * precedes frame 0, or NULL (then TC[0] = 0).  block_size in {8, 16, 32}; dct_size must be
+ * 8.  sc, tc: float32 (T, By, Bx).  minmax: NULL or 4 floats {sc_min, sc_max, tc_min,
+ * tc_max} over frames [mm_begin, mm_end) -- overwritten, not accumulated. */
+ELVIS_API int elvis_score_sc_tc(const elvis_plane* y, int32_t n_frames, const uint8_t* prev_halo,
+                      int32_t block_size, int32_t dct_size, float* sc, float* tc,
+                      float* minmax, int32_t mm_begin, int32_t mm_end, elvis_stream_t stream);
+
+/* min and max of n block values -> out[0], out[1] (float64). */
+ELVIS_API int elvis_minmax(const void* x, int32_t dtype, int64_t n, double* out, elvis_stream_t stream);
+
+/* ---- a2: in-tree tail of calculate_removability_scores (elvis.py:1173-1215).
+ * sc/tc: (t_ext, By, Bx) of `dtype`, covering local frames [0, t_ext).  The call produces
+ * the un-normalised (smoothed) score for frames [t_begin, t_begin + t_count) into
+ * out (t_count, By, Bx) float64 and their min/max into out_minmax[2] (overwritten).
+ * norm: {sc_min, sc_max, tc_min, tc_max} of the WHOLE clip (same dtype as sc/tc).
+ * is_first / is_last: local frame t_begin is the clip's first frame / local frame
+ * t_begin + t_count - 1 is the clip's last frame (elvis.py:1183, 1206); when they are 0
+ * the halo frames t_begin - 1 / t_begin + t_count must be present in sc/tc.
+ * background: NULL or uint8 (t_ext, By, Bx), non-zero where the block is background
+ * (elvis.py:1193-1195).  smooth = (beta < 1 && clip length >= 2) (elvis.py:1202). */
+ELVIS_API int elvis_combine_removability(const void* sc, const void* tc, int32_t dtype, const void* norm,
+                               int32_t t_ext, int32_t by, int32_t bx,
+                               int32_t t_begin, int32_t t_count, int32_t is_first, int32_t is_last,
+                               const uint8_t* background, double alpha, double beta, int32_t smooth,
+                               double* out, double* out_minmax, elvis_stream_t stream);
+
+/* final normalize_array (elvis.py:864-867, 1218): x = (x - min) / (max - min) when
+ * max > min, unchanged otherwise.  minmax: 2 float64 on the device. */
+ELVIS_API int elvis_normalize(double* x, int64_t n, const double* minmax, elvis_stream_t stream);
+
+/* ---- a3: calculate_importance_scores (utils.py:665-688 == presley.py:129-152).
+ * Same extended-range convention as above.  foreground: NULL (all foreground) or
+ * (t_ext, By, Bx) of `dtype`.  out: float64 (t_count, By, Bx), per-frame normalised. */
+ELVIS_API int elvis_importance_scores(const void* sc, const void* tc, const void* foreground, int32_t dtype,
+                            int32_t t_ext, int32_t by, int32_t bx,
+                            int32_t t_begin, int32_t t_count, int32_t is_first, int32_t is_last,
+                            double alpha, double beta, double* out, elvis_stream_t stream);
+
+/* ---- a4/a6: per block-row top-k removal mask (elvis.py:1399-1415; utils.py:716-733).
+ * scores: float64 (T, By, Bx).  Row (t, by) removes k = k_per_row[by] blocks when
+ * k_per_row != NULL, else k_uniform; ties are broken lowest column first.  mask: uint8
+ * (T, By, Bx), 1 = removed.  Bx <= 4096. */
+ELVIS_API int elvis_select_rows(const double* scores, int32_t n_frames, int32_t by, int32_t bx,
+                      const int32_t* k_per_row, int32_t k_uniform, int32_t polarity,
+                      uint8_t* mask, elvis_stream_t stream);
+
+/* ---- a4/a6: shrink -- left-compact the kept blocks of every block row
+ * (elvis.py:1418-1425; utils.py:727-735).  Plane block = block_px x block_px pixels.
+ * dst must hold (By*block_px) rows of out_bx*block_px pixels; a row that keeps fewer than
+ * out_bx blocks is zero padded, one that keeps more is truncated (utils.py:735). */
+ELVIS_API int elvis_shrink(const elvis_plane* src, const elvis_plane* dst, int32_t n_frames,
+                 int32_t block_px, int32_t by, int32_t bx, int32_t out_bx,
+                 const uint8_t* mask, elvis_stream_t stream);
+
+/* ---- a5/a7: stretch -- scatter shrunk blocks back to the mask == 0 positions of their
+ * row, zeros elsewhere (elvis.py:1436-1455; utils.py:739-759).  shrunk_bx = blocks per
+ * row of src. */
+ELVIS_API int elvis_stretch(const elvis_plane* src, const elvis_plane* dst, int32_t n_frames,
+                  int32_t block_px, int32_t by, int32_t bx, int32_t shrunk_bx,
+                  const uint8_t* mask, elvis_stream_t stream);
+
+/* ---- a8-a12: level maps from scores.  scores float64 (n), levels int32 (n). */
+ELVIS_API int elvis_levels_from_scores(const double* scores, int64_t n, int32_t rule, int32_t param,
+                             int32_t* levels, elvis_stream_t stream);
+
+/* ---- a9/a11/a12: per-block repeated 5x5 sigma=1 Gaussian blur (elvis.py:2183-2191,
+ * utils.py:1200-1210, presley.py:986-990).  rounds: int32 (T, By, Bx), values <= 0 copy.
+ * block_px <= 64.  Rows/columns beyond By*block_px / Bx*block_px are copied through
+ * (utils.py:1215-1216).  src and dst must not overlap. */
+ELVIS_API int elvis_degrade_blur(const elvis_plane* src, const elvis_plane* dst, int32_t n_frames,
+                       int32_t block_px, int32_t by, int32_t bx, const int32_t* rounds,
+                       elvis_stream_t stream);
+
+/* ---- a8/a10/a12: per-block AREA down + LINEAR up (elvis.py:2154-2164,
+ * utils.py:1151-1161, presley.py:978-983).  levels: int32 (T, By, Bx) indexing
+ * `tables`, the device copy of the blob built by elvis_b200/_tables.py
+ * (n_levels entries; layout documented there); a level whose small size equals block_px
+ * copies the block.  block_px <= 64. */
+ELVIS_API int elvis_degrade_downsample(const elvis_plane* src, const elvis_plane* dst, int32_t n_frames,
+                             int32_t block_px, int32_t by, int32_t bx, const int32_t* levels,
+                             const int32_t* tables, int32_t n_levels, elvis_stream_t stream);
+
+/* ---- a14: DCT-coefficient dampening (README.md:11,44 only; defined by
+ * oracle/spec_dct_dampen.py -- parity unpinned).  strength: float32 (T, By, Bx).
+ * block_px must be a multiple of 8. */
+ELVIS_API int elvis_dct_dampen(const elvis_plane* src, const elvis_plane* dst, int32_t n_frames,
+                     int32_t block_px, int32_t by, int32_t bx, const float* strength,
+                     elvis_stream_t stream);
+
+/* ---- a13: side-channel packers.  Bit packing is np.packbits-compatible (elvis.py:4414):
+ * flat over n values, MSB first, last byte zero padded.  The 2-bit level packer is new
+ * (README.md:50 TODO): per row of bx levels, ceil(bx/4) bytes, level i in bits
+ * 2*(i%4).. of byte i/4. */
+ELVIS_API int elvis_pack_mask_bits(const uint8_t* mask, int64_t n, uint8_t* packed, elvis_stream_t stream);
+ELVIS_API int elvis_unpack_mask_bits(const uint8_t* packed, int64_t n, uint8_t* mask, elvis_stream_t stream);
+ELVIS_API int elvis_pack_levels_2bit(const int32_t* levels, int64_t rows, int32_t bx, uint8_t* packed,
+                           elvis_stream_t stream);
+ELVIS_API int elvis_unpack_levels_2bit(const uint8_t* packed, int64_t rows, int32_t bx, int32_t* levels,
+                             elvis_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELVIS_B200_H */

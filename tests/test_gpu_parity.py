@@ -1,0 +1,324 @@
+"""-m gpu: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+Bit-exact for masks, frames, level maps, blurred/downsampled pixels and -- given identical
+SC/TC -- float64 scores; <= 1e-4 relative for SC/TC and dampened pixels."""
+import numpy as np
+import pytest
+
+from _util import random_scores, synth_luma, synth_yuv420
+from oracle import ref_port as P
+from oracle import spec_dct_dampen, spec_scoring
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4   # north_star tolerance for float scores / dampened pixels
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import elvis_b200.ops  # noqa: F401  (raises if libelvis_b200.so is missing)
+    return torch.device("cuda")
+
+
+def to_dev(a, dev):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+# ---------------------------------------------------------------------------------- a1
+@pytest.mark.parametrize("bs,H,W,T", [(16, 64, 96, 7), (8, 40, 72, 5), (32, 64, 128, 4), (16, 48, 272, 30), (16, 1080, 1920, 3)])
+def test_sc_tc_vs_spec(dev, bs, H, W, T):
+    from elvis_b200 import ops
+    y = synth_luma(T, H, W, seed=bs + T)
+    sc, tc, mm = ops.score_sc_tc(to_dev(y, dev), bs)
+    rsc, rtc = spec_scoring.sc_tc(y, bs)
+    sc, tc, mm = sc.cpu().numpy(), tc.cpu().numpy(), mm.cpu().numpy()
+    assert sc.shape == rsc.shape
+    np.testing.assert_allclose(sc, rsc, rtol=RTOL, atol=0)
+    np.testing.assert_allclose(tc, rtc, rtol=RTOL, atol=0)
+    assert np.all(tc[0] == 0)
+    assert mm.tolist() == [sc.min(), sc.max(), tc.min(), tc.max()]
+
+
+def test_sc_tc_random_noise_and_static(dev):
+    from elvis_b200 import ops
+    rng = np.random.default_rng(5)
+    y = rng.integers(0, 256, (6, 64, 64), dtype=np.uint8)
+    y[3] = y[2]                      # a repeated frame: TC must be exactly 0
+    y[5] = y[4]
+    y[5, 10, 10] ^= 1                # a single-LSB change: the smallest non-zero TC
+    sc, tc, _ = ops.score_sc_tc(to_dev(y, dev), 16)
+    rsc, rtc = spec_scoring.sc_tc(y, 16)
+    np.testing.assert_allclose(sc.cpu().numpy(), rsc, rtol=RTOL, atol=0)
+    np.testing.assert_allclose(tc.cpu().numpy(), rtc, rtol=RTOL, atol=0)
+    assert np.all(tc.cpu().numpy()[3] == 0)
+
+
+def test_sc_tc_chunking_and_halo(dev, monkeypatch):
+    """Chunk boundaries and the sharding halo must not change any value."""
+    from elvis_b200 import ops
+    y = synth_luma(21, 32, 64, seed=9)
+    yd = to_dev(y, dev)
+    monkeypatch.setenv("ELVIS_SCORE_CHUNK", "64")
+    sc1, tc1, _ = ops.score_sc_tc(yd, 16)
+    monkeypatch.setenv("ELVIS_SCORE_CHUNK", "4")
+    sc4, tc4, _ = ops.score_sc_tc(yd, 16)
+    rsc, rtc = spec_scoring.sc_tc(y, 16)
+    for a in (sc1, sc4):
+        np.testing.assert_allclose(a.cpu().numpy(), rsc, rtol=RTOL, atol=0)
+    for a in (tc1, tc4):
+        np.testing.assert_allclose(a.cpu().numpy(), rtc, rtol=RTOL, atol=0)
+    # halo: frames 8.. scored alone with frame 7 as prev_halo == the tail of the full run
+    sch, tch, mm = ops.score_sc_tc(yd[8:], 16, prev_halo=yd[7], minmax_range=(2, 5))
+    rsc_h, rtc_h = spec_scoring.sc_tc(y[8:], 16, prev=y[7])
+    np.testing.assert_allclose(sch.cpu().numpy(), rsc_h, rtol=RTOL, atol=0)
+    np.testing.assert_allclose(tch.cpu().numpy(), rtc_h, rtol=RTOL, atol=0)
+    s, t = sch.cpu().numpy()[2:5], tch.cpu().numpy()[2:5]
+    assert mm.cpu().numpy().tolist() == [s.min(), s.max(), t.min(), t.max()]
+
+
+def test_sc_tc_strided_rows(dev):
+    """A cropped view (row stride > width, width not a multiple of the warp tile)."""
+    from elvis_b200 import ops
+    y = synth_luma(4, 48, 112, seed=3)
+    yd = to_dev(y, dev)[:, :, :88]          # 88 = 5.5 blocks of 16 -> Bx = 5
+    sc, tc, _ = ops.score_sc_tc(yd, 16)
+    rsc, rtc = spec_scoring.sc_tc(y[:, :, :88], 16)
+    np.testing.assert_allclose(sc.cpu().numpy(), rsc, rtol=RTOL, atol=0)
+    np.testing.assert_allclose(tc.cpu().numpy(), rtc, rtol=RTOL, atol=0)
+    yo = to_dev(y, dev)[:, :, 3:3 + 80]     # misaligned base pointer -> byte-load path
+    sc, tc, _ = ops.score_sc_tc(yo, 16)
+    rsc, rtc = spec_scoring.sc_tc(y[:, :, 3:83], 16)
+    np.testing.assert_allclose(sc.cpu().numpy(), rsc, rtol=RTOL, atol=0)
+    np.testing.assert_allclose(tc.cpu().numpy(), rtc, rtol=RTOL, atol=0)
+
+
+# ---------------------------------------------------------------------------------- a2 / a3
+@pytest.mark.parametrize("beta", [1.0, 0.5, 0.25])
+@pytest.mark.parametrize("with_bg", [False, True])
+def test_removability_bit_exact(dev, beta, with_bg):
+    from elvis_b200 import elvis as E
+    rng = np.random.default_rng(11)
+    T, By, Bx = 9, 7, 13
+    sc, tc = rng.random((T, By, Bx)) * 60, rng.random((T, By, Bx)) * 30
+    tc[0] = 0
+    bg = rng.random((T, By, Bx)) > 0.6 if with_bg else None
+    got = E.removability_from_features(sc, tc, 0.3, beta, bg)
+    ref = P.combine_removability(sc, tc, 0.3, beta, bg)
+    assert got.dtype == np.float64 and np.array_equal(got, ref)
+
+
+def test_removability_flat_inputs(dev):
+    from elvis_b200 import elvis as E
+    sc = np.full((3, 4, 5), 2.5)
+    tc = np.zeros((3, 4, 5))
+    assert np.array_equal(E.removability_from_features(sc, tc, 0.5, 0.5), P.combine_removability(sc, tc, 0.5, 0.5))
+    one = np.random.default_rng(0).random((1, 4, 5))
+    assert np.array_equal(E.removability_from_features(one, one * 0, 0.5, 0.5), P.combine_removability(one, one * 0, 0.5, 0.5))
+
+
+def test_importance_bit_exact(dev):
+    from elvis_b200 import utils as U
+    rng = np.random.default_rng(12)
+
+    class Cx:
+        pass
+    T, By, Bx = 6, 9, 11
+    cx = Cx()
+    cx.SC, cx.TC = rng.random((T, By, Bx)) * 50, rng.random((T, By, Bx)) * 20
+    fg = rng.random((T, By, Bx))
+    got = np.stack(U.calculate_importance_scores(None, 16, 0.3, 0.6, cx, fg))
+    assert np.array_equal(got, P.importance_scores(cx.SC, cx.TC, 0.3, 0.6, fg))
+    cx.SC, cx.TC = cx.SC[:1], cx.TC[:1]
+    got = np.stack(U.calculate_importance_scores(None, 16, 0.3, 0.6, cx, fg[:1]))
+    assert np.array_equal(got, P.importance_scores(cx.SC, cx.TC, 0.3, 0.6, fg[:1]))
+
+
+# ---------------------------------------------------------------------------------- a4-a7
+@pytest.mark.parametrize("ties", ["none", "quantised", "all"])
+@pytest.mark.parametrize("bx", [5, 64, 120, 240, 300, 700])
+def test_select_rows_bit_exact(dev, ties, bx):
+    from elvis_b200 import ops
+    rng = np.random.default_rng(bx)
+    s = random_scores(rng, (3, 6, bx), ties)
+    s[0, 0, : min(3, bx)] = [0.0, -0.0, 0.0][: min(3, bx)]
+    for pol in (P.REMOVE_HIGH, P.REMOVE_LOW):
+        for k in (0, 1, bx // 2, bx - 1, bx):
+            got = ops.select_rows(to_dev(s, dev), k, pol).cpu().numpy()
+            assert np.array_equal(got, P.select_rows(s, k, pol)), (pol, k)
+    kk = rng.integers(0, bx + 1, 6).astype(np.int32)
+    got = ops.select_rows(to_dev(s, dev), to_dev(kk, dev), P.REMOVE_LOW).cpu().numpy()
+    assert np.array_equal(got, P.select_rows(s, np.broadcast_to(kk, (3, 6)), P.REMOVE_LOW))
+
+
+@pytest.mark.parametrize("H,W,bs,shrink", [(64, 96, 16, 0.5), (48, 80, 8, 0.25), (32, 64, 16, 3), (32, 64, 16, 0.0),
+                                          (32, 64, 16, 0.999), (32, 64, 16, 1.0), (64, 64, 32, 0.5), (24, 36, 12, 0.34),
+                                          (270, 480, 4, 0.4)])
+def test_elvis_shrink_stretch_packed(dev, H, W, bs, shrink):
+    from elvis_b200 import elvis as E
+    rng = np.random.default_rng(H + W)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    sc = rng.random((H // bs, W // bs))
+    g_img, g_mask, g_coords = E.apply_selective_removal(img, sc, bs, shrink)
+    r_img, r_mask, r_coords = P.apply_selective_removal(img, sc, bs, shrink)
+    assert g_img.shape == r_img.shape and np.array_equal(g_img, r_img)
+    assert g_mask.dtype == np.int8 and np.array_equal(g_mask, r_mask) and g_coords == r_coords
+    g_full = E.stretch_frame(g_img, g_mask, bs)
+    assert np.array_equal(g_full, P.stretch_frame(r_img, r_mask, bs))
+    keep = np.kron(1 - r_mask, np.ones((bs, bs), np.uint8)).astype(bool)
+    assert np.array_equal(g_full[keep], img[keep]) and not g_full[~keep].any()   # round trip
+
+
+def test_elvis_errors(dev):
+    from elvis_b200 import elvis as E
+    img = np.zeros((50, 64, 3), np.uint8)
+    with pytest.raises(ValueError):
+        E.apply_selective_removal(img, np.zeros((3, 4)), 16, 0.5)
+    with pytest.raises(ValueError):
+        E.split_image_into_blocks(img, 16)
+    with pytest.raises(ValueError):
+        E.filter_frame_gaussian(img, np.zeros((3, 4)), 16)
+
+
+@pytest.mark.parametrize("H,W,bs,shrink", [(64, 96, 16, 0.5), (50, 85, 8, 0.25), (80, 128, 16, 0.3), (80, 128, 16, 0.0),
+                                          (80, 128, 16, 0.99), (40, 64, 8, 0.3)])
+def test_row_only_shrink_stretch(dev, H, W, bs, shrink):
+    from elvis_b200 import utils as U
+    rng = np.random.default_rng(H * W)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    imp = np.round(rng.random((H // bs, W // bs)) * 8) / 8
+    g_img, g_mask = U.shrink_frame_row_only(img, imp, bs, shrink)
+    r_img, r_mask = P.shrink_frame_row_only(img, imp, bs, shrink)
+    assert g_mask.dtype == bool and np.array_equal(g_mask, r_mask)
+    assert g_img.shape == r_img.shape and np.array_equal(g_img, r_img)
+    assert np.array_equal(U.stretch_frame_row_only(g_img, g_mask, bs), P.stretch_frame_row_only(r_img, r_mask, bs))
+
+
+def test_planar_pipeline_matches_per_plane_oracle(dev):
+    """Planar YUV 4:2:0: mask from luma scores, applied to chroma at half block size."""
+    from elvis_b200.pipeline import ElvisV1, Yuv420
+    T, H, W, bs = 6, 96, 160, 16
+    y, u, v = synth_yuv420(T, H, W, seed=21)
+    clip = Yuv420(to_dev(y, dev), to_dev(u, dev), to_dev(v, dev))
+    pipe = ElvisV1(bs, 0.5, 0.5, 0.5)
+    scores, mask, shrunk, stretched = pipe.run(clip)
+    scores, mask = scores.cpu().numpy(), mask.cpu().numpy()
+    rsc, rtc = spec_scoring.sc_tc(y, bs)
+    ref_scores = P.combine_removability(rsc, rtc, 0.5, 0.5)
+    np.testing.assert_allclose(scores, ref_scores, rtol=RTOL, atol=1e-9)
+    k = P.blocks_to_remove_elvis(0.5, W // bs)
+    # the mask must be the exact top-k of the scores the GPU itself produced ...
+    assert np.array_equal(mask, P.select_rows(scores, k, P.REMOVE_HIGH))
+    # ... and equal to the oracle's wherever the oracle's decision margin exceeds the tolerance
+    ref_mask = P.select_rows(ref_scores, k, P.REMOVE_HIGH)
+    srt = np.sort(ref_scores, axis=-1)[..., ::-1]
+    margin = srt[..., k - 1] - srt[..., k]
+    safe = margin > 2 * RTOL
+    assert safe.mean() > 0.5 and np.array_equal(mask[safe], ref_mask[safe])
+    for name, plane, pb in (("y", y, bs), ("u", u, bs // 2), ("v", v, bs // 2)):
+        g_s = getattr(shrunk, name).cpu().numpy()
+        g_f = getattr(stretched, name).cpu().numpy()
+        for t in range(T):
+            r_s = P.shrink_plane(plane[t], mask[t], pb)
+            assert np.array_equal(g_s[t], r_s), (name, t)
+            assert np.array_equal(g_f[t], P.stretch_plane(r_s, mask[t], pb)), (name, t)
+
+
+# ---------------------------------------------------------------------------------- a8-a12
+@pytest.mark.parametrize("bs", [8, 16, 32])
+def test_elvis_filters_packed(dev, bs):
+    from elvis_b200 import elvis as E
+    rng = np.random.default_rng(bs)
+    H, W = bs * 5, bs * 7
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    sc = rng.random((5, 7))
+    sc[0, :5] = [0.5, 0.125, 1.0, 0.0, 0.25]     # exact .5 products -> round-half-even cases
+    for name in ("filter_frame_downsample", "filter_frame_gaussian"):
+        g_img, g_map = getattr(E, name)(img, sc, bs)
+        r_img, r_map = getattr(P, name)(img, sc, bs)
+        assert g_map.dtype == np.int32 and np.array_equal(g_map, r_map), name
+        assert np.array_equal(g_img, r_img), (name, np.argwhere(g_img != r_img)[:5])
+
+
+@pytest.mark.parametrize("bs", [8, 16])
+def test_utils_degrade_packed_with_crop(dev, bs):
+    from elvis_b200 import utils as U
+    rng = np.random.default_rng(bs + 1)
+    img = rng.integers(0, 256, (bs * 5 + 3, bs * 7 + 5, 3), dtype=np.uint8)
+    imp = rng.random((5, 7))
+    for name in ("degrade_adaptive_downsample", "degrade_adaptive_blur"):
+        g_img, g_map = getattr(U, name)(img, imp, bs)
+        r_img, r_map = getattr(P, name)(img, imp, bs)
+        assert np.array_equal(g_map, r_map), name
+        assert np.array_equal(g_img, r_img), name
+
+
+def test_presley_degrade_video(dev):
+    from elvis_b200 import presley as Pr
+    rng = np.random.default_rng(77)
+    frames = [rng.integers(0, 256, (64, 96, 3), dtype=np.uint8) for _ in range(3)]
+    imps = [rng.random((4, 6)) for _ in range(3)]
+    for method, tag in ((Pr.downscale_block, "downscale"), (Pr.blur_block, "blur")):
+        out, maps = Pr.degrade_video_adaptive(frames, imps, 16, 4, method)
+        for f, imp, o, m in zip(frames, imps, out, maps):
+            rm = P.levels_inverted_round(imp, 4)
+            assert np.array_equal(m, rm)
+            assert np.array_equal(o, P.presley_degrade_frame(f, rm, 16, tag)), tag
+    blk = frames[0][:16, :16]
+    assert np.array_equal(Pr.downscale_block(blk, 3), P.presley_degrade_frame(blk, np.array([[3]]), 16, "downscale"))
+    assert np.array_equal(Pr.blur_block(blk, 2), P.presley_degrade_frame(blk, np.array([[2]]), 16, "blur"))
+
+
+def test_planar_degrade(dev):
+    from elvis_b200 import ops
+    from elvis_b200.pipeline import PresleyV2, Yuv420
+    T, H, W, bs = 3, 64, 96, 16
+    y, u, v = synth_yuv420(T, H, W, seed=4)
+    clip = Yuv420(to_dev(y, dev), to_dev(u, dev), to_dev(v, dev))
+    rng = np.random.default_rng(8)
+    rounds = rng.integers(0, 11, (T, H // bs, W // bs)).astype(np.int32)
+    levels = rng.integers(0, 4, (T, H // bs, W // bs)).astype(np.int32)
+    v2 = PresleyV2(bs)
+    b = v2.blur(clip, to_dev(rounds, dev))
+    d = v2.downsample_pow2(clip, to_dev(levels, dev), 3)
+    for name, plane, pb in (("y", y, bs), ("u", u, bs // 2), ("v", v, bs // 2)):
+        for t in range(T):
+            assert np.array_equal(getattr(b, name)[t].cpu().numpy(), P.blur_plane(plane[t], rounds[t], pb)), name
+            small = np.maximum(1, pb >> levels[t])
+            assert np.array_equal(getattr(d, name)[t].cpu().numpy(), P.downsample_plane(plane[t], small, pb)), name
+    packed = ops.pack_levels_2bit(to_dev(levels, dev))
+    assert np.array_equal(packed.cpu().numpy(), P.pack_levels_2bit(levels))
+    assert np.array_equal(ops.unpack_levels_2bit(packed, W // bs).cpu().numpy(), levels)
+
+
+# ---------------------------------------------------------------------------------- a13 / a14
+def test_mask_bit_packing(dev):
+    from elvis_b200 import elvis as E
+    rng = np.random.default_rng(2)
+    m = (rng.random((5, 7, 13)) > 0.5).astype(np.int8)
+    packed, shape = E.pack_removal_masks(m)
+    ref, _ = P.pack_masks(m)
+    assert np.array_equal(packed, ref) and shape == m.shape
+    assert np.array_equal(E.unpack_removal_masks(packed, shape), m)
+
+
+@pytest.mark.parametrize("pb", [8, 16])
+def test_dct_dampen(dev, pb):
+    from elvis_b200 import ops
+    T, H, W = 2, pb * 4, pb * 6
+    y = synth_luma(T, H, W, seed=pb)
+    rng = np.random.default_rng(pb)
+    s = rng.random((T, H // pb, W // pb)).astype(np.float32)
+    s[0, 0, 0], s[0, 0, 1] = 0.0, 1.0
+    out = ops.dct_dampen(to_dev(y, dev), to_dev(s, dev), pb).cpu().numpy()
+    for t in range(T):
+        ref_f = spec_dct_dampen.dampen_plane(y[t], s[t], pb, return_float=True)
+        # the u8 result is the rounding of a value within RTOL (relative to full scale) of the spec
+        assert np.all(np.abs(out[t].astype(np.float64) - np.clip(ref_f, 0, 255)) <= 0.5 + RTOL * 255)
+        ref = spec_dct_dampen.dampen_plane(y[t], s[t], pb)
+        assert (out[t] != ref).mean() < 1e-3
+    assert np.array_equal(out[0, :pb, :pb], y[0, :pb, :pb])     # strength 0 is the identity
+    packed = np.repeat(y[..., None], 3, axis=-1)                  # packed 3-channel path
+    outp = ops.dct_dampen(to_dev(packed, dev), to_dev(s, dev), pb).cpu().numpy()
+    assert np.array_equal(outp[..., 1], out)
