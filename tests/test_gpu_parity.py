@@ -154,7 +154,7 @@ def test_select_rows_bit_exact(dev, ties, bx):
 
 @pytest.mark.parametrize("H,W,bs,shrink", [(64, 96, 16, 0.5), (48, 80, 8, 0.25), (32, 64, 16, 3), (32, 64, 16, 0.0),
                                           (32, 64, 16, 0.999), (32, 64, 16, 1.0), (64, 64, 32, 0.5), (24, 36, 12, 0.34),
-                                          (270, 480, 4, 0.4)])
+                                          (272, 480, 4, 0.4)])
 def test_elvis_shrink_stretch_packed(dev, H, W, bs, shrink):
     from elvis_b200 import elvis as E
     rng = np.random.default_rng(H + W)
