@@ -1,6 +1,7 @@
 // Shared host/device helpers for the elvis_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 #include "../../include/elvis_b200.h"
 

@@ -1,10 +1,14 @@
 // a4 / a6: per block-row top-k removal mask, and a13: side-channel bit packers.
 //
-// One CTA sorts one (frame, block-row) of scores: a shared-memory bitonic network over
-// (order-preserving 64-bit key, column) pairs.  The comparator is the strict total order
-// "key, then column", which realises the tie rule of the oracle (lowest column first ==
-// np.argmin's rule, utils.py:721, and the stable reading of np.argsort(-row),
-// elvis.py:1401).  The first k entries of the sorted row are the removed blocks.
+// Scores become order-preserving 64-bit keys; together with the column index they form a
+// strict total order "key, then column", which realises the tie rule of the oracle (lowest
+// column first == np.argmin's rule, utils.py:721, and the stable reading of
+// np.argsort(-row), elvis.py:1401).  The removed blocks of a row are its k smallest elements
+// in that order -- a SELECTION problem, not a sort:
+//   * rows of up to 512 blocks: one WARP per (frame, block-row), the row held in registers
+//     (32 columns per register slot), randomised quickselect with ballot/shuffle counting --
+//     about 2 ln(Bx) rounds of Bx/32 compares per lane, no shared memory, no barriers;
+//   * longer rows: one CTA per row, shared-memory bitonic sort of (key, column) pairs.
 #include "common.cuh"
 
 namespace elvis {
@@ -15,6 +19,11 @@ __device__ __forceinline__ unsigned long long sortable_key(double v) {
     v = __dadd_rn(v, 0.0);   // -0.0 -> +0.0 so that signed zeros tie like they compare
     const unsigned long long b = (unsigned long long)__double_as_longlong(v);
     return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+
+__device__ __forceinline__ unsigned long long row_key(double v, int polarity) {
+    // NaN ranks last in either polarity (np.argsort's rule), but ahead of the padding
+    return (v != v) ? ~0ULL - 1 : sortable_key(polarity == ELVIS_REMOVE_HIGH ? -v : v);
 }
 
 constexpr int select_threads(int n) { return n / 2 > 512 ? 512 : (n / 2 < 32 ? 32 : n / 2); }
@@ -36,9 +45,7 @@ __global__ void __launch_bounds__(select_threads(N)) select_rows_kernel(
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         unsigned long long key = ~0ULL;
         if (i < bx) {
-            const double v = src[i];
-            // NaN ranks last in either polarity (np.argsort's rule), but ahead of the padding
-            key = (v != v) ? ~0ULL - 1 : sortable_key(polarity == ELVIS_REMOVE_HIGH ? -v : v);
+            key = row_key(src[i], polarity);
         }
         s_key[i] = key;
         s_col[i] = (uint16_t)i;
@@ -67,6 +74,104 @@ __global__ void __launch_bounds__(select_threads(N)) select_rows_kernel(
         const int c = s_col[i];
         if (c < bx) dst[c] = i < k ? 1 : 0;
     }
+}
+
+
+// One warp per row; slot j of lane l holds column j*32 + l.
+template <int E>
+__global__ void __launch_bounds__(256) select_rows_warp_kernel(
+        const double* __restrict__ scores, int64_t rows, int by, int bx, const int32_t* __restrict__ k_per_row,
+        int k_uniform, int polarity, uint8_t* __restrict__ mask) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int k = k_per_row ? k_per_row[row % by] : k_uniform;
+    const double* src = scores + row * bx;
+    uint8_t* dst = mask + row * bx;
+
+    unsigned long long key[E];
+    unsigned valid = 0;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+        const int c = j * 32 + lane;
+        key[j] = ~0ULL;
+        if (c < bx) {
+            key[j] = row_key(src[c], polarity);
+            valid |= 1u << j;
+        }
+    }
+    unsigned selected = 0;
+    if (k >= bx) {
+        selected = valid;
+    } else if (k > 0) {
+        unsigned active = valid;
+        int need = k;
+        unsigned round = 0;
+        while (need > 0) {
+            // inclusive scan of the per-lane active counts
+            const int cnt = __popc(active);
+            int pre = cnt;
+#pragma unroll
+            for (int m = 1; m < 32; m <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, pre, m);
+                if (lane >= m) pre += o;
+            }
+            const int total = __shfl_sync(0xffffffffu, pre, 31);
+            if (total <= need) {   // (== by the loop invariant) every remaining candidate is removed
+                selected |= active;
+                break;
+            }
+            // pivot: the r-th active element, r pseudo-random but reproducible
+            const unsigned h = ((unsigned)row * 2654435761u) ^ (round * 0x9E3779B9u + 0x7F4A7C15u);
+            const int r = (int)__umulhi(h * 2246822519u, (unsigned)total);
+            const bool mine = (pre - cnt <= r) && (r < pre);
+            const int src_lane = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+            unsigned long long pk = 0;
+            int pslot = 0;
+            if (mine) {
+                unsigned a = active;
+                for (int skip = r - (pre - cnt); skip > 0; --skip) a &= a - 1;   // drop the lowest set bits
+                pslot = __ffs(a) - 1;
+#pragma unroll
+                for (int j = 0; j < E; ++j)
+                    if (j == pslot) pk = key[j];
+            }
+            pk = __shfl_sync(0xffffffffu, pk, src_lane);
+            pslot = __shfl_sync(0xffffffffu, pslot, src_lane);
+            const int pcol = pslot * 32 + src_lane;
+            // candidates at or before the pivot in (key, column) order
+            unsigned le = 0;
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                const bool b = key[j] < pk || (key[j] == pk && j * 32 + lane <= pcol);
+                le |= (unsigned)b << j;
+            }
+            le &= active;
+            const int c_le = __reduce_add_sync(0xffffffffu, __popc(le));
+            if (c_le <= need) {          // all of them belong to the k smallest
+                selected |= le;
+                need -= c_le;
+                active &= ~le;
+            } else {                     // the k-th smallest lies strictly before the pivot
+                active = le;
+                if (mine) active &= ~(1u << pslot);
+            }
+            ++round;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+        const int c = j * 32 + lane;
+        if (c < bx) dst[c] = (selected >> j) & 1u;
+    }
+}
+
+template <int E>
+int launch_select_warp(const double* scores, int64_t rows, int by, int bx, const int32_t* kpr, int ku, int pol, uint8_t* mask, cudaStream_t st) {
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    select_rows_warp_kernel<E><<<grid, 256, 0, st>>>(scores, rows, by, bx, kpr, ku, pol, mask);
+    ELVIS_CHECK_LAUNCH();
+    return ELVIS_OK;
 }
 
 // np.packbits over a flat array: bit 7 of byte j is value 8j
@@ -138,6 +243,13 @@ extern "C" int elvis_select_rows(const double* scores, int32_t n_frames, int32_t
     if (bx > 4096) return ELVIS_ERR_UNSUPPORTED;
     const int64_t rows = (int64_t)n_frames * by;
     cudaStream_t st = as_stream(stream);
+    const bool force_sort = getenv("ELVIS_SELECT_SORT") != nullptr;   // test hook: exercise the CTA path on short rows
+    if (!force_sort) {
+        if (bx <= 64) return launch_select_warp<2>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+        if (bx <= 128) return launch_select_warp<4>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+        if (bx <= 256) return launch_select_warp<8>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+        if (bx <= 512) return launch_select_warp<16>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+    }
     if (bx <= 64) return launch_select<64>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
     if (bx <= 128) return launch_select<128>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
     if (bx <= 256) return launch_select<256>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);

@@ -121,3 +121,64 @@ class PresleyV2:
 
     def dampen(self, clip: Yuv420, strength: torch.Tensor, out: Optional[Yuv420] = None) -> Yuv420:
         return self._each(clip, lambda p, pb, o: ops.dct_dampen(p, strength, pb, out=o), out)
+
+
+class HostElvisV1:
+    """The headline path for callers whose frames live in HOST memory (the end-to-end API):
+    an I420 clip in, removal masks + shrunk I420 clip + stretched I420 clip out, all host
+    tensors.  Work is enqueued on one of `depth` private streams with its own device
+    buffers, so consecutive calls overlap one clip's device->host copies with the next
+    clip's host->device copy (full-duplex PCIe).  Pass pinned tensors to get async copies.
+    """
+
+    def __init__(self, n_frames: int, height: int, width: int, block_size: int = 16, shrink_amount: float = 0.5,
+                 alpha: float = 0.5, beta: float = 0.5, device="cuda", depth: int = 2):
+        self.pipe = ElvisV1(block_size, shrink_amount, alpha, beta)
+        self.T, self.H, self.W = n_frames, height, width
+        self.dev = torch.device(device)
+        by, bx = height // block_size, width // block_size
+        self.k = blocks_to_remove(shrink_amount, bx)
+        self.sw = (bx - self.k) * block_size
+        self.slots = []
+        for _ in range(depth):
+            self.slots.append({
+                "stream": torch.cuda.Stream(self.dev),
+                "in": torch.empty((n_frames, height * width * 3 // 2), dtype=torch.uint8, device=self.dev),
+                "shrunk": torch.empty((n_frames, height * self.sw * 3 // 2), dtype=torch.uint8, device=self.dev),
+                "full": torch.empty((n_frames, height * width * 3 // 2), dtype=torch.uint8, device=self.dev),
+            })
+        self._next = 0
+
+    def host_buffers(self, pinned: bool = True):
+        """Convenience: (shrunk_i420, stretched_i420, masks) host tensors of the right shapes."""
+        by, bx = self.H // self.pipe.bs, self.W // self.pipe.bs
+        mk = lambda *s: torch.empty(s, dtype=torch.uint8, pin_memory=pinned)   # noqa: E731
+        return mk(self.T, self.H * self.sw * 3 // 2), mk(self.T, self.H * self.W * 3 // 2), mk(self.T, by, bx)
+
+    @property
+    def h2d_bytes(self) -> int:
+        return self.T * self.H * self.W * 3 // 2
+
+    @property
+    def d2h_bytes(self) -> int:
+        by, bx = self.H // self.pipe.bs, self.W // self.pipe.bs
+        return self.T * (self.H * self.sw * 3 // 2 + self.H * self.W * 3 // 2 + by * bx)
+
+    def process(self, i420_host: torch.Tensor, shrunk_host: torch.Tensor, stretched_host: torch.Tensor,
+                mask_host: torch.Tensor) -> torch.cuda.Event:
+        """Enqueue one clip; returns an event that fires when the three outputs are in host
+        memory.  Call .synchronize() on it (or on the device) before reading them."""
+        slot = self.slots[self._next]
+        self._next = (self._next + 1) % len(self.slots)
+        with torch.cuda.stream(slot["stream"]):
+            slot["in"].copy_(i420_host, non_blocking=True)
+            clip = Yuv420.from_i420(slot["in"], self.H, self.W)
+            shrunk = Yuv420.from_i420(slot["shrunk"], self.H, self.sw)
+            full = Yuv420.from_i420(slot["full"], self.H, self.W)
+            _, mask, _, _ = self.pipe.run(clip, shrunk_out=shrunk, stretched_out=full)
+            mask_host.copy_(mask, non_blocking=True)
+            shrunk_host.copy_(slot["shrunk"], non_blocking=True)
+            stretched_host.copy_(slot["full"], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        return done

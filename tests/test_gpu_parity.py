@@ -322,3 +322,27 @@ def test_dct_dampen(dev, pb):
     packed = np.repeat(y[..., None], 3, axis=-1)                  # packed 3-channel path
     outp = ops.dct_dampen(to_dev(packed, dev), to_dev(s, dev), pb).cpu().numpy()
     assert np.array_equal(outp[..., 1], out)
+
+
+def test_select_rows_cta_sort_path(dev, monkeypatch):
+    """Short rows normally take the warp quickselect; force the CTA bitonic path as well."""
+    from elvis_b200 import ops
+    monkeypatch.setenv("ELVIS_SELECT_SORT", "1")
+    rng = np.random.default_rng(99)
+    for bx, ties in ((120, "none"), (240, "quantised"), (37, "all")):
+        s = random_scores(rng, (2, 5, bx), ties)
+        for pol in (P.REMOVE_HIGH, P.REMOVE_LOW):
+            for k in (1, bx // 2, bx - 1):
+                assert np.array_equal(ops.select_rows(to_dev(s, dev), k, pol).cpu().numpy(), P.select_rows(s, k, pol))
+
+
+def test_select_rows_sorted_and_adversarial_rows(dev):
+    """Quickselect must not depend on input order: sorted, reversed, constant-with-one-outlier."""
+    from elvis_b200 import ops
+    bx = 240
+    base = np.linspace(0, 1, bx)
+    rows = np.stack([base, base[::-1], np.full(bx, 0.25), np.r_[np.full(bx - 1, 0.25), 0.9], np.r_[0.1, np.full(bx - 1, 0.25)],
+                     np.where(np.arange(bx) % 2 == 0, 0.0, 1.0)])[None]
+    for pol in (P.REMOVE_HIGH, P.REMOVE_LOW):
+        for k in (1, 60, 120, 239):
+            assert np.array_equal(ops.select_rows(to_dev(rows, dev), k, pol).cpu().numpy(), P.select_rows(rows, k, pol))
