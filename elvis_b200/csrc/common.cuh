@@ -52,5 +52,13 @@ template <typename V> __device__ __forceinline__ void st_stream(V* p, V v) { __s
 template <int K> __device__ __forceinline__ float byte_as_biased_float(uint32_t w) {
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 + K));
 }
+// Same, with the 0x4B000000 pattern supplied in a REGISTER (`magic`, a run-time value the
+// assembler cannot fold): PRMT takes one immediate, and with a literal pattern ptxas spends it
+// on the pattern and re-materialises the selector with a MOV before every PRMT.
+template <int K> __device__ __forceinline__ float byte_as_biased_float(uint32_t w, uint32_t magic) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(magic), "n"(0x7540 + K));
+    return __uint_as_float(r);
+}
 
 }  // namespace elvis

@@ -15,22 +15,12 @@
 // (|C_t| - |C_{t-1}| computed from two large fp32 coefficients would not).  Every luma byte is
 // read from HBM once per chunk of frames; a chunk primes its accumulator with one extra
 // transform of the frame before it.
-#include "common.cuh"
+#include "score_params.cuh"
 #include "dct8.cuh"
+#include "dct8_packed.cuh"
+#include <cstring>
 
 namespace elvis {
-
-struct ScoreParams {
-    const uint8_t* y;
-    const uint8_t* halo;
-    int64_t frame_stride, row_stride;
-    int32_t T, By, Bx, tiles_x, chunk_len, n_chunks;
-    float* sc;
-    float* tc;
-    unsigned* mm;   // {sc_min, sc_max, tc_min, tc_max} as float bits (all values are >= +0)
-    int32_t mm_begin, mm_end;
-    float inv_area;
-};
 
 namespace {
 
@@ -39,6 +29,7 @@ __device__ constexpr float kW[8][8] = {
 };
 
 constexpr int kScoreThreads = 128;
+constexpr int kRing = 3;   // cp.async ring depth: two frames in flight ahead of the one being transformed
 
 template <bool ALIGNED>
 __device__ __forceinline__ void load_tile(uint2 (&dst)[8], const uint8_t* p, int64_t row_stride, bool valid) {
@@ -88,35 +79,80 @@ __global__ void __launch_bounds__(kScoreThreads, 2) score_kernel(const ScorePara
         return (t < 0 ? p.halo : p.y + (int64_t)t * p.frame_stride) + tile_off;
     };
 
-    float acc[8][8];
+    // running coefficients C_t, packed over column pairs: acc[u][j] = (C[u][2j], C[u][2j+1])
+    float2 acc[8][4];
 #pragma unroll
     for (int u = 0; u < 8; ++u)
 #pragma unroll
-        for (int v = 0; v < 8; ++v) acc[u][v] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[u][j] = make_float2(0.f, 0.f);
 
-    uint2 cur[8], prv[8], nxt[8];
+    // Luma rows reach the thread through a private 3-slot ring in shared memory filled with
+    // cp.async two frames ahead.  (Prefetching into registers does not survive ptxas: it sinks
+    // the loads to the end of the loop body to save registers, which leaves one frame of
+    // loads in flight per warp and the kernel latency bound -- profiles/r1b.)  Every thread
+    // reads back only what it copied itself, so no barrier is needed, only wait_group.
+    __shared__ uint2 s_ring[kRing][8][kScoreThreads];
+    uint2 cur[8], prv[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) prv[r] = make_uint2(0u, 0u);
-    load_tile<ALIGNED>(cur, frame_ptr(t_start), p.row_stride, valid);
+    auto prefetch = [&](int slot, int t) {
+        if (ALIGNED && valid && t < t1) {
+            const uint8_t* src = frame_ptr(t);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_ring[slot][r][threadIdx.x]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + r * p.row_stride) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");   // always: keeps the group count uniform
+    };
+    if (ALIGNED) {
+        prefetch(0, t_start);
+        prefetch(1, t_start + 1);
+    }
 
     float smin = __int_as_float(0x7f800000), smax = 0.f, tmin = __int_as_float(0x7f800000), tmax = 0.f;
+    const uint32_t magic = p.magic;
 
-    for (int t = t_start; t < t1; ++t) {
-        if (t + 1 < t1) load_tile<ALIGNED>(nxt, frame_ptr(t + 1), p.row_stride, valid);
-
-        float x[8][8];
+    for (int t = t_start, it = 0; t < t1; ++t, ++it) {
+        if (ALIGNED) {
+            prefetch((it + 2) % kRing, t + 2);
+            asm volatile("cp.async.wait_group 2;" ::: "memory");
+            const int slot = it % kRing;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            x[r][0] = byte_as_biased_float<0>(cur[r].x) - byte_as_biased_float<0>(prv[r].x);
-            x[r][1] = byte_as_biased_float<1>(cur[r].x) - byte_as_biased_float<1>(prv[r].x);
-            x[r][2] = byte_as_biased_float<2>(cur[r].x) - byte_as_biased_float<2>(prv[r].x);
-            x[r][3] = byte_as_biased_float<3>(cur[r].x) - byte_as_biased_float<3>(prv[r].x);
-            x[r][4] = byte_as_biased_float<0>(cur[r].y) - byte_as_biased_float<0>(prv[r].y);
-            x[r][5] = byte_as_biased_float<1>(cur[r].y) - byte_as_biased_float<1>(prv[r].y);
-            x[r][6] = byte_as_biased_float<2>(cur[r].y) - byte_as_biased_float<2>(prv[r].y);
-            x[r][7] = byte_as_biased_float<3>(cur[r].y) - byte_as_biased_float<3>(prv[r].y);
+            for (int r = 0; r < 8; ++r) cur[r] = valid ? s_ring[slot][r][threadIdx.x] : make_uint2(0u, 0u);
+        } else {
+            load_tile<false>(cur, frame_ptr(t), p.row_stride, valid);
         }
-        fdct8x8(x);   // x[u][v]: u = vertical frequency, v = horizontal frequency (AAN-scaled)
+
+        // frame difference, packed over ROW pairs: y[i][c] = (d[2i][c], d[2i+1][c]).  The 2^23
+        // bias of the byte->float trick cancels in the subtraction.
+        float2 y[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint2 ca = cur[2 * i], cb = cur[2 * i + 1], pa = prv[2 * i], pb = prv[2 * i + 1];
+#define ELVIS_DIFF(C, K, W)                                                                                   \
+    y[i][C] = f2sub(make_float2(byte_as_biased_float<K>(ca.W, magic), byte_as_biased_float<K>(cb.W, magic)),  \
+                    make_float2(byte_as_biased_float<K>(pa.W, magic), byte_as_biased_float<K>(pb.W, magic)))
+            ELVIS_DIFF(0, 0, x); ELVIS_DIFF(1, 1, x); ELVIS_DIFF(2, 2, x); ELVIS_DIFF(3, 3, x);
+            ELVIS_DIFF(4, 0, y); ELVIS_DIFF(5, 1, y); ELVIS_DIFF(6, 2, y); ELVIS_DIFF(7, 3, y);
+#undef ELVIS_DIFF
+        }
+        // horizontal pass: two rows per instruction
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ELVIS_FDCT8_X2(y[i][0], y[i][1], y[i][2], y[i][3], y[i][4], y[i][5], y[i][6], y[i][7]);
+        // re-pair (2x2 register transposes): x[r][j] = (h[r][2j], h[r][2j+1])
+        float2 x[8][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                x[2 * i][j] = make_float2(y[i][2 * j].x, y[i][2 * j + 1].x);
+                x[2 * i + 1][j] = make_float2(y[i][2 * j].y, y[i][2 * j + 1].y);
+            }
+        // vertical pass: two columns per instruction.  x[u][j] = (dC[u][2j], dC[u][2j+1]), AAN-scaled
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ELVIS_FDCT8_X2(x[0][j], x[1][j], x[2][j], x[3][j], x[4][j], x[5][j], x[6][j], x[7][j]);
 
         // per-row partial sums keep 16 independent FMA chains in flight; fixed order => deterministic
         float s_part[8], d_part[8];
@@ -124,11 +160,14 @@ __global__ void __launch_bounds__(kScoreThreads, 2) score_kernel(const ScorePara
         for (int u = 0; u < 8; ++u) {
             float s = 0.f, d = 0.f;
 #pragma unroll
-            for (int v = 0; v < 8; ++v) {
-                if (u == 0 && v == 0) continue;   // DC carries no texture energy
-                acc[u][v] += x[u][v];
-                s = fmaf(fabsf(acc[u][v]), kW[u][v], s);
-                d = fmaf(fabsf(x[u][v]), kW[u][v], d);
+            for (int j = 0; j < 4; ++j) {
+                acc[u][j] = f2add(acc[u][j], x[u][j]);
+                if (u != 0 || j != 0) {   // DC (u = v = 0) carries no texture energy
+                    s = fmaf(fabsf(acc[u][j].x), kW[u][2 * j], s);
+                    d = fmaf(fabsf(x[u][j].x), kW[u][2 * j], d);
+                }
+                s = fmaf(fabsf(acc[u][j].y), kW[u][2 * j + 1], s);
+                d = fmaf(fabsf(x[u][j].y), kW[u][2 * j + 1], d);
             }
             s_part[u] = s;
             d_part[u] = d;
@@ -162,10 +201,7 @@ __global__ void __launch_bounds__(kScoreThreads, 2) score_kernel(const ScorePara
             }
         }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            prv[r] = cur[r];
-            cur[r] = nxt[r];
-        }
+        for (int r = 0; r < 8; ++r) prv[r] = cur[r];
     }
 
     if (p.mm != nullptr) {
@@ -204,13 +240,24 @@ int launch_score(const ScoreParams& p, bool aligned, cudaStream_t st) {
 
 }  // namespace
 
-// chunking heuristic: enough (tile-group x chunk) units for >= 16 waves of resident warps, but
-// chunks no shorter than 16 frames (each chunk pays one extra priming transform).
-static int pick_chunks(int T, int tile_groups, int override_len) {
+int launch_score_simt(ScoreParams p, int block_size, bool aligned8, cudaStream_t st) {
+    const int R = block_size / 8;
+    const int TW = 32 / R;
+    p.tiles_x = (p.Bx * R + TW - 1) / TW;
+    p.tiles_y = p.By;
+    switch (R) {
+        case 1: return launch_score<1>(p, aligned8, st);
+        case 2: return launch_score<2>(p, aligned8, st);
+        default: return launch_score<4>(p, aligned8, st);
+    }
+}
+
+// chunking heuristic: enough (spatial tile x chunk) work units for >= 16 waves of resident
+// workers, but chunks no shorter than 16 frames (each chunk pays one extra priming transform).
+static int pick_chunks(int T, long tiles, long resident, int override_len) {
     if (override_len > 0) return (T + override_len - 1) / override_len;
-    const int resident_warps = kNumSMs * 2 * (kScoreThreads / 32);
-    const long target = 16L * resident_warps;
-    long n = (target + tile_groups - 1) / tile_groups;
+    const long target = 16L * resident;
+    long n = (target + tiles - 1) / tiles;
     const long max_chunks = (T + 15) / 16;
     if (n > max_chunks) n = max_chunks;
     if (n < 1) n = 1;
@@ -229,8 +276,6 @@ extern "C" int elvis_score_sc_tc(const elvis_plane* y, int32_t n_frames, const u
     if (block_size != 8 && block_size != 16 && block_size != 32) return ELVIS_ERR_UNSUPPORTED;
     const int By = y->height / block_size, Bx = y->width / block_size;
     if (By <= 0 || Bx <= 0) return ELVIS_ERR_SHAPE;
-    const int R = block_size / 8;
-    const int TW = 32 / R;
 
     ScoreParams p;
     p.y = static_cast<const uint8_t*>(y->data);
@@ -240,29 +285,46 @@ extern "C" int elvis_score_sc_tc(const elvis_plane* y, int32_t n_frames, const u
     p.T = n_frames;
     p.By = By;
     p.Bx = Bx;
-    p.tiles_x = (Bx * R + TW - 1) / TW;
-    int override_len = 0;
-    if (const char* e = getenv("ELVIS_SCORE_CHUNK")) override_len = atoi(e);
-    p.n_chunks = pick_chunks(n_frames, By * p.tiles_x, override_len);
-    p.chunk_len = (n_frames + p.n_chunks - 1) / p.n_chunks;
-    p.n_chunks = (n_frames + p.chunk_len - 1) / p.chunk_len;
     p.sc = sc;
     p.tc = tc;
     p.mm = reinterpret_cast<unsigned*>(minmax);
     p.mm_begin = mm_begin;
     p.mm_end = mm_end;
     p.inv_area = 1.0f / (float)(block_size * block_size);
+    p.magic = 0x4B000000u;
+
+    // Implementation choice.  Default: the CUDA-core kernel (packed-fp32 butterflies, cp.async
+    // ring) -- on B200 it is the fastest of the three (profiles/).  ELVIS_SCORE_IMPL = mma | tma
+    // selects the tensor-core kernel with direct loads / with the TMA ring (16x16 blocks, plane
+    // 4- / 16-byte aligned); the tests exercise every path.
+    auto al = [&](int a) {
+        return aligned_to(p.y, a) && p.frame_stride % a == 0 && p.row_stride % a == 0 && (!prev_halo || aligned_to(prev_halo, a));
+    };
+    enum { SIMT, MMA_DIRECT, MMA_TMA } impl = SIMT;
+    if (const char* e = getenv("ELVIS_SCORE_IMPL")) {
+        if (!strcmp(e, "mma") && block_size == 16 && al(4)) impl = MMA_DIRECT;
+        else if (!strcmp(e, "tma") && block_size == 16 && al(16)) impl = MMA_TMA;
+    }
+    int override_len = 0;
+    if (const char* e = getenv("ELVIS_SCORE_CHUNK")) override_len = atoi(e);
+    long tiles, resident;
+    if (impl == SIMT) {
+        const int R = block_size / 8;
+        tiles = (long)By * ((Bx * R * R + 31) / 32);
+        resident = (long)kNumSMs * 8;               // warps
+    } else {
+        tiles = (long)((Bx + 7) / 8) * ((By + 2) / 3);
+        resident = (long)kNumSMs * 2;               // CTAs
+    }
+    p.n_chunks = pick_chunks(n_frames, tiles, resident, override_len);
+    p.chunk_len = (n_frames + p.n_chunks - 1) / p.n_chunks;
+    p.n_chunks = (n_frames + p.chunk_len - 1) / p.chunk_len;
 
     cudaStream_t st = as_stream(stream);
     if (minmax) {
         score_minmax_init<<<1, 32, 0, st>>>(p.mm);
         ELVIS_CHECK_LAUNCH();
     }
-    const bool aligned = aligned_to(p.y, 8) && p.frame_stride % 8 == 0 && p.row_stride % 8 == 0 &&
-                         (prev_halo == nullptr || aligned_to(prev_halo, 8));
-    switch (R) {
-        case 1: return launch_score<1>(p, aligned, st);
-        case 2: return launch_score<2>(p, aligned, st);
-        default: return launch_score<4>(p, aligned, st);
-    }
+    if (impl == SIMT) return launch_score_simt(p, block_size, al(8), st);
+    return launch_score_mma(p, y->height, y->width, impl == MMA_TMA, st);
 }

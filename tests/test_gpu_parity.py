@@ -346,3 +346,43 @@ def test_select_rows_sorted_and_adversarial_rows(dev):
     for pol in (P.REMOVE_HIGH, P.REMOVE_LOW):
         for k in (1, 60, 120, 239):
             assert np.array_equal(ops.select_rows(to_dev(rows, dev), k, pol).cpu().numpy(), P.select_rows(rows, k, pol))
+
+
+@pytest.mark.parametrize("impl", ["simt", "mma", "tma"])
+@pytest.mark.parametrize("H,W,T", [(48, 128, 5), (64, 96, 7), (112, 400, 9), (1080, 1920, 3), (16, 16, 2)])
+def test_score_impls_agree_with_spec(dev, monkeypatch, impl, H, W, T):
+    """The CUDA-core kernel, the tensor-core kernel with direct loads and the tensor-core
+    kernel fed by TMA must all match the spec (16x16 blocks; edge tiles, partial block rows)."""
+    from elvis_b200 import ops
+    monkeypatch.setenv("ELVIS_SCORE_IMPL", impl)
+    monkeypatch.setenv("ELVIS_SCORE_CHUNK", "4")
+    y = synth_luma(T, H, W, seed=H + W + T)
+    rng = np.random.default_rng(T)
+    y[-1] = rng.integers(0, 256, (H, W), dtype=np.uint8)      # full-range noise frame
+    yd = to_dev(y, dev)
+    sc, tc, mm = ops.score_sc_tc(yd, 16)
+    rsc, rtc = spec_scoring.sc_tc(y, 16)
+    np.testing.assert_allclose(sc.cpu().numpy(), rsc, rtol=RTOL, atol=0)
+    np.testing.assert_allclose(tc.cpu().numpy(), rtc, rtol=RTOL, atol=0)
+    s, t = sc.cpu().numpy(), tc.cpu().numpy()
+    assert mm.cpu().numpy().tolist() == [s.min(), s.max(), t.min(), t.max()]
+    if T > 2:
+        sch, tch, _ = ops.score_sc_tc(yd[2:], 16, prev_halo=yd[1])
+        rsc_h, rtc_h = spec_scoring.sc_tc(y[2:], 16, prev=y[1])
+        np.testing.assert_allclose(sch.cpu().numpy(), rsc_h, rtol=RTOL, atol=0)
+        np.testing.assert_allclose(tch.cpu().numpy(), rtc_h, rtol=RTOL, atol=0)
+
+
+def test_score_tightness(dev, monkeypatch):
+    """Report (and bound) the actual relative error of each implementation: far below RTOL."""
+    from elvis_b200 import ops
+    y = synth_luma(12, 96, 256, seed=77)
+    rsc, rtc = spec_scoring.sc_tc(y, 16)
+    for impl in ("simt", "mma", "tma"):
+        monkeypatch.setenv("ELVIS_SCORE_IMPL", impl)
+        sc, tc, _ = ops.score_sc_tc(to_dev(y, dev), 16)
+        e_sc = np.abs(sc.cpu().numpy() - rsc).max() / np.abs(rsc).max()
+        nz = rtc > 0
+        e_tc = (np.abs(tc.cpu().numpy() - rtc)[nz] / rtc[nz]).max()
+        print(f"{impl}: max rel err SC {e_sc:.2e} TC {e_tc:.2e}")
+        assert e_sc < 2e-5 and e_tc < 2e-5
