@@ -1,0 +1,93 @@
+"""Freeze golden input/output vectors from the UNMODIFIED reference (imported from
+/root/reference through oracle/ref_import.py; calculate_removability_scores is driven with
+EVCA/UFO faked, see tests/_ref_drive.py).  Run in the build container:
+
+    python tests/golden/gen_golden.py
+
+Library versions of the run are recorded in the file (the reference pins numpy<2 and
+opencv-python 4.8.0.76; this image has numpy 2.3 / cv2 4.13)."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+from _ref_drive import run_reference_removability  # noqa: E402
+from oracle import ref_import  # noqa: E402
+
+
+def main():
+    import cv2
+    E, U = ref_import.load("elvis"), ref_import.load("utils")
+    rng = np.random.default_rng(20260101)
+    g = {"versions": np.array([np.__version__, cv2.__version__])}
+
+    # a2 -- in-tree tail of calculate_removability_scores
+    T, By, Bx = 5, 4, 6
+    sc, tc = rng.random((T, By, Bx)) * 60, rng.random((T, By, Bx)) * 30
+    tc[0] = 0
+    fg = (rng.random((T, By, Bx)) > 0.4).astype(np.uint8) * 255
+    g.update(a2_sc=sc, a2_tc=tc, a2_fg=fg)
+    for tag, beta, masks in (("b1", 1, None), ("b05", 0.5, None), ("b05m", 0.5, fg), ("b025m", 0.25, fg)):
+        g[f"a2_out_{tag}"] = run_reference_removability(sc, tc, masks, 0.3, beta, 16)
+
+    # a3 -- calculate_importance_scores
+    class Cx:
+        pass
+    cx = Cx()
+    cx.SC, cx.TC = sc, tc
+    fgf = rng.random((T, By, Bx))
+    g["a3_fg"] = fgf
+    g["a3_out"] = np.stack(U.calculate_importance_scores(None, 16, 0.3, 0.6, cx, fgf))
+
+    # a4 / a5 -- elvis shrink + stretch
+    img = rng.integers(0, 256, (32, 48, 3), dtype=np.uint8)
+    scores = rng.random((4, 6))
+    g.update(a4_img=img, a4_scores=scores)
+    for tag, bs, amount in (("s25", 8, 0.25), ("s50", 8, 0.5), ("n2", 8, 2)):
+        s8 = rng.random((32 // bs, 48 // bs))
+        g[f"a4_scores_{tag}"] = s8
+        small, mask, _ = E.apply_selective_removal(img, s8, bs, amount)
+        g[f"a4_small_{tag}"], g[f"a4_mask_{tag}"] = small, mask
+        g[f"a5_full_{tag}"] = E.stretch_frame(small, mask, bs)
+
+    # a6 / a7 -- utils row-only shrink (incl. the partial-last-pass quirk) + stretch
+    img2 = rng.integers(0, 256, (43, 67, 3), dtype=np.uint8)
+    g["a6_img"] = img2
+    for tag, amount in (("q30", 0.3), ("q50", 0.5)):
+        imp = np.round(rng.random((5, 8)) * 8) / 8      # ties on purpose
+        g[f"a6_imp_{tag}"] = imp
+        small, mask = U.shrink_frame_row_only(img2, imp, 8, amount)
+        g[f"a6_small_{tag}"], g[f"a6_mask_{tag}"] = small, mask
+        g[f"a7_full_{tag}"] = U.stretch_frame_row_only(small, mask, 8)
+
+    # a8 / a9 -- elvis filters; a10 / a11 -- utils degradations (with crop)
+    for bs in (8, 16):
+        im = rng.integers(0, 256, (bs * 3, bs * 4, 3), dtype=np.uint8)
+        s = rng.random((3, 4))
+        s[0, :4] = [0.5, 0.125, 1.0, 0.0]
+        g[f"a8_img_{bs}"], g[f"a8_scores_{bs}"] = im, s
+        g[f"a8_out_{bs}"], g[f"a8_map_{bs}"] = E.filter_frame_downsample(im, s, bs)
+        g[f"a9_out_{bs}"], g[f"a9_map_{bs}"] = E.filter_frame_gaussian(im, s, bs)
+        im2 = rng.integers(0, 256, (bs * 3 + 3, bs * 4 + 5, 3), dtype=np.uint8)
+        g[f"a10_img_{bs}"] = im2
+        g[f"a10_out_{bs}"], g[f"a10_map_{bs}"] = U.degrade_adaptive_downsample(im2, s, bs)
+        g[f"a11_out_{bs}"], g[f"a11_map_{bs}"] = U.degrade_adaptive_blur(im2, s, bs)
+
+    # a13 -- mask side channel (elvis.py:4412-4418)
+    masks = (rng.random((3, 5, 7)) > 0.5).astype(np.int8)
+    g["a13_masks"] = masks
+    g["a13_packed"] = np.packbits(masks.astype(np.uint8))
+
+    out = os.path.join(HERE, "reference_vectors.npz")
+    np.savez_compressed(out, **g)
+    print(f"wrote {out}: {len(g)} arrays, {os.path.getsize(out) / 1024:.1f} KiB")
+
+
+if __name__ == "__main__":
+    main()

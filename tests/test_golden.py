@@ -1,0 +1,93 @@
+"""Golden vectors frozen from the unmodified reference (tests/golden/gen_golden.py):
+  * CPU: the oracle port reproduces them bit for bit (pins the oracle);
+  * GPU (-m gpu): the CUDA path, called through the reference-signature mirrors, reproduces
+    them bit for bit."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_port as P
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+
+
+class _Impl:
+    """Uniform view over the oracle port and the CUDA mirrors."""
+
+    def __init__(self, kind):
+        self.kind = kind
+        if kind == "gpu":
+            import torch
+            assert torch.cuda.is_available()
+            from elvis_b200 import elvis, utils
+            self.E, self.U = elvis, utils
+
+    def removability(self, sc, tc, alpha, beta, bg):
+        if self.kind == "gpu":
+            return self.E.removability_from_features(sc, tc, alpha, beta, bg)
+        return P.combine_removability(sc, tc, alpha, beta, bg)
+
+    def importance(self, sc, tc, alpha, beta, fg):
+        if self.kind == "gpu":
+            class Cx:
+                pass
+            cx = Cx()
+            cx.SC, cx.TC = sc, tc
+            return np.stack(self.U.calculate_importance_scores(None, 16, alpha, beta, cx, fg))
+        return P.importance_scores(sc, tc, alpha, beta, fg)
+
+    def __getattr__(self, name):
+        if self.kind == "gpu":
+            mod = self.E if hasattr(self.E, name) else self.U
+            return getattr(mod, name)
+        return getattr(P, name)
+
+
+def _check_all(impl):
+    sc, tc, fg = G["a2_sc"], G["a2_tc"], G["a2_fg"]
+    for tag, beta, m in (("b1", 1, None), ("b05", 0.5, None), ("b05m", 0.5, fg), ("b025m", 0.25, fg)):
+        got = impl.removability(sc, tc, 0.3, beta, None if m is None else m == 0)
+        assert np.array_equal(got, G[f"a2_out_{tag}"]), tag
+    assert np.array_equal(impl.importance(sc, tc, 0.3, 0.6, G["a3_fg"]), G["a3_out"])
+
+    img = G["a4_img"]
+    for tag, bs, amount in (("s25", 8, 0.25), ("s50", 8, 0.5), ("n2", 8, 2)):
+        small, mask, coords = impl.apply_selective_removal(img, G[f"a4_scores_{tag}"], bs, amount)
+        assert small.dtype == np.uint8 and np.array_equal(small, G[f"a4_small_{tag}"]), tag
+        assert mask.dtype == np.int8 and np.array_equal(mask, G[f"a4_mask_{tag}"]), tag
+        assert coords == [np.flatnonzero(r).tolist() for r in G[f"a4_mask_{tag}"]]
+        assert np.array_equal(impl.stretch_frame(small, mask, bs), G[f"a5_full_{tag}"]), tag
+
+    for tag, amount in (("q30", 0.3), ("q50", 0.5)):
+        small, mask = impl.shrink_frame_row_only(G["a6_img"], G[f"a6_imp_{tag}"], 8, amount)
+        assert mask.dtype == bool and np.array_equal(mask, G[f"a6_mask_{tag}"]), tag
+        assert np.array_equal(small, G[f"a6_small_{tag}"]), tag
+        assert np.array_equal(impl.stretch_frame_row_only(small, mask, 8), G[f"a7_full_{tag}"]), tag
+
+    for bs in (8, 16):
+        s = G[f"a8_scores_{bs}"]
+        for fn, key in (("filter_frame_downsample", "a8"), ("filter_frame_gaussian", "a9")):
+            out, lv = getattr(impl, fn)(G[f"a8_img_{bs}"], s, bs)
+            assert lv.dtype == np.int32 and np.array_equal(lv, G[f"{key}_map_{bs}"]), (fn, bs)
+            assert np.array_equal(out, G[f"{key}_out_{bs}"]), (fn, bs)
+        for fn, key in (("degrade_adaptive_downsample", "a10"), ("degrade_adaptive_blur", "a11")):
+            out, lv = getattr(impl, fn)(G[f"a10_img_{bs}"], s, bs)
+            assert np.array_equal(lv, G[f"{key}_map_{bs}"]), (fn, bs)
+            assert np.array_equal(out, G[f"{key}_out_{bs}"]), (fn, bs)
+
+
+def test_oracle_reproduces_golden_vectors():
+    _check_all(_Impl("oracle"))
+    packed, shape = P.pack_masks(G["a13_masks"])
+    assert np.array_equal(packed, G["a13_packed"])
+    assert np.array_equal(P.unpack_masks(packed, shape), G["a13_masks"])
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_golden_vectors():
+    impl = _Impl("gpu")
+    _check_all(impl)
+    packed, shape = impl.E.pack_removal_masks(G["a13_masks"])
+    assert np.array_equal(packed, G["a13_packed"])
+    assert np.array_equal(impl.E.unpack_removal_masks(packed, shape), G["a13_masks"])

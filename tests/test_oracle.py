@@ -1,0 +1,172 @@
+"""Pins the oracle (CPU only): spec_cv against the real cv2 of the image, ref_port against
+the unmodified reference modules when the reference tree is present (build container), the
+coefficient tables against spec_cv, and domain properties with hypothesis."""
+import numpy as np
+import pytest
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from oracle import ref_import
+from oracle import ref_port as P
+from oracle import spec_cv, spec_dct_dampen, spec_scoring
+
+cv2 = pytest.importorskip("cv2")
+needs_reference = pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+
+
+def _blocks(rng, bs, n):
+    out = []
+    for i in range(n):
+        k = i % 3
+        if k == 0:
+            out.append(rng.integers(0, 256, (bs, bs), dtype=np.uint8))
+        elif k == 1:
+            out.append((rng.integers(0, 2, (bs, bs)) * 255).astype(np.uint8))
+        else:
+            out.append(np.clip(rng.normal(128, 20, (bs, bs)), 0, 255).astype(np.uint8))
+    return out
+
+
+@pytest.mark.parametrize("bs", [4, 8, 16, 32, 12, 20])
+def test_spec_cv_bit_exact_vs_cv2(bs):
+    rng = np.random.default_rng(bs)
+    for b in _blocks(rng, bs, 24):
+        ref = mine = b
+        for _ in range(3):
+            ref = cv2.GaussianBlur(ref, (5, 5), sigmaX=1.0)
+            mine = spec_cv.gaussian_blur5(mine)
+            assert np.array_equal(ref, mine)
+        for small in sorted({max(1, bs // k) for k in (1, 2, 3, 4, 5, 8, 16)}):
+            ra = cv2.resize(b, (small, small), interpolation=cv2.INTER_AREA)
+            assert np.array_equal(ra, spec_cv.resize_area(b, small)), (bs, small)
+            ru = cv2.resize(ra, (bs, bs), interpolation=cv2.INTER_LINEAR)
+            assert np.array_equal(ru, spec_cv.resize_linear(ra, bs)), (bs, small)
+
+
+def test_spec_cv_channels_are_independent():
+    rng = np.random.default_rng(0)
+    blk = rng.integers(0, 256, (16, 16, 3), dtype=np.uint8)
+    r3 = cv2.GaussianBlur(blk, (5, 5), sigmaX=1.0)
+    assert np.array_equal(r3, np.stack([spec_cv.gaussian_blur5(blk[..., c]) for c in range(3)], -1))
+    for small in (8, 5, 4, 1):
+        r3 = cv2.resize(cv2.resize(blk, (small, small), interpolation=cv2.INTER_AREA), (16, 16), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(r3, np.stack([spec_cv.down_up(blk[..., c], small) for c in range(3)], -1))
+
+
+def test_tables_match_spec_cv():
+    from elvis_b200 import _tables as T
+    for pb in (4, 8, 16, 32, 12, 20):
+        for small in range(1, pb):
+            for h in (True, False):
+                assert all(np.array_equal(a, b) for a, b in zip(T._linear_taps(small, pb, h), spec_cv.linear_coeffs(small, pb, h)))
+            if pb % small:
+                start, src, alpha = T._area_entries(pb, small)
+                tab = spec_cv.area_table(pb, small)
+                assert [t[0] for t in tab] == src.tolist()
+                assert np.array_equal(np.array([t[2] for t in tab], np.float32), alpha)
+                assert [t[1] for t in tab] == [d for d in range(small) for _ in range(start[d + 1] - start[d])]
+
+
+@needs_reference
+def test_port_matches_reference_v1():
+    E, U = ref_import.load("elvis"), ref_import.load("utils")
+    rng = np.random.default_rng(1)
+    for (H, W, bs, sh) in [(64, 96, 16, 0.5), (48, 80, 8, 0.25), (32, 64, 16, 3), (32, 64, 16, 0.0), (32, 64, 16, 0.999)]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        sc = rng.random((H // bs, W // bs))
+        r, m = E.apply_selective_removal(img, sc, bs, sh), P.apply_selective_removal(img, sc, bs, sh)
+        assert np.array_equal(r[0], m[0]) and np.array_equal(r[1], m[1]) and r[1].dtype == m[1].dtype and r[2] == m[2]
+        assert np.array_equal(E.stretch_frame(r[0], r[1], bs), P.stretch_frame(m[0], m[1], bs))
+    for (H, W, bs, sh) in [(64, 96, 16, 0.5), (50, 85, 8, 0.25), (80, 128, 16, 0.3), (80, 128, 16, 0.0), (80, 128, 16, 0.99), (40, 64, 8, 0.3)]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        imp = np.round(rng.random((H // bs, W // bs)) * 8) / 8
+        r, m = U.shrink_frame_row_only(img, imp, bs, sh), P.shrink_frame_row_only(img, imp, bs, sh)
+        assert np.array_equal(r[1], m[1]) and np.array_equal(r[0], m[0])
+        assert np.array_equal(U.stretch_frame_row_only(r[0], r[1], bs), P.stretch_frame_row_only(m[0], m[1], bs))
+
+
+@needs_reference
+def test_port_matches_reference_v2_and_scores():
+    from _ref_drive import run_reference_removability
+    E, U = ref_import.load("elvis"), ref_import.load("utils")
+    rng = np.random.default_rng(2)
+    for bs in (8, 16):
+        img = rng.integers(0, 256, (bs * 4, bs * 5, 3), dtype=np.uint8)
+        sc = rng.random((4, 5))
+        sc[0, :4] = [0.5, 0.125, 1.0, 0.0]
+        for fn in ("filter_frame_downsample", "filter_frame_gaussian"):
+            r, m = getattr(E, fn)(img, sc, bs), getattr(P, fn)(img, sc, bs)
+            assert np.array_equal(r[0], m[0]) and np.array_equal(r[1], m[1]) and r[1].dtype == m[1].dtype
+        img2 = rng.integers(0, 256, (bs * 4 + 3, bs * 5 + 5, 3), dtype=np.uint8)
+        for fn in ("degrade_adaptive_downsample", "degrade_adaptive_blur"):
+            r, m = getattr(U, fn)(img2, sc, bs), getattr(P, fn)(img2, sc, bs)
+            assert np.array_equal(r[0], m[0]) and np.array_equal(r[1], m[1])
+    T, By, Bx = 6, 5, 9
+    s, t = rng.random((T, By, Bx)) * 60, rng.random((T, By, Bx)) * 30
+    t[0] = 0
+    fg = (rng.random((T, By, Bx)) > 0.4).astype(np.uint8) * 255
+    for beta in (1, 0.5):
+        for m in (None, fg):
+            ref = run_reference_removability(s, t, m, 0.3, beta, 16)
+            assert np.array_equal(ref, P.combine_removability(s, t, 0.3, beta, None if m is None else m == 0))
+
+    class Cx:
+        pass
+    cx = Cx()
+    cx.SC, cx.TC = s, t
+    f = rng.random((T, By, Bx))
+    assert np.array_equal(np.stack(U.calculate_importance_scores(None, 16, 0.3, 0.6, cx, f)), P.importance_scores(s, t, 0.3, 0.6, f))
+
+
+# ---------------------------------------------------------------------------- properties
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 6), st.integers(2, 12), st.sampled_from([4, 8, 16]), st.floats(0, 0.99), st.integers(0, 2 ** 31))
+def test_shrink_stretch_round_trip(by, bx, bs, amount, seed):
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (by * bs, bx * bs, 3), dtype=np.uint8)
+    scores = np.round(rng.random((by, bx)) * 5) / 5
+    small, mask, coords = P.apply_selective_removal(img, scores, bs, amount)
+    k = P.blocks_to_remove_elvis(amount, bx)
+    assert (mask.sum(axis=1) == k).all() and small.shape == (by * bs, (bx - k) * bs, 3)
+    full = P.stretch_frame(small, mask, bs)
+    keep = np.kron(1 - mask, np.ones((bs, bs), np.int8)).astype(bool)
+    assert np.array_equal(full[keep], img[keep]) and not full[~keep].any()
+    # the removed set is the stable top-k
+    for j in range(by):
+        assert coords[j] == sorted(np.argsort(-scores[j], kind="stable")[:k].tolist())
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.integers(1, 7), st.integers(2, 12), st.floats(0, 0.99))
+def test_row_only_plan_counts(by, bx, amount):
+    k, out_bx = P.row_only_plan(by, bx, amount)
+    target = int(by * bx * amount)
+    assert k.sum() == min(target, by * (bx - 1)) and out_bx == bx - k.max() and k.max() - k.min() <= 1
+
+
+def test_level_rules_and_2bit_packing():
+    s = np.array([[0.0, 0.125, 0.5, 0.375, 0.625, 1.0]])
+    assert P.levels_elvis_downsample(s, 16).tolist() == [[0, 0, 2, 2, 2, 4]]       # round half to even
+    assert P.levels_elvis_blur(np.array([0.05, 0.15, 0.25])).tolist() == [0, 2, 2]
+    assert P.levels_utils_downsample(np.array([1.0, 0.74, 0.5, 0.26, 0.0])).tolist() == [0, 2, 3, 3, 4]
+    rng = np.random.default_rng(0)
+    lv = rng.integers(0, 4, (2, 3, 13))
+    packed = P.pack_levels_2bit(lv)
+    assert packed.shape == (2, 3, 4) and np.array_equal(P.unpack_levels_2bit(packed, 13), lv)
+    with pytest.raises(ValueError):
+        P.pack_levels_2bit(np.array([[4]]))
+
+
+def test_scoring_spec_properties():
+    rng = np.random.default_rng(3)
+    y = rng.integers(0, 256, (4, 32, 48), dtype=np.uint8)
+    y[2] = y[1]
+    sc, tc = spec_scoring.sc_tc(y, 16)
+    assert np.all(tc[0] == 0) and np.all(tc[2] == 0) and np.all(sc >= 0)
+    flat = np.full((2, 16, 16), 77, np.uint8)
+    s2, t2 = spec_scoring.sc_tc(flat, 16)
+    assert np.allclose(s2, 0, atol=1e-9) and np.all(t2 == 0)      # DC carries no energy
+    s3, t3 = spec_scoring.sc_tc(y[1:], 16, prev=y[0])
+    assert np.allclose(t3, tc[1:]) and np.allclose(s3, sc[1:])
+    p = y[0]
+    assert np.array_equal(spec_dct_dampen.dampen_plane(p, np.zeros((2, 3)), 16), p)
