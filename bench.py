@@ -89,6 +89,10 @@ class ClockSampler:
                 pass
             time.sleep(0.002)
 
+    def reset(self):
+        """Drop the samples taken so far (warm-up); called right before the timed region."""
+        self.sm, self.bits = [], 0
+
     def stop(self):
         if not self.thread:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -186,10 +190,12 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None   # NVML init happens here, before the barrier
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.reset()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
