@@ -24,6 +24,7 @@ struct MoveParams {
     int32_t bh;              // pixel rows per block
     int32_t upb;             // vector units per block row (block_px * channels / sizeof(V))
     int32_t tx_dim, ty_dim;  // thread tile: tx over destination units, ty over pixel rows
+    int32_t n_units;         // T * By (frame, block-row) units, grid-strided
 };
 
 template <typename V> __device__ __forceinline__ V zero_v();
@@ -71,50 +72,56 @@ __device__ __forceinline__ void build_map(const uint8_t* __restrict__ mrow, int 
 template <typename V, bool STRETCH>
 __global__ void __launch_bounds__(kThreads) move_blocks_kernel(const MoveParams p) {
     extern __shared__ int16_t s_map[];
-    const int t = blockIdx.x / p.By;
-    const int by = blockIdx.x - t * p.By;
-    build_map<STRETCH>(p.mask + ((int64_t)t * p.By + by) * p.Bx, p.Bx, p.small_bx, s_map);
-
     const int tx = threadIdx.x % p.tx_dim, ty = threadIdx.x / p.tx_dim;
-    if (ty >= p.ty_dim) return;
     const int dst_blocks = STRETCH ? p.Bx : p.small_bx;
     const int cols = dst_blocks * p.upb;
     const int64_t srow = p.src_row / (int64_t)sizeof(V), drow = p.dst_row / (int64_t)sizeof(V);
-    const V* sbase = reinterpret_cast<const V*>(p.src + (int64_t)t * p.src_frame + (int64_t)by * p.bh * p.src_row);
-    V* dbase = reinterpret_cast<V*>(p.dst + (int64_t)t * p.dst_frame + (int64_t)by * p.bh * p.dst_row);
 
-    for (int c = tx; c < cols; c += p.tx_dim) {
-        const int j = c / p.upb;
-        const int u = c - j * p.upb;
-        const int sj = s_map[j];
-        const V* sp = sbase + (sj < 0 ? 0 : sj * p.upb + u);
-        V* dp = dbase + c;
-        int r = ty;
-        // four rows in flight per thread: all loads issued before the stores
-        for (; r + 3 * p.ty_dim < p.bh; r += 4 * p.ty_dim) {
-            V v0 = zero_v<V>(), v1 = zero_v<V>(), v2 = zero_v<V>(), v3 = zero_v<V>();
-            if (sj >= 0) {
-                v0 = ld_stream(sp + (int64_t)r * srow);
-                v1 = ld_stream(sp + (int64_t)(r + p.ty_dim) * srow);
-                v2 = ld_stream(sp + (int64_t)(r + 2 * p.ty_dim) * srow);
-                v3 = ld_stream(sp + (int64_t)(r + 3 * p.ty_dim) * srow);
+    // grid-stride over (frame, block-row) units: the default grid has one CTA per unit; a capped
+    // grid (tuning knob) keeps the kernel's footprint per SM fixed so that it can share the SMs
+    // with the scoring kernel of the next clip
+    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+        const int t = unit / p.By;
+        const int by = unit - t * p.By;
+        build_map<STRETCH>(p.mask + ((int64_t)t * p.By + by) * p.Bx, p.Bx, p.small_bx, s_map);
+        if (ty < p.ty_dim) {
+            const V* sbase = reinterpret_cast<const V*>(p.src + (int64_t)t * p.src_frame + (int64_t)by * p.bh * p.src_row);
+            V* dbase = reinterpret_cast<V*>(p.dst + (int64_t)t * p.dst_frame + (int64_t)by * p.bh * p.dst_row);
+            for (int c = tx; c < cols; c += p.tx_dim) {
+                const int j = c / p.upb;
+                const int u = c - j * p.upb;
+                const int sj = s_map[j];
+                const V* sp = sbase + (sj < 0 ? 0 : sj * p.upb + u);
+                V* dp = dbase + c;
+                int r = ty;
+                // four rows in flight per thread: all loads issued before the stores
+                for (; r + 3 * p.ty_dim < p.bh; r += 4 * p.ty_dim) {
+                    V v0 = zero_v<V>(), v1 = zero_v<V>(), v2 = zero_v<V>(), v3 = zero_v<V>();
+                    if (sj >= 0) {
+                        v0 = ld_stream(sp + (int64_t)r * srow);
+                        v1 = ld_stream(sp + (int64_t)(r + p.ty_dim) * srow);
+                        v2 = ld_stream(sp + (int64_t)(r + 2 * p.ty_dim) * srow);
+                        v3 = ld_stream(sp + (int64_t)(r + 3 * p.ty_dim) * srow);
+                    }
+                    st_stream(dp + (int64_t)r * drow, v0);
+                    st_stream(dp + (int64_t)(r + p.ty_dim) * drow, v1);
+                    st_stream(dp + (int64_t)(r + 2 * p.ty_dim) * drow, v2);
+                    st_stream(dp + (int64_t)(r + 3 * p.ty_dim) * drow, v3);
+                }
+                for (; r < p.bh; r += p.ty_dim) {
+                    V v = zero_v<V>();
+                    if (sj >= 0) v = ld_stream(sp + (int64_t)r * srow);
+                    st_stream(dp + (int64_t)r * drow, v);
+                }
             }
-            st_stream(dp + (int64_t)r * drow, v0);
-            st_stream(dp + (int64_t)(r + p.ty_dim) * drow, v1);
-            st_stream(dp + (int64_t)(r + 2 * p.ty_dim) * drow, v2);
-            st_stream(dp + (int64_t)(r + 3 * p.ty_dim) * drow, v3);
         }
-        for (; r < p.bh; r += p.ty_dim) {
-            V v = zero_v<V>();
-            if (sj >= 0) v = ld_stream(sp + (int64_t)r * srow);
-            st_stream(dp + (int64_t)r * drow, v);
-        }
+        __syncthreads();   // the column map is rebuilt for the next unit
     }
 }
 
 template <bool STRETCH>
 int launch_move(const elvis_plane* src, const elvis_plane* dst, int T, int block_px, int By, int Bx, int small_bx,
-                const uint8_t* mask, cudaStream_t st) {
+                const uint8_t* mask, int ctas_per_sm, cudaStream_t st) {
     const elvis_plane* full = STRETCH ? dst : src;
     const elvis_plane* small = STRETCH ? src : dst;
     if (!plane_ok(src) || !plane_ok(dst) || !mask || T <= 0 || block_px <= 0 || By <= 0 || Bx <= 0 || small_bx < 0)
@@ -151,7 +158,9 @@ int launch_move(const elvis_plane* src, const elvis_plane* dst, int T, int block
     if (p.ty_dim > block_px) p.ty_dim = block_px;
 
     const size_t smem = sizeof(int16_t) * (size_t)(Bx > small_bx ? Bx : small_bx);
-    const unsigned grid = (unsigned)((int64_t)T * By);
+    p.n_units = (int)((int64_t)T * By);
+    unsigned grid = (unsigned)p.n_units;
+    if (ctas_per_sm > 0 && (unsigned)(ctas_per_sm * kNumSMs) < grid) grid = (unsigned)(ctas_per_sm * kNumSMs);
     switch (unit) {
         case 16: move_blocks_kernel<uint4, STRETCH><<<grid, kThreads, smem, st>>>(p); break;
         case 8: move_blocks_kernel<uint2, STRETCH><<<grid, kThreads, smem, st>>>(p); break;
@@ -168,12 +177,12 @@ int launch_move(const elvis_plane* src, const elvis_plane* dst, int T, int block
 
 extern "C" int elvis_shrink(const elvis_plane* src, const elvis_plane* dst, int32_t n_frames,
                             int32_t block_px, int32_t by, int32_t bx, int32_t out_bx,
-                            const uint8_t* mask, elvis_stream_t stream) {
-    return elvis::launch_move<false>(src, dst, n_frames, block_px, by, bx, out_bx, mask, elvis::as_stream(stream));
+                            const uint8_t* mask, int32_t ctas_per_sm, elvis_stream_t stream) {
+    return elvis::launch_move<false>(src, dst, n_frames, block_px, by, bx, out_bx, mask, ctas_per_sm, elvis::as_stream(stream));
 }
 
 extern "C" int elvis_stretch(const elvis_plane* src, const elvis_plane* dst, int32_t n_frames,
                              int32_t block_px, int32_t by, int32_t bx, int32_t shrunk_bx,
-                             const uint8_t* mask, elvis_stream_t stream) {
-    return elvis::launch_move<true>(src, dst, n_frames, block_px, by, bx, shrunk_bx, mask, elvis::as_stream(stream));
+                             const uint8_t* mask, int32_t ctas_per_sm, elvis_stream_t stream) {
+    return elvis::launch_move<true>(src, dst, n_frames, block_px, by, bx, shrunk_bx, mask, ctas_per_sm, elvis::as_stream(stream));
 }

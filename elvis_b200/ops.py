@@ -66,7 +66,7 @@ def _float_dtype(t: torch.Tensor, name: str) -> int:
 
 # ------------------------------------------------------------------------------ a1
 def score_sc_tc(y: torch.Tensor, block_size: int, prev_halo: torch.Tensor | None = None, dct_size: int = 8,
-                minmax_range: tuple | None = None):
+                minmax_range: tuple | None = None, out: tuple | None = None):
     """SC/TC of a (T, H, W) luma clip -> (sc, tc, minmax): float32 (T, By, Bx) each and a
     float32[4] {sc_min, sc_max, tc_min, tc_max} over frames minmax_range (default: all)."""
     pl = plane_of(y, "y")
@@ -78,9 +78,14 @@ def score_sc_tc(y: torch.Tensor, block_size: int, prev_halo: torch.Tensor | None
         _check_cuda(prev_halo, torch.uint8, "prev_halo")
         if prev_halo.shape != y.shape[1:] or prev_halo.stride() != y.stride()[1:]:
             prev_halo = _match_halo(prev_halo, y)
-    sc = torch.empty((T, by, bx), dtype=torch.float32, device=y.device)
-    tc = torch.empty_like(sc)
-    mm = torch.empty(4, dtype=torch.float32, device=y.device)
+    if out is None:
+        sc = torch.empty((T, by, bx), dtype=torch.float32, device=y.device)
+        tc = torch.empty_like(sc)
+        mm = torch.empty(4, dtype=torch.float32, device=y.device)
+    else:   # caller-owned (T', By, Bx) float32 buffers with T' >= T, and a float32[4]
+        sc, tc, mm = out[0][:T], out[1][:T], out[2]
+        if sc.shape != (T, by, bx) or tc.shape != sc.shape or not (sc.is_contiguous() and tc.is_contiguous()):
+            raise ValueError("out buffers must be contiguous (T, By, Bx) float32")
     lo, hi = (0, T) if minmax_range is None else minmax_range
     call("elvis_score_sc_tc", C.byref(pl), T, _ptr(prev_halo), block_size, dct_size, _ptr(sc), _ptr(tc), _ptr(mm),
          lo, hi, _stream())
@@ -106,7 +111,8 @@ def minmax(x: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------ a2
 def combine_removability(sc: torch.Tensor, tc: torch.Tensor, norm: torch.Tensor, alpha: float, beta: float,
                          background: torch.Tensor | None = None, t_begin: int = 0, t_count: int | None = None,
-                         is_first: bool = True, is_last: bool = True, clip_frames: int | None = None):
+                         is_first: bool = True, is_last: bool = True, clip_frames: int | None = None,
+                         out: tuple | None = None):
     """Un-normalised smoothed removability of frames [t_begin, t_begin + t_count) plus its
     {min, max} (float64[2]).  clip_frames = length of the whole clip (for the reference's
     `shape[0] >= 2` smoothing condition); defaults to the local length."""
@@ -122,8 +128,13 @@ def combine_removability(sc: torch.Tensor, tc: torch.Tensor, norm: torch.Tensor,
         _check_cuda(background, torch.uint8, "background")
         if background.shape != sc.shape or not background.is_contiguous():
             raise ValueError("background must be contiguous (T, By, Bx) uint8")
-    out = torch.empty((t_count, by, bx), dtype=torch.float64, device=sc.device)
-    mm = torch.empty(2, dtype=torch.float64, device=sc.device)
+    if out is None:
+        out = torch.empty((t_count, by, bx), dtype=torch.float64, device=sc.device)
+        mm = torch.empty(2, dtype=torch.float64, device=sc.device)
+    else:
+        out, mm = out
+        if out.shape != (t_count, by, bx) or not out.is_contiguous() or out.dtype != torch.float64:
+            raise ValueError("out must be contiguous (t_count, By, Bx) float64")
     smooth = int(beta < 1 and clip_frames >= 2)
     call("elvis_combine_removability", _ptr(sc), _ptr(tc), dt, _ptr(norm), t_ext, by, bx, t_begin, t_count,
          int(is_first), int(is_last), _ptr(background), float(alpha), float(beta), smooth, _ptr(out), _ptr(mm), _stream())
@@ -158,13 +169,15 @@ def importance_scores(sc: torch.Tensor, tc: torch.Tensor, foreground: torch.Tens
 
 
 # ------------------------------------------------------------------------------ a4-a7
-def select_rows(scores: torch.Tensor, k, polarity: int = REMOVE_HIGH) -> torch.Tensor:
+def select_rows(scores: torch.Tensor, k, polarity: int = REMOVE_HIGH, out: torch.Tensor | None = None) -> torch.Tensor:
     """(T, By, Bx) float64 -> uint8 mask, 1 = removed.  k: int, or int32 CUDA tensor (By,)."""
     _check_cuda(scores, torch.float64, "scores")
     if scores.dim() != 3 or not scores.is_contiguous():
         raise ValueError("scores must be contiguous (T, By, Bx)")
     T, by, bx = scores.shape
-    mask = torch.empty((T, by, bx), dtype=torch.uint8, device=scores.device)
+    mask = out if out is not None else torch.empty((T, by, bx), dtype=torch.uint8, device=scores.device)
+    if mask.shape != (T, by, bx) or mask.dtype != torch.uint8 or not mask.is_contiguous():
+        raise ValueError("out must be contiguous (T, By, Bx) uint8")
     if isinstance(k, torch.Tensor):
         _check_cuda(k, torch.int32, "k")
         if k.shape != (by,) or not k.is_contiguous():
@@ -182,7 +195,8 @@ def _mask_arg(mask: torch.Tensor) -> torch.Tensor:
     return mask
 
 
-def shrink(clip: torch.Tensor, mask: torch.Tensor, block_px: int, out_bx: int, out: torch.Tensor | None = None) -> torch.Tensor:
+def shrink(clip: torch.Tensor, mask: torch.Tensor, block_px: int, out_bx: int, out: torch.Tensor | None = None,
+           ctas_per_sm: int = 0) -> torch.Tensor:
     """Left-compact the blocks with mask == 0.  clip: (T, H, W[, C]); returns
     (T, By*block_px, out_bx*block_px[, C])."""
     mask = _mask_arg(mask)
@@ -199,11 +213,12 @@ def shrink(clip: torch.Tensor, mask: torch.Tensor, block_px: int, out_bx: int, o
     if out_bx == 0 or out.numel() == 0:
         return out
     src, dst = plane_of(clip), plane_of(out, "out")
-    call("elvis_shrink", C.byref(src), C.byref(dst), T, block_px, by, bx, out_bx, _ptr(mask), _stream())
+    call("elvis_shrink", C.byref(src), C.byref(dst), T, block_px, by, bx, out_bx, _ptr(mask), int(ctas_per_sm), _stream())
     return out
 
 
-def stretch(shrunk: torch.Tensor, mask: torch.Tensor, block_px: int, out: torch.Tensor | None = None) -> torch.Tensor:
+def stretch(shrunk: torch.Tensor, mask: torch.Tensor, block_px: int, out: torch.Tensor | None = None,
+            ctas_per_sm: int = 0) -> torch.Tensor:
     """Inverse of shrink: (T, By*block_px, sbx*block_px[, C]) -> (T, By*block_px, Bx*block_px[, C])."""
     mask = _mask_arg(mask)
     T, by, bx = mask.shape
@@ -220,7 +235,7 @@ def stretch(shrunk: torch.Tensor, mask: torch.Tensor, block_px: int, out: torch.
     if sbx == 0:   # every block was removed: the canvas stays black
         return out.zero_()
     src, dst = plane_of(shrunk), plane_of(out, "out")
-    call("elvis_stretch", C.byref(src), C.byref(dst), T, block_px, by, bx, sbx, _ptr(mask), _stream())
+    call("elvis_stretch", C.byref(src), C.byref(dst), T, block_px, by, bx, sbx, _ptr(mask), int(ctas_per_sm), _stream())
     return out
 
 

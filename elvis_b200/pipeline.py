@@ -94,6 +94,91 @@ class ElvisV1:
         return scores, mask, shrunk, stretched
 
 
+class ElvisV1Pipelined:
+    """Throughput mode for a stream of clips (GOPs): two clips in flight on two CUDA streams.
+
+    Scoring is bound by instruction issue and uses ~1/4 of the HBM bandwidth; shrink and stretch
+    are pure data movement and use almost no issue slots.  Run back to back they leave one of the
+    two resources idle at any time, so the scoring of clip i+1 is overlapped with the
+    shrink + stretch of clip i: `submit` enqueues the score stage on one stream and the move
+    stage on the other, ordered by events; each of the `depth` slots owns its score, mask,
+    shrunk and stretched buffers.  Every clip still takes exactly the serial path
+    (score -> combine/normalise -> top-k -> shrink -> stretch); nothing is skipped or reused.
+    """
+
+    def __init__(self, n_frames: int, height: int, width: int, block_size: int = 16, shrink_amount: float = 0.5,
+                 alpha: float = 0.5, beta: float = 0.5, device="cuda", depth: int = 2, score_fn=None,
+                 move_ctas_per_sm: int = 3):
+        self.pipe = ElvisV1(block_size, shrink_amount, alpha, beta)
+        self.dev = torch.device(device)
+        # footprint of the shrink/stretch kernels per SM while they share it with the scoring
+        # kernel: 3 x 256 threads keeps ~85 % of their stand-alone bandwidth and leaves the two
+        # resident scoring CTAs their registers and issue slots (measured optimum on B200)
+        self.move_ctas = move_ctas_per_sm
+        self.T, self.H, self.W = n_frames, height, width
+        by, bx = height // block_size, width // block_size
+        self.k = blocks_to_remove(shrink_amount, bx)
+        sw = (bx - self.k) * block_size
+        # the move stage gets the higher stream priority: its short, register-light CTAs are placed
+        # into the resources the long-running scoring CTAs leave free instead of queueing behind them
+        self.s_score = torch.cuda.Stream(self.dev, priority=0)
+        self.s_move = torch.cuda.Stream(self.dev, priority=-1)
+        self.score_fn = score_fn      # optional: clip, slot -> scores (e.g. the sharded scorer)
+        self.slots = []
+        for _ in range(depth):
+            self.slots.append({
+                "sc": torch.empty((n_frames, by, bx), dtype=torch.float32, device=self.dev),
+                "tc": torch.empty((n_frames, by, bx), dtype=torch.float32, device=self.dev),
+                "norm": torch.empty(4, dtype=torch.float32, device=self.dev),
+                "scores": torch.empty((n_frames, by, bx), dtype=torch.float64, device=self.dev),
+                "smm": torch.empty(2, dtype=torch.float64, device=self.dev),
+                "mask": torch.empty((n_frames, by, bx), dtype=torch.uint8, device=self.dev),
+                "shrunk": Yuv420.empty(n_frames, height, sw, self.dev),
+                "full": Yuv420.empty(n_frames, height, width, self.dev),
+                "scored": torch.cuda.Event(), "done": torch.cuda.Event(), "used": False,
+            })
+        self._next = 0
+
+    def submit(self, clip: Yuv420) -> dict:
+        """Enqueue one clip; returns its slot (dict with `scores`, `mask`, `shrunk`, `full`,
+        and the `done` event).  The clip must stay unmodified until `done` fires."""
+        slot = self.slots[self._next]
+        self._next = (self._next + 1) % len(self.slots)
+        ready = torch.cuda.Event()
+        ready.record()                                   # inputs produced on the caller's stream
+        with torch.cuda.stream(self.s_score):
+            self.s_score.wait_event(ready)
+            if slot["used"]:
+                self.s_score.wait_event(slot["done"])    # the slot's previous clip has left the move stage
+            if self.score_fn is not None:
+                slot["scores"] = self.score_fn(clip, slot)
+            else:
+                p = self.pipe
+                ops.score_sc_tc(clip.y, p.bs, out=(slot["sc"], slot["tc"], slot["norm"]))
+                ops.combine_removability(slot["sc"], slot["tc"], slot["norm"], p.alpha, p.beta,
+                                         out=(slot["scores"], slot["smm"]))
+                ops.normalize_(slot["scores"], slot["smm"])
+            slot["scored"].record()
+        with torch.cuda.stream(self.s_move):
+            self.s_move.wait_event(slot["scored"])
+            ops.select_rows(slot["scores"], self.k, ops.REMOVE_HIGH, out=slot["mask"])
+            sh, fu, bs = slot["shrunk"], slot["full"], self.pipe.bs
+            for src, dst, pb in ((clip.y, sh.y, bs), (clip.u, sh.u, bs // 2), (clip.v, sh.v, bs // 2)):
+                ops.shrink(src, slot["mask"], pb, sh.y.shape[2] // bs, out=dst, ctas_per_sm=self.move_ctas)
+            for src, dst, pb in ((sh.y, fu.y, bs), (sh.u, fu.u, bs // 2), (sh.v, fu.v, bs // 2)):
+                ops.stretch(src, slot["mask"], pb, out=dst, ctas_per_sm=self.move_ctas)
+            slot["done"].record()
+        slot["used"] = True
+        return slot
+
+    def join(self) -> None:
+        """Make the caller's current stream wait for everything submitted so far."""
+        cur = torch.cuda.current_stream()
+        for slot in self.slots:
+            if slot["used"]:
+                cur.wait_event(slot["done"])
+
+
 class PresleyV2:
     """v2 per-block degradations on a planar clip (luma block bs, chroma block bs/2)."""
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ELVIS_B200_ABI_VERSION 1
+#define ELVIS_B200_ABI_VERSION 2
 
 #define ELVIS_OK               0
 #define ELVIS_ERR_INVALID_ARG (-1)   /* NULL pointer, non-positive size, out-of-range parameter   */
@@ -127,17 +127,20 @@ ELVIS_API int elvis_select_rows(const double* scores, int32_t n_frames, int32_t 
 /* ---- a4/a6: shrink -- left-compact the kept blocks of every block row
  * (elvis.py:1418-1425; utils.py:727-735).  Plane block = block_px x block_px pixels.
  * dst must hold (By*block_px) rows of out_bx*block_px pixels; a row that keeps fewer than
- * out_bx blocks is zero padded, one that keeps more is truncated (utils.py:735). */
+ * out_bx blocks is zero padded, one that keeps more is truncated (utils.py:735).
+ * ctas_per_sm: 0 = one CTA per (frame, block row) (fastest on an otherwise idle GPU);
+ * n > 0 caps the grid at n CTAs per SM (grid-stride) so that the kernel can share the SMs
+ * with a concurrently running scoring kernel (see elvis_b200.pipeline.ElvisV1Pipelined). */
 ELVIS_API int elvis_shrink(const elvis_plane* src, const elvis_plane* dst, int32_t n_frames,
                  int32_t block_px, int32_t by, int32_t bx, int32_t out_bx,
-                 const uint8_t* mask, elvis_stream_t stream);
+                 const uint8_t* mask, int32_t ctas_per_sm, elvis_stream_t stream);
 
 /* ---- a5/a7: stretch -- scatter shrunk blocks back to the mask == 0 positions of their
  * row, zeros elsewhere (elvis.py:1436-1455; utils.py:739-759).  shrunk_bx = blocks per
  * row of src. */
 ELVIS_API int elvis_stretch(const elvis_plane* src, const elvis_plane* dst, int32_t n_frames,
                   int32_t block_px, int32_t by, int32_t bx, int32_t shrunk_bx,
-                  const uint8_t* mask, elvis_stream_t stream);
+                  const uint8_t* mask, int32_t ctas_per_sm, elvis_stream_t stream);
 
 /* ---- a8-a12: level maps from scores.  scores float64 (n), levels int32 (n). */
 ELVIS_API int elvis_levels_from_scores(const double* scores, int64_t n, int32_t rule, int32_t param,

@@ -386,3 +386,33 @@ def test_score_tightness(dev, monkeypatch):
         e_tc = (np.abs(tc.cpu().numpy() - rtc)[nz] / rtc[nz]).max()
         print(f"{impl}: max rel err SC {e_sc:.2e} TC {e_tc:.2e}")
         assert e_sc < 2e-5 and e_tc < 2e-5
+
+
+def test_pipelined_equals_serial(dev):
+    """Two clips in flight on two streams must give exactly the serial results."""
+    import torch
+    from elvis_b200.pipeline import ElvisV1, ElvisV1Pipelined, Yuv420
+    T, H, W, bs = 5, 96, 160, 16
+    clips = []
+    for seed in (1, 2, 3):
+        y, u, v = synth_yuv420(T, H, W, seed=seed)
+        clips.append(Yuv420(to_dev(y, dev), to_dev(u, dev), to_dev(v, dev)))
+    serial = ElvisV1(bs, 0.5, 0.5, 0.5)
+    ref = [serial.run(c) for c in clips]
+    pp = ElvisV1Pipelined(T, H, W, bs, 0.5, 0.5, 0.5, dev, depth=2)
+    for i, c in enumerate(clips):
+        slot = pp.submit(c)
+        slot["done"].synchronize()      # read the slot before it is reused
+        scores, mask, shrunk, full = ref[i]
+        assert torch.equal(slot["scores"], scores) and torch.equal(slot["mask"], mask)
+        for a, b in zip(slot["shrunk"].planes, shrunk.planes):
+            assert torch.equal(a, b)
+        for a, b in zip(slot["full"].planes, full.planes):
+            assert torch.equal(a, b)
+    # back-to-back submissions without waiting: the last two clips must still be intact
+    s1 = pp.submit(clips[0])
+    s2 = pp.submit(clips[1])
+    pp.join()
+    torch.cuda.synchronize()
+    assert torch.equal(s1["mask"], ref[0][1]) and torch.equal(s2["mask"], ref[1][1])
+    assert torch.equal(s1["full"].y, ref[0][3].y) and torch.equal(s2["full"].y, ref[1][3].y)
