@@ -44,7 +44,7 @@ SIGNATURES = {
     "elvis_stretch": [_PP, _PP, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
     "elvis_levels_from_scores": [_vp, _i64, _i32, _i32, _vp, _vp],
     "elvis_degrade_blur": [_PP, _PP, _i32, _i32, _i32, _i32, _vp, _vp],
-    "elvis_degrade_downsample": [_PP, _PP, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
+    "elvis_degrade_downsample": [_PP, _PP, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp],
     "elvis_dct_dampen": [_PP, _PP, _i32, _i32, _i32, _i32, _vp, _vp],
     "elvis_pack_mask_bits": [_vp, _i64, _vp, _vp],
     "elvis_unpack_mask_bits": [_vp, _i64, _vp, _vp],

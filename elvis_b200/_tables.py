@@ -17,6 +17,12 @@ def level_stride(pb: int) -> int:
     return 8 + (pb + 1) + 4 * pb + 8 * pb
 
 
+def fast_stride(pb: int) -> int:
+    """Words per level of the byte-weight tables used by downsample_fast_kernel:
+    pb x {wx, wy} horizontal weight vectors, then pb x {i0, i1, b0, b1} vertical taps."""
+    return 2 * pb + 4 * pb
+
+
 def _linear_taps(ssize: int, dsize: int, horizontal: bool):
     d = np.arange(dsize, dtype=np.float64)
     pos = ((d + 0.5) * (ssize / dsize) - 0.5).astype(np.float32)
@@ -92,4 +98,35 @@ def build(pb: int, small_sizes: tuple) -> np.ndarray:
             e[off + 2 * pb:off + 3 * pb] = c0
             e[off + 3 * pb:off + 4 * pb] = c1
             off += 4 * pb
-    return blob.reshape(-1)
+    # fast-path tables (planar 8/16-pixel blocks, power-of-two reductions): when every 11-bit
+    # horizontal coefficient of a level is a multiple of 64 the two taps of an output pixel
+    # become byte weights over the (<= 8 byte) source row, so that
+    #     S[i0]*a0 + S[i1]*a1  ==  64 * (dp4a(row.lo, wx) + dp4a(row.hi, wy))
+    fast = np.zeros((len(small_sizes), fast_stride(pb)), np.int32)
+    for lv, small in enumerate(small_sizes):
+        small = int(small)
+        ok = small < pb and pb % small == 0 and (pb // small) & (pb // small - 1) == 0 and small <= 8 and pb in (8, 16)
+        if small >= pb:
+            ok = True          # copy level: nothing to tabulate
+        if ok and small < pb:
+            i0, i1, c0, c1 = _linear_taps(small, pb, True)
+            ok = bool(np.all(c0 % 64 == 0) and np.all(c1 % 64 == 0))
+            if ok:
+                w = np.zeros((pb, 8), np.uint8)
+                for d in range(pb):
+                    w[d, i0[d]] += c0[d] // 64
+                    w[d, i1[d]] += c1[d] // 64
+                fast[lv, :2 * pb] = w.view(np.uint32).view(np.int32).reshape(-1)
+                v = np.stack(_linear_taps(small, pb, False), axis=1).astype(np.int32)     # (pb, 4)
+                fast[lv, 2 * pb:] = v.reshape(-1)
+        blob[lv, 5] = 1 if ok else 0
+    generic = blob.reshape(-1)
+    pad = (-len(generic)) % 4                 # the fast part is read with 128-bit loads
+    return np.concatenate([generic, np.zeros(pad, np.int32), fast.reshape(-1)])
+
+
+def all_fast(pb: int, small_sizes: tuple) -> bool:
+    """True when every level of the blob has fast-path (byte-weight) tables."""
+    blob = build(pb, tuple(small_sizes))
+    st = level_stride(pb)
+    return pb in (8, 16) and all(int(blob[i * st + 5]) == 1 for i in range(len(small_sizes)))

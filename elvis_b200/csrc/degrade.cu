@@ -87,6 +87,156 @@ __global__ void __launch_bounds__(256) blur_kernel(const BlockGeom g, const int3
     }
 }
 
+
+// ----------------------------------------------------------------------- blur, fast path
+// Planar planes with 16- or 8-pixel blocks (luma / 4:2:0 chroma of 16x16 blocks).  A group of
+// G lanes owns one block (G = 32 for PB = 16, 8 for PB = 8 -> four blocks per warp); every
+// lane produces 8 pixels per pass:
+//   row pass     lane = (row, 8-pixel half): the row is read with one 128/64-bit LDS, the 12-byte
+//                tap window (block-edge reflection folded into PRMT selectors) is walked with
+//                two IDP.4A per pixel: (14,62,104,62).(x-2..x+1) + 14*x(+2).  The 16-bit results
+//                are stored TRANSPOSED (column major, two halo rows per side holding the
+//                reflected rows), so that
+//   column pass  lane = (column, 8-row half): 12 vertically consecutive 16-bit values arrive as
+//                six 32-bit pairs (LDS.128 + LDS.64) and each output is three IDP.2A
+//                (pair . two 8-bit taps) on top of the rounding constant; >> 16 gives the u8.
+// About 11 instructions per pixel and round, all integer, bit-exact with cv2 by construction.
+template <int PB> struct BlurGeom;
+template <> struct BlurGeom<16> { static constexpr int G = 32, kBlocks = 1, kPitch = 48; };
+template <> struct BlurGeom<8>  { static constexpr int G = 8,  kBlocks = 4, kPitch = 32; };
+
+template <int PB, bool ALIGNED>
+__global__ void __launch_bounds__(256) blur_fast_kernel(const BlockGeom g, const int32_t* __restrict__ rounds) {
+    using GG = BlurGeom<PB>;
+    constexpr int kWarps = 8;
+    constexpr int kABytes = GG::kBlocks * PB * PB;            // u8 blocks, row major
+    constexpr int kTBytes = GG::kBlocks * PB * GG::kPitch;    // u16 row-pass results, column major + halo
+    __shared__ __align__(16) uint8_t s_a[kWarps][kABytes];
+    __shared__ __align__(16) uint8_t s_t[kWarps][kTBytes];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int blk = PB == 16 ? 0 : lane >> 3;
+    const int r = PB == 16 ? lane >> 1 : lane & 7;            // row pass: my row ...
+    const int h = PB == 16 ? lane & 1 : 0;                    // ... and 8-pixel half
+    const int x = PB == 16 ? lane & 15 : lane & 7;            // column pass: my column ...
+    const int yh = PB == 16 ? lane >> 4 : 0;                  // ... and 8-row half
+    uint8_t* a = s_a[w] + blk * PB * PB;
+    uint8_t* tm = s_t[w] + blk * PB * GG::kPitch;
+    const uint32_t kTaps4 = 14u | (62u << 8) | (104u << 16) | (62u << 24);
+
+    const int64_t n_blocks = (int64_t)g.T * g.By * g.Bx;
+    const int64_t stride = (int64_t)gridDim.x * kWarps * GG::kBlocks;
+    for (int64_t b0 = ((int64_t)blockIdx.x * kWarps + w) * GG::kBlocks; b0 < n_blocks; b0 += stride) {
+        const int64_t b = b0 + blk;
+        const bool live = b < n_blocks;
+        int nr = 0;
+        const uint8_t* sp = g.src;
+        uint8_t* dp = g.dst;
+        if (live) {
+            const int bx = (int)(b % g.Bx);
+            const int64_t q = b / g.Bx;
+            const int by = (int)(q % g.By), t = (int)(q / g.By);
+            nr = rounds[b];
+            const int64_t off_s = (int64_t)t * g.src_frame + ((int64_t)by * PB + r) * g.src_row + (int64_t)bx * PB + 8 * h;
+            const int64_t off_d = (int64_t)t * g.dst_frame + ((int64_t)by * PB + r) * g.dst_row + (int64_t)bx * PB + 8 * h;
+            sp += off_s;
+            dp += off_d;
+        }
+        uint2 px = make_uint2(0u, 0u);
+        if (live) {
+            if (ALIGNED) {
+                px = __ldcs(reinterpret_cast<const uint2*>(sp));
+            } else {
+                px.x = sp[0] | (sp[1] << 8) | (sp[2] << 16) | ((uint32_t)sp[3] << 24);
+                px.y = sp[4] | (sp[5] << 8) | (sp[6] << 16) | ((uint32_t)sp[7] << 24);
+            }
+        }
+        int max_r = nr;
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) max_r = max(max_r, __shfl_xor_sync(0xffffffffu, max_r, m));
+        if (max_r > 0) {
+            *reinterpret_cast<uint2*>(a + r * PB + 8 * h) = px;
+            __syncwarp();
+            for (int k = 0; k < max_r; ++k) {
+                const bool act = k < nr;
+                // ---- row pass
+                if (act) {
+                    uint32_t W0, W1, W2;
+                    if (PB == 16) {
+                        const uint4 row = *reinterpret_cast<const uint4*>(a + r * 16);
+                        // h == 0: pixels -2..9 = (b2,b1,b0,b1 | b2..b5 | b6..b9); h == 1: pixels 6..17 = (b6..b9 | b10..b13 | b14,b15,b14,b13)
+                        const uint32_t A0 = h ? row.y : row.x, B0 = h ? row.z : row.x;
+                        const uint32_t A1 = h ? row.z : row.x, B1 = h ? row.w : row.y;
+                        const uint32_t A2 = h ? row.w : row.y, B2 = h ? row.w : row.z;
+                        W0 = __byte_perm(A0, B0, h ? 0x5432 : 0x1012);
+                        W1 = __byte_perm(A1, B1, 0x5432);
+                        W2 = __byte_perm(A2, B2, h ? 0x1232 : 0x5432);
+                    } else {
+                        const uint2 row = *reinterpret_cast<const uint2*>(a + r * 8);
+                        W0 = __byte_perm(row.x, row.x, 0x1012);      // b2 b1 b0 b1
+                        W1 = __byte_perm(row.x, row.y, 0x5432);      // b2 b3 b4 b5
+                        W2 = __byte_perm(row.y, row.y, 0x1232);      // b6 b7 b6 b5
+                    }
+                    uint32_t o[8];
+                    o[0] = __dp4a(W0, kTaps4, __dp4a(W1, 14u, 0u));
+                    o[1] = __dp4a(__byte_perm(W0, W1, 0x4321), kTaps4, __dp4a(W1, 14u << 8, 0u));
+                    o[2] = __dp4a(__byte_perm(W0, W1, 0x5432), kTaps4, __dp4a(W1, 14u << 16, 0u));
+                    o[3] = __dp4a(__byte_perm(W0, W1, 0x6543), kTaps4, __dp4a(W1, 14u << 24, 0u));
+                    o[4] = __dp4a(W1, kTaps4, __dp4a(W2, 14u, 0u));
+                    o[5] = __dp4a(__byte_perm(W1, W2, 0x4321), kTaps4, __dp4a(W2, 14u << 8, 0u));
+                    o[6] = __dp4a(__byte_perm(W1, W2, 0x5432), kTaps4, __dp4a(W2, 14u << 16, 0u));
+                    o[7] = __dp4a(__byte_perm(W1, W2, 0x6543), kTaps4, __dp4a(W2, 14u << 24, 0u));
+                    // transposed store: column c = 8h + j, stored row r + 2; reflected halo rows
+                    uint16_t* tcol = reinterpret_cast<uint16_t*>(tm) + (8 * h) * (GG::kPitch / 2) + (r + 2);
+                    int dup = -1;                                   // halo slot that mirrors my row
+                    if (r == 1) dup = 1; else if (r == 2) dup = 0;
+                    else if (r == PB - 2) dup = PB + 2; else if (r == PB - 3) dup = PB + 3;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        tcol[j * (GG::kPitch / 2)] = (uint16_t)o[j];
+                        if (dup >= 0) tcol[j * (GG::kPitch / 2) + (dup - (r + 2))] = (uint16_t)o[j];
+                    }
+                }
+                __syncwarp();
+                // ---- column pass
+                if (act) {
+                    const uint8_t* col = tm + x * GG::kPitch + 16 * yh;     // stored rows 8yh .. 8yh+11
+                    const uint4 q0 = *reinterpret_cast<const uint4*>(col);
+                    const uint2 q1 = *reinterpret_cast<const uint2*>(col + 16);
+                    const uint32_t P[6] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y};
+                    uint8_t* acol = a + (8 * yh) * PB + x;
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        const int p = i >> 1;
+                        // even row: taps (14,62 | 104,62 | 14,-); odd row: (-,14 | 62,104 | 62,14)
+                        uint32_t ve = __dp2a_lo(P[p], 14u | (62u << 8), 32768u);
+                        ve = __dp2a_lo(P[p + 1], 104u | (62u << 8), ve);
+                        ve = __dp2a_lo(P[p + 2], 14u, ve);
+                        uint32_t vo = __dp2a_lo(P[p], 14u << 8, 32768u);
+                        vo = __dp2a_lo(P[p + 1], 62u | (104u << 8), vo);
+                        vo = __dp2a_lo(P[p + 2], 62u | (14u << 8), vo);
+                        acol[i * PB] = (uint8_t)(ve >> 16);
+                        acol[(i + 1) * PB] = (uint8_t)(vo >> 16);
+                    }
+                }
+                __syncwarp();
+            }
+            px = *reinterpret_cast<const uint2*>(a + r * PB + 8 * h);
+            __syncwarp();
+        }
+        if (live) {
+            if (ALIGNED) {
+                __stcs(reinterpret_cast<uint2*>(dp), px);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dp[j] = (uint8_t)(px.x >> (8 * j));
+                    dp[4 + j] = (uint8_t)(px.y >> (8 * j));
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------- downsample
 // Table blob layout (int32 words), one entry of `level_stride(pb)` words per level:
 //   [0] small  [1] area_kind (0 copy, 1 2x2, 2 integer factor, 3 fractional)  [2] factor
@@ -184,6 +334,148 @@ __global__ void __launch_bounds__(256) downsample_kernel(const BlockGeom g, cons
             dp[(int64_t)d2 * g.dst_row + d * g.C] = (uint8_t)v;
         }
         __syncwarp();
+    }
+}
+
+
+// ----------------------------------------------------------------- downsample, fast path
+// Planar planes, 16- or 8-pixel blocks, power-of-two reductions (the elvis 1x/2x/4x/8x(/16x)
+// pyramid).  Same lane geometry as blur_fast_kernel (8 pixels of one row per lane).
+//   area     per-lane byte sums (packed 16-bit adds) + xor-shuffle sums over the f rows;
+//            f = 2: (s + 2) >> 2, f >= 4: round-half-even(s / f^2)  (cv2's two integer paths)
+//   linear   every 11-bit horizontal coefficient of these ratios is a multiple of 64, so the two
+//            taps of an output pixel are byte weights over the <= 8-byte source row and
+//            S[i0]*a0 + S[i1]*a1 == 64 * (dp4a(row.lo, wx) + dp4a(row.hi, wy)); the vertical
+//            pass is cv2's  ((b0*(R0>>4))>>16) + ((b1*(R1>>4))>>16) + 2 >> 2.
+// Weight vectors come from elvis_b200/_tables.py (fast part of the blob).
+template <int PB, bool ALIGNED>
+__global__ void __launch_bounds__(256) downsample_fast_kernel(const BlockGeom g, const int32_t* __restrict__ levels,
+                                                              const int32_t* __restrict__ tables, int n_levels) {
+    constexpr int kWarps = 8;
+    constexpr int kBlocks = PB == 16 ? 1 : 4;
+    constexpr int kLevelStride = 8 + (PB + 1) + 4 * PB + 8 * PB;
+    constexpr int kFastStride = 6 * PB;
+    __shared__ __align__(8) uint8_t s_small[kWarps][kBlocks][8 * 8];   // reduced image, 8-byte row pitch
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int blk = PB == 16 ? 0 : lane >> 3;
+    const int r = PB == 16 ? lane >> 1 : lane & 7;
+    const int h = PB == 16 ? lane & 1 : 0;
+    uint8_t* S = s_small[w][blk];
+    const int32_t* fast_base = tables + (((size_t)n_levels * kLevelStride + 3) & ~(size_t)3);   // 16-byte aligned
+
+    const int64_t n_blocks = (int64_t)g.T * g.By * g.Bx;
+    const int64_t stride = (int64_t)gridDim.x * kWarps * kBlocks;
+    for (int64_t b0 = ((int64_t)blockIdx.x * kWarps + w) * kBlocks; b0 < n_blocks; b0 += stride) {
+        const int64_t b = b0 + blk;
+        const bool live = b < n_blocks;
+        int L = 0;            // log2 of the reduction factor; 0 = copy
+        int lv = 0;
+        const uint8_t* sp = g.src;
+        uint8_t* dp = g.dst;
+        if (live) {
+            const int bx = (int)(b % g.Bx);
+            const int64_t q = b / g.Bx;
+            const int by = (int)(q % g.By), t = (int)(q / g.By);
+            lv = levels[b];
+            lv = lv < 0 ? 0 : (lv >= n_levels ? n_levels - 1 : lv);
+            const int small = __ldg(tables + (size_t)lv * kLevelStride);
+            L = small >= PB ? 0 : 31 - __clz(PB / small);
+            sp += (int64_t)t * g.src_frame + ((int64_t)by * PB + r) * g.src_row + (int64_t)bx * PB + 8 * h;
+            dp += (int64_t)t * g.dst_frame + ((int64_t)by * PB + r) * g.dst_row + (int64_t)bx * PB + 8 * h;
+        }
+        uint2 px = make_uint2(0u, 0u);
+        if (live) {
+            if (ALIGNED) {
+                px = __ldcs(reinterpret_cast<const uint2*>(sp));
+            } else {
+                px.x = sp[0] | (sp[1] << 8) | (sp[2] << 16) | ((uint32_t)sp[3] << 24);
+                px.y = sp[4] | (sp[5] << 8) | (sp[6] << 16) | ((uint32_t)sp[7] << 24);
+            }
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, L > 0);
+        if (any) {
+            // ---- area: horizontal sums inside the lane
+            const uint32_t e0 = (px.x & 0x00ff00ffu) + ((px.x >> 8) & 0x00ff00ffu);   // (b0+b1, b2+b3)
+            const uint32_t e1 = (px.y & 0x00ff00ffu) + ((px.y >> 8) & 0x00ff00ffu);   // (b4+b5, b6+b7)
+            int hs[4];
+            if (L == 1) {
+                hs[0] = e0 & 0xffff; hs[1] = e0 >> 16; hs[2] = e1 & 0xffff; hs[3] = e1 >> 16;
+            } else if (L == 2) {
+                hs[0] = (e0 & 0xffff) + (e0 >> 16); hs[1] = (e1 & 0xffff) + (e1 >> 16); hs[2] = hs[3] = 0;
+            } else {
+                hs[0] = (e0 & 0xffff) + (e0 >> 16) + (e1 & 0xffff) + (e1 >> 16); hs[1] = hs[2] = hs[3] = 0;
+            }
+            if (PB == 16) {        // factor 16: the two halves of the row
+                const int o = __shfl_xor_sync(0xffffffffu, hs[0], 1);
+                if (L == 4) hs[0] += o;
+            }
+            // ---- vertical sums over the f rows of the cell (row bits of the lane index)
+            constexpr int kRowBit = PB == 16 ? 2 : 1;
+#pragma unroll
+            for (int sft = 0; sft < (PB == 16 ? 4 : 3); ++sft) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int o = __shfl_xor_sync(0xffffffffu, hs[i], kRowBit << sft);
+                    if (sft < L) hs[i] += o;
+                }
+            }
+            // ---- rounding and store of the reduced image (one writer per cell)
+            if (L > 0 && (r & ((1 << L) - 1)) == 0 && !(L == 4 && h == 1)) {
+                const int k = 2 * L;
+                const int cnt = L >= 3 ? 1 : (8 >> L);                 // cells of this lane in the row
+                const int col0 = L >= 3 ? (L == 4 ? 0 : h) : (8 * h) >> L;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (i < cnt) {
+                        int v;
+                        if (L == 1) {
+                            v = (hs[i] + 2) >> 2;
+                        } else {
+                            v = hs[i] >> k;
+                            const int rem = hs[i] & ((1 << k) - 1), half = 1 << (k - 1);
+                            v += (rem > half) || (rem == half && (v & 1));
+                        }
+                        S[(r >> L) * 8 + col0 + i] = (uint8_t)v;
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- bilinear back up
+            if (L > 0) {
+                const int32_t* ft = fast_base + (size_t)lv * kFastStride;
+                const int4 vt = __ldg(reinterpret_cast<const int4*>(ft + 2 * PB) + r);           // i0, i1, b0, b1
+                const uint2 r0 = *reinterpret_cast<const uint2*>(S + vt.x * 8);
+                const uint2 r1 = *reinterpret_cast<const uint2*>(S + vt.y * 8);
+                const int4* wv = reinterpret_cast<const int4*>(ft) + 4 * h;                       // {wx,wy} x 8 pixels
+                uint32_t o[8];
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const int4 wq = __ldg(wv + j4);                                               // pixels 2*j4, 2*j4+1
+                    const uint32_t wxy[4] = {(uint32_t)wq.x, (uint32_t)wq.y, (uint32_t)wq.z, (uint32_t)wq.w};
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const uint32_t d0 = __dp4a(r0.y, wxy[2 * e + 1], __dp4a(r0.x, wxy[2 * e], 0u));   // R0 / 64
+                        const uint32_t d1 = __dp4a(r1.y, wxy[2 * e + 1], __dp4a(r1.x, wxy[2 * e], 0u));   // R1 / 64
+                        const int v = (int)((((uint32_t)vt.z * (d0 * 4u)) >> 16) + (((uint32_t)vt.w * (d1 * 4u)) >> 16) + 2u) >> 2;
+                        o[2 * j4 + e] = (uint32_t)(v > 255 ? 255 : v);
+                    }
+                }
+                px.x = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+                px.y = o[4] | (o[5] << 8) | (o[6] << 16) | (o[7] << 24);
+            }
+            __syncwarp();
+        }
+        if (live) {
+            if (ALIGNED) {
+                __stcs(reinterpret_cast<uint2*>(dp), px);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dp[j] = (uint8_t)(px.x >> (8 * j));
+                    dp[4 + j] = (uint8_t)(px.y >> (8 * j));
+                }
+            }
+        }
     }
 }
 
@@ -331,6 +623,22 @@ extern "C" int elvis_degrade_blur(const elvis_plane* src, const elvis_plane* dst
     cudaStream_t st = as_stream(stream);
     if (int rc = copy_edges(g, st)) return rc;
     const int n = block_px * block_px;
+    if (g.C == 1 && (block_px == 16 || block_px == 8) && !getenv("ELVIS_BLUR_GENERIC")) {
+        const bool al = aligned_to(g.src, 8) && aligned_to(g.dst, 8) && g.src_frame % 8 == 0 && g.dst_frame % 8 == 0 &&
+                        g.src_row % 8 == 0 && g.dst_row % 8 == 0;
+        const int64_t blocks = (int64_t)n_frames * by * bx;
+        const int per_cta = 8 * (block_px == 16 ? 1 : 4);
+        const int grid = grid_for_units(blocks, per_cta);
+        if (block_px == 16) {
+            if (al) blur_fast_kernel<16, true><<<grid, 256, 0, st>>>(g, rounds);
+            else blur_fast_kernel<16, false><<<grid, 256, 0, st>>>(g, rounds);
+        } else {
+            if (al) blur_fast_kernel<8, true><<<grid, 256, 0, st>>>(g, rounds);
+            else blur_fast_kernel<8, false><<<grid, 256, 0, st>>>(g, rounds);
+        }
+        ELVIS_CHECK_LAUNCH();
+        return ELVIS_OK;
+    }
     int wpc = 8;
     while (wpc > 1 && (size_t)wpc * n * 3 + 16 > 48 * 1024) wpc >>= 1;
     const size_t smem = (((size_t)wpc * n + 15) & ~(size_t)15) + (size_t)wpc * n * 2;
@@ -342,7 +650,8 @@ extern "C" int elvis_degrade_blur(const elvis_plane* src, const elvis_plane* dst
 
 extern "C" int elvis_degrade_downsample(const elvis_plane* src, const elvis_plane* dst, int32_t n_frames,
                                         int32_t block_px, int32_t by, int32_t bx, const int32_t* levels,
-                                        const int32_t* tables, int32_t n_levels, elvis_stream_t stream) {
+                                        const int32_t* tables, int32_t n_levels, int32_t fast_tables_ok,
+                                        elvis_stream_t stream) {
     BlockGeom g;
     if (int rc = make_geom(src, dst, n_frames, block_px, by, bx, g)) return rc;
     if (!levels || !tables || n_levels <= 0) return ELVIS_ERR_INVALID_ARG;
@@ -350,6 +659,21 @@ extern "C" int elvis_degrade_downsample(const elvis_plane* src, const elvis_plan
     cudaStream_t st = as_stream(stream);
     if (int rc = copy_edges(g, st)) return rc;
     const int n = block_px * block_px;
+    if (g.C == 1 && (block_px == 16 || block_px == 8) && fast_tables_ok && !getenv("ELVIS_DOWNSAMPLE_GENERIC")) {
+        const bool al = aligned_to(g.src, 8) && aligned_to(g.dst, 8) && g.src_frame % 8 == 0 && g.dst_frame % 8 == 0 &&
+                        g.src_row % 8 == 0 && g.dst_row % 8 == 0;
+        const int64_t blocks = (int64_t)n_frames * by * bx;
+        const int grid = grid_for_units(blocks, 8 * (block_px == 16 ? 1 : 4));
+        if (block_px == 16) {
+            if (al) downsample_fast_kernel<16, true><<<grid, 256, 0, st>>>(g, levels, tables, n_levels);
+            else downsample_fast_kernel<16, false><<<grid, 256, 0, st>>>(g, levels, tables, n_levels);
+        } else {
+            if (al) downsample_fast_kernel<8, true><<<grid, 256, 0, st>>>(g, levels, tables, n_levels);
+            else downsample_fast_kernel<8, false><<<grid, 256, 0, st>>>(g, levels, tables, n_levels);
+        }
+        ELVIS_CHECK_LAUNCH();
+        return ELVIS_OK;
+    }
     int wpc = 8;
     while (wpc > 1 && (size_t)wpc * n * 6 > 48 * 1024) wpc >>= 1;
     const size_t smem = (size_t)wpc * n * 6;
