@@ -29,6 +29,10 @@ __device__ constexpr float kW[8][8] = {
 };
 
 constexpr int kScoreThreads = 128;
+#ifndef ELVIS_PACKED_PAIRS
+#define ELVIS_PACKED_PAIRS 4
+#endif
+constexpr int kPackedColumnPairs = ELVIS_PACKED_PAIRS;   // column pairs of the vertical pass done with FADD2/FFMA2
 constexpr int kRing = 3;   // cp.async ring depth: two frames in flight ahead of the one being transformed
 
 template <bool ALIGNED>
@@ -138,21 +142,29 @@ __global__ void __launch_bounds__(kScoreThreads, 2) score_kernel(const ScorePara
             ELVIS_DIFF(4, 0, y); ELVIS_DIFF(5, 1, y); ELVIS_DIFF(6, 2, y); ELVIS_DIFF(7, 3, y);
 #undef ELVIS_DIFF
         }
-        // horizontal pass: two rows per instruction
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ELVIS_FDCT8_X2(y[i][0], y[i][1], y[i][2], y[i][3], y[i][4], y[i][5], y[i][6], y[i][7]);
-        // re-pair (2x2 register transposes): x[r][j] = (h[r][2j], h[r][2j+1])
+        // horizontal pass: SCALAR butterflies (they can issue to both FMA sub-pipes, whereas the
+        // packed instructions only run on the heavy one), written straight into the column-pair
+        // registers of the vertical pass -- no register transposition in between
         float2 x[8][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                x[2 * i][j] = make_float2(y[i][2 * j].x, y[i][2 * j + 1].x);
-                x[2 * i + 1][j] = make_float2(y[i][2 * j].y, y[i][2 * j + 1].y);
-            }
+        for (int i = 0; i < 4; ++i) {
+            float a0 = y[i][0].x, a1 = y[i][1].x, a2 = y[i][2].x, a3 = y[i][3].x, a4 = y[i][4].x, a5 = y[i][5].x, a6 = y[i][6].x, a7 = y[i][7].x;
+            ELVIS_FDCT8(a0, a1, a2, a3, a4, a5, a6, a7);
+            x[2 * i][0] = make_float2(a0, a1); x[2 * i][1] = make_float2(a2, a3);
+            x[2 * i][2] = make_float2(a4, a5); x[2 * i][3] = make_float2(a6, a7);
+            float b0 = y[i][0].y, b1 = y[i][1].y, b2 = y[i][2].y, b3 = y[i][3].y, b4 = y[i][4].y, b5 = y[i][5].y, b6 = y[i][6].y, b7 = y[i][7].y;
+            ELVIS_FDCT8(b0, b1, b2, b3, b4, b5, b6, b7);
+            x[2 * i + 1][0] = make_float2(b0, b1); x[2 * i + 1][1] = make_float2(b2, b3);
+            x[2 * i + 1][2] = make_float2(b4, b5); x[2 * i + 1][3] = make_float2(b6, b7);
+        }
         // vertical pass: two columns per instruction.  x[u][j] = (dC[u][2j], dC[u][2j+1]), AAN-scaled
 #pragma unroll
-        for (int j = 0; j < 4; ++j) ELVIS_FDCT8_X2(x[0][j], x[1][j], x[2][j], x[3][j], x[4][j], x[5][j], x[6][j], x[7][j]);
+        for (int j = 0; j < kPackedColumnPairs; ++j) ELVIS_FDCT8_X2(x[0][j], x[1][j], x[2][j], x[3][j], x[4][j], x[5][j], x[6][j], x[7][j]);
+#pragma unroll
+        for (int j = kPackedColumnPairs; j < 4; ++j) {   // remaining columns: scalar (both FMA sub-pipes)
+            ELVIS_FDCT8(x[0][j].x, x[1][j].x, x[2][j].x, x[3][j].x, x[4][j].x, x[5][j].x, x[6][j].x, x[7][j].x);
+            ELVIS_FDCT8(x[0][j].y, x[1][j].y, x[2][j].y, x[3][j].y, x[4][j].y, x[5][j].y, x[6][j].y, x[7][j].y);
+        }
 
         // per-row partial sums keep 16 independent FMA chains in flight; fixed order => deterministic
         float s_part[8], d_part[8];
@@ -252,11 +264,12 @@ int launch_score_simt(ScoreParams p, int block_size, bool aligned8, cudaStream_t
     }
 }
 
-// chunking heuristic: enough (spatial tile x chunk) work units for >= 16 waves of resident
-// workers, but chunks no shorter than 16 frames (each chunk pays one extra priming transform).
+// chunking heuristic: enough (spatial tile x chunk) work units for >= 6 waves of resident
+// workers (measured on B200: 60-frame chunks beat 24-frame ones by 3 %, each chunk pays one
+// extra priming transform), and chunks no shorter than 16 frames.
 static int pick_chunks(int T, long tiles, long resident, int override_len) {
     if (override_len > 0) return (T + override_len - 1) / override_len;
-    const long target = 16L * resident;
+    const long target = 6L * resident;
     long n = (target + tiles - 1) / tiles;
     const long max_chunks = (T + 15) / 16;
     if (n > max_chunks) n = max_chunks;
