@@ -306,7 +306,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             cb = cpu_arm(16, 2, 1)
             cb = {k_: cb[k_] for k_ in ("value", "unit", "cores", "kind", "sample")}
-        launches_per_step = 2 + 2 + 1 + 1 + 3 + 3   # score(init+kernel) combine(init+kernel) normalize select shrink x3 stretch x3
+        launches_per_step = 2 + 2 + 1 + 1 + 1 + 1   # score(init+kernel) combine(init+kernel) normalize select shrink(YUV fused) stretch(YUV fused)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8 pixels, f32 DCT, f64 scores", "data": "synthetic",

@@ -42,6 +42,8 @@ SIGNATURES = {
     "elvis_select_rows": [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp],
     "elvis_shrink": [_PP, _PP, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
     "elvis_stretch": [_PP, _PP, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
+    "elvis_shrink_yuv420": [_PP, _PP, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
+    "elvis_stretch_yuv420": [_PP, _PP, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
     "elvis_levels_from_scores": [_vp, _i64, _i32, _i32, _vp, _vp],
     "elvis_degrade_blur": [_PP, _PP, _i32, _i32, _i32, _i32, _vp, _vp],
     "elvis_degrade_downsample": [_PP, _PP, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp],

@@ -69,13 +69,49 @@ __device__ __forceinline__ void build_map(const uint8_t* __restrict__ mrow, int 
     __syncthreads();
 }
 
+// Gather one block row: destination unit c of every pixel row <- source unit map[c / upb]*upb + c % upb
+// (zeros when the map says -1).  Four rows in flight per thread: all loads issued before the stores.
+template <typename V>
+__device__ __forceinline__ void copy_block_row(const uint8_t* __restrict__ src, int64_t src_row, uint8_t* __restrict__ dst,
+                                               int64_t dst_row, const int16_t* s_map, int cols, int upb, int bh, int tx,
+                                               int ty, int tx_dim, int ty_dim) {
+    const int64_t srow = src_row / (int64_t)sizeof(V), drow = dst_row / (int64_t)sizeof(V);
+    const V* sbase = reinterpret_cast<const V*>(src);
+    V* dbase = reinterpret_cast<V*>(dst);
+    for (int c = tx; c < cols; c += tx_dim) {
+        const int j = c / upb;
+        const int u = c - j * upb;
+        const int sj = s_map[j];
+        const V* sp = sbase + (sj < 0 ? 0 : sj * upb + u);
+        V* dp = dbase + c;
+        int r = ty;
+        for (; r + 3 * ty_dim < bh; r += 4 * ty_dim) {
+            V v0 = zero_v<V>(), v1 = zero_v<V>(), v2 = zero_v<V>(), v3 = zero_v<V>();
+            if (sj >= 0) {
+                v0 = ld_stream(sp + (int64_t)r * srow);
+                v1 = ld_stream(sp + (int64_t)(r + ty_dim) * srow);
+                v2 = ld_stream(sp + (int64_t)(r + 2 * ty_dim) * srow);
+                v3 = ld_stream(sp + (int64_t)(r + 3 * ty_dim) * srow);
+            }
+            st_stream(dp + (int64_t)r * drow, v0);
+            st_stream(dp + (int64_t)(r + ty_dim) * drow, v1);
+            st_stream(dp + (int64_t)(r + 2 * ty_dim) * drow, v2);
+            st_stream(dp + (int64_t)(r + 3 * ty_dim) * drow, v3);
+        }
+        for (; r < bh; r += ty_dim) {
+            V v = zero_v<V>();
+            if (sj >= 0) v = ld_stream(sp + (int64_t)r * srow);
+            st_stream(dp + (int64_t)r * drow, v);
+        }
+    }
+}
+
 template <typename V, bool STRETCH>
 __global__ void __launch_bounds__(kThreads) move_blocks_kernel(const MoveParams p) {
     extern __shared__ int16_t s_map[];
     const int tx = threadIdx.x % p.tx_dim, ty = threadIdx.x / p.tx_dim;
     const int dst_blocks = STRETCH ? p.Bx : p.small_bx;
     const int cols = dst_blocks * p.upb;
-    const int64_t srow = p.src_row / (int64_t)sizeof(V), drow = p.dst_row / (int64_t)sizeof(V);
 
     // grid-stride over (frame, block-row) units: the default grid has one CTA per unit; a capped
     // grid (tuning knob) keeps the kernel's footprint per SM fixed so that it can share the SMs
@@ -84,38 +120,11 @@ __global__ void __launch_bounds__(kThreads) move_blocks_kernel(const MoveParams 
         const int t = unit / p.By;
         const int by = unit - t * p.By;
         build_map<STRETCH>(p.mask + ((int64_t)t * p.By + by) * p.Bx, p.Bx, p.small_bx, s_map);
-        if (ty < p.ty_dim) {
-            const V* sbase = reinterpret_cast<const V*>(p.src + (int64_t)t * p.src_frame + (int64_t)by * p.bh * p.src_row);
-            V* dbase = reinterpret_cast<V*>(p.dst + (int64_t)t * p.dst_frame + (int64_t)by * p.bh * p.dst_row);
-            for (int c = tx; c < cols; c += p.tx_dim) {
-                const int j = c / p.upb;
-                const int u = c - j * p.upb;
-                const int sj = s_map[j];
-                const V* sp = sbase + (sj < 0 ? 0 : sj * p.upb + u);
-                V* dp = dbase + c;
-                int r = ty;
-                // four rows in flight per thread: all loads issued before the stores
-                for (; r + 3 * p.ty_dim < p.bh; r += 4 * p.ty_dim) {
-                    V v0 = zero_v<V>(), v1 = zero_v<V>(), v2 = zero_v<V>(), v3 = zero_v<V>();
-                    if (sj >= 0) {
-                        v0 = ld_stream(sp + (int64_t)r * srow);
-                        v1 = ld_stream(sp + (int64_t)(r + p.ty_dim) * srow);
-                        v2 = ld_stream(sp + (int64_t)(r + 2 * p.ty_dim) * srow);
-                        v3 = ld_stream(sp + (int64_t)(r + 3 * p.ty_dim) * srow);
-                    }
-                    st_stream(dp + (int64_t)r * drow, v0);
-                    st_stream(dp + (int64_t)(r + p.ty_dim) * drow, v1);
-                    st_stream(dp + (int64_t)(r + 2 * p.ty_dim) * drow, v2);
-                    st_stream(dp + (int64_t)(r + 3 * p.ty_dim) * drow, v3);
-                }
-                for (; r < p.bh; r += p.ty_dim) {
-                    V v = zero_v<V>();
-                    if (sj >= 0) v = ld_stream(sp + (int64_t)r * srow);
-                    st_stream(dp + (int64_t)r * drow, v);
-                }
-            }
-        }
-        __syncthreads();   // the column map is rebuilt for the next unit
+        if (ty < p.ty_dim)
+            copy_block_row<V>(p.src + (int64_t)t * p.src_frame + (int64_t)by * p.bh * p.src_row, p.src_row,
+                              p.dst + (int64_t)t * p.dst_frame + (int64_t)by * p.bh * p.dst_row, p.dst_row,
+                              s_map, cols, p.upb, p.bh, tx, ty, p.tx_dim, p.ty_dim);
+        if (unit + (int)gridDim.x < p.n_units) __syncthreads();   // the column map is rebuilt for the next unit
     }
 }
 
@@ -172,6 +181,85 @@ int launch_move(const elvis_plane* src, const elvis_plane* dst, int T, int block
     return ELVIS_OK;
 }
 
+
+// ---- planar YUV 4:2:0, luma blocks a multiple of 16 pixels: Y, U and V of one (frame, block row)
+// in ONE CTA -- the mask row is turned into the column map once, luma moves in 128-bit units and
+// the two chroma planes in 64-bit units, and a clip needs one launch instead of three.
+struct MoveYuvParams {
+    const uint8_t* src[3];
+    uint8_t* dst[3];
+    int64_t src_frame[3], src_row[3], dst_frame[3], dst_row[3];
+    const uint8_t* mask;
+    int32_t By, Bx, small_bx, bs, tx_dim, ty_dim, n_units;
+};
+
+template <bool STRETCH>
+__global__ void __launch_bounds__(kThreads) move_yuv420_kernel(const MoveYuvParams p) {
+    extern __shared__ int16_t s_map[];
+    const int tx = threadIdx.x % p.tx_dim, ty = threadIdx.x / p.tx_dim;
+    const int upb = p.bs / 16;                       // uint4 units per luma block row == uint2 units per chroma block row
+    const int cols = (STRETCH ? p.Bx : p.small_bx) * upb;
+    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+        const int t = unit / p.By;
+        const int by = unit - t * p.By;
+        build_map<STRETCH>(p.mask + ((int64_t)t * p.By + by) * p.Bx, p.Bx, p.small_bx, s_map);
+        if (ty < p.ty_dim) {
+            copy_block_row<uint4>(p.src[0] + (int64_t)t * p.src_frame[0] + (int64_t)by * p.bs * p.src_row[0], p.src_row[0],
+                                  p.dst[0] + (int64_t)t * p.dst_frame[0] + (int64_t)by * p.bs * p.dst_row[0], p.dst_row[0],
+                                  s_map, cols, upb, p.bs, tx, ty, p.tx_dim, p.ty_dim);
+#pragma unroll
+            for (int c = 1; c < 3; ++c)
+                copy_block_row<uint2>(p.src[c] + (int64_t)t * p.src_frame[c] + (int64_t)by * (p.bs / 2) * p.src_row[c], p.src_row[c],
+                                      p.dst[c] + (int64_t)t * p.dst_frame[c] + (int64_t)by * (p.bs / 2) * p.dst_row[c], p.dst_row[c],
+                                      s_map, cols, upb, p.bs / 2, tx, ty, p.tx_dim, p.ty_dim);
+        }
+        if (unit + (int)gridDim.x < p.n_units) __syncthreads();   // the column map is rebuilt for the next unit
+    }
+}
+
+template <bool STRETCH>
+int launch_move_yuv(const elvis_plane* src, const elvis_plane* dst, int T, int bs, int By, int Bx, int small_bx,
+                    const uint8_t* mask, int ctas_per_sm, cudaStream_t st) {
+    if (!src || !dst || !mask || T <= 0 || By <= 0 || Bx <= 0 || small_bx < 0 || small_bx > Bx || Bx > 32767) return ELVIS_ERR_INVALID_ARG;
+    if (bs <= 0 || bs % 16) return ELVIS_ERR_UNSUPPORTED;
+    MoveYuvParams p;
+    for (int c = 0; c < 3; ++c) {
+        const int pb = c == 0 ? bs : bs / 2, al = c == 0 ? 16 : 8;
+        const elvis_plane* full = STRETCH ? &dst[c] : &src[c];
+        const elvis_plane* small = STRETCH ? &src[c] : &dst[c];
+        if (!plane_ok(&src[c]) || !plane_ok(&dst[c]) || src[c].channels != 1 || dst[c].channels != 1) return ELVIS_ERR_INVALID_ARG;
+        if (full->height < By * pb || full->width < Bx * pb) return ELVIS_ERR_SHAPE;
+        if (small->height < By * pb || small->width < small_bx * pb) return ELVIS_ERR_SHAPE;
+        if (vector_unit(&src[c], pb) < al || vector_unit(&dst[c], pb) < al) return ELVIS_ERR_UNSUPPORTED;   // caller falls back per plane
+        p.src[c] = static_cast<const uint8_t*>(src[c].data);
+        p.dst[c] = static_cast<uint8_t*>(dst[c].data);
+        p.src_frame[c] = src[c].frame_stride;
+        p.src_row[c] = src[c].row_stride;
+        p.dst_frame[c] = dst[c].frame_stride;
+        p.dst_row[c] = dst[c].row_stride;
+    }
+    if (small_bx == 0 && !STRETCH) return ELVIS_OK;
+    p.mask = mask;
+    p.By = By;
+    p.Bx = Bx;
+    p.small_bx = small_bx;
+    p.bs = bs;
+    const int cols = (STRETCH ? Bx : small_bx) * (bs / 16);
+    int tx_dim = ((cols + 31) / 32) * 32;
+    if (tx_dim > kThreads) tx_dim = kThreads;
+    if (tx_dim < 32) tx_dim = 32;
+    p.tx_dim = tx_dim;
+    p.ty_dim = kThreads / tx_dim;
+    if (p.ty_dim > bs / 2) p.ty_dim = bs / 2;
+    p.n_units = (int)((int64_t)T * By);
+    unsigned grid = (unsigned)p.n_units;
+    if (ctas_per_sm > 0 && (unsigned)(ctas_per_sm * kNumSMs) < grid) grid = (unsigned)(ctas_per_sm * kNumSMs);
+    const size_t smem = sizeof(int16_t) * (size_t)(Bx > small_bx ? Bx : small_bx);
+    move_yuv420_kernel<STRETCH><<<grid, kThreads, smem, st>>>(p);
+    ELVIS_CHECK_LAUNCH();
+    return ELVIS_OK;
+}
+
 }  // namespace
 }  // namespace elvis
 
@@ -185,4 +273,16 @@ extern "C" int elvis_stretch(const elvis_plane* src, const elvis_plane* dst, int
                              int32_t block_px, int32_t by, int32_t bx, int32_t shrunk_bx,
                              const uint8_t* mask, int32_t ctas_per_sm, elvis_stream_t stream) {
     return elvis::launch_move<true>(src, dst, n_frames, block_px, by, bx, shrunk_bx, mask, ctas_per_sm, elvis::as_stream(stream));
+}
+
+extern "C" int elvis_shrink_yuv420(const elvis_plane* src_yuv, const elvis_plane* dst_yuv, int32_t n_frames,
+                                   int32_t block_size, int32_t by, int32_t bx, int32_t out_bx,
+                                   const uint8_t* mask, int32_t ctas_per_sm, elvis_stream_t stream) {
+    return elvis::launch_move_yuv<false>(src_yuv, dst_yuv, n_frames, block_size, by, bx, out_bx, mask, ctas_per_sm, elvis::as_stream(stream));
+}
+
+extern "C" int elvis_stretch_yuv420(const elvis_plane* src_yuv, const elvis_plane* dst_yuv, int32_t n_frames,
+                                    int32_t block_size, int32_t by, int32_t bx, int32_t shrunk_bx,
+                                    const uint8_t* mask, int32_t ctas_per_sm, elvis_stream_t stream) {
+    return elvis::launch_move_yuv<true>(src_yuv, dst_yuv, n_frames, block_size, by, bx, shrunk_bx, mask, ctas_per_sm, elvis::as_stream(stream));
 }

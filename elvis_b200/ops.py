@@ -18,7 +18,7 @@ from ._lib import (F32, F64, LEVELS_INVERTED_BINS, LEVELS_INVERTED_ROUND, LEVELS
                    REMOVE_LOW, Plane, call)
 
 __all__ = ["score_sc_tc", "minmax", "combine_removability", "normalize_", "importance_scores", "select_rows",
-           "shrink", "stretch", "levels_from_scores", "degrade_blur", "degrade_downsample", "dct_dampen",
+           "shrink", "stretch", "move_yuv420", "levels_from_scores", "degrade_blur", "degrade_downsample", "dct_dampen",
            "pack_mask_bits", "unpack_mask_bits", "pack_levels_2bit", "unpack_levels_2bit",
            "REMOVE_HIGH", "REMOVE_LOW", "LEVELS_ROUND", "LEVELS_INVERTED_ROUND", "LEVELS_INVERTED_BINS"]
 
@@ -237,6 +237,29 @@ def stretch(shrunk: torch.Tensor, mask: torch.Tensor, block_px: int, out: torch.
     src, dst = plane_of(shrunk), plane_of(out, "out")
     call("elvis_stretch", C.byref(src), C.byref(dst), T, block_px, by, bx, sbx, _ptr(mask), int(ctas_per_sm), _stream())
     return out
+
+
+def _yuv_planes(planes, name: str):
+    arr = (Plane * 3)(*[plane_of(p, name) for p in planes])
+    return arr
+
+
+def move_yuv420(src, dst, mask: torch.Tensor, block_size: int, small_bx: int, stretch_: bool, ctas_per_sm: int = 0) -> bool:
+    """Y, U and V of a planar 4:2:0 clip in one launch (src, dst: 3-tuples of (T, H, W) planes).
+    Returns False when the geometry is not supported by the fused kernel (caller falls back to
+    the per-plane operators)."""
+    mask = _mask_arg(mask)
+    T, by, bx = mask.shape
+    if block_size % 16:
+        return False
+    s, d = _yuv_planes(src, "src"), _yuv_planes(dst, "dst")
+    name = "elvis_stretch_yuv420" if stretch_ else "elvis_shrink_yuv420"
+    rc = getattr(_lib.lib, name)(s, d, T, block_size, by, bx, small_bx, _ptr(mask), int(ctas_per_sm), _stream())
+    if rc == _lib.ERR_UNSUPPORTED:
+        return False
+    if rc != 0:
+        call(name, s, d, T, block_size, by, bx, small_bx, _ptr(mask), int(ctas_per_sm), _stream())   # raises
+    return True
 
 
 # ------------------------------------------------------------------------------ a8-a12, a14

@@ -45,6 +45,18 @@ class Yuv420:
         return sum(p.numel() for p in self.planes)
 
 
+def move_planes(src: Yuv420, dst: Yuv420, mask: torch.Tensor, bs: int, small_bx: int, stretch_: bool,
+                ctas_per_sm: int = 0) -> None:
+    """Shrink or stretch the three planes: one fused launch when the geometry allows, else per plane."""
+    if small_bx > 0 and ops.move_yuv420(src.planes, dst.planes, mask, bs, small_bx, stretch_, ctas_per_sm):
+        return
+    for s, d, pb in ((src.y, dst.y, bs), (src.u, dst.u, bs // 2), (src.v, dst.v, bs // 2)):
+        if stretch_:
+            ops.stretch(s, mask, pb, out=d, ctas_per_sm=ctas_per_sm)
+        else:
+            ops.shrink(s, mask, pb, small_bx, out=d, ctas_per_sm=ctas_per_sm)
+
+
 class ElvisV1:
     """score -> per-row top-k mask -> shrink, and stretch (elvis.py:4350-4394, 4550-4557),
     for a planar clip resident on the GPU."""
@@ -71,18 +83,14 @@ class ElvisV1:
         mask = ops.select_rows(scores, k, ops.REMOVE_HIGH)
         if out is None:
             out = Yuv420.empty(clip.y.shape[0], by * self.bs, (bx - k) * self.bs, clip.y.device)
-        ops.shrink(clip.y, mask, self.bs, bx - k, out=out.y)
-        ops.shrink(clip.u, mask, self.bs // 2, bx - k, out=out.u)
-        ops.shrink(clip.v, mask, self.bs // 2, bx - k, out=out.v)
+        move_planes(clip, out, mask, self.bs, bx - k, stretch_=False)
         return out, mask
 
     def stretch(self, shrunk: Yuv420, mask: torch.Tensor, out: Optional[Yuv420] = None) -> Yuv420:
         t, by, bx = mask.shape
         if out is None:
             out = Yuv420.empty(t, by * self.bs, bx * self.bs, shrunk.y.device)
-        ops.stretch(shrunk.y, mask, self.bs, out=out.y)
-        ops.stretch(shrunk.u, mask, self.bs // 2, out=out.u)
-        ops.stretch(shrunk.v, mask, self.bs // 2, out=out.v)
+        move_planes(shrunk, out, mask, self.bs, shrunk.y.shape[2] // self.bs, stretch_=True)
         return out
 
     def run(self, clip: Yuv420, background: Optional[torch.Tensor] = None,
@@ -163,10 +171,8 @@ class ElvisV1Pipelined:
             self.s_move.wait_event(slot["scored"])
             ops.select_rows(slot["scores"], self.k, ops.REMOVE_HIGH, out=slot["mask"])
             sh, fu, bs = slot["shrunk"], slot["full"], self.pipe.bs
-            for src, dst, pb in ((clip.y, sh.y, bs), (clip.u, sh.u, bs // 2), (clip.v, sh.v, bs // 2)):
-                ops.shrink(src, slot["mask"], pb, sh.y.shape[2] // bs, out=dst, ctas_per_sm=self.move_ctas)
-            for src, dst, pb in ((sh.y, fu.y, bs), (sh.u, fu.u, bs // 2), (sh.v, fu.v, bs // 2)):
-                ops.stretch(src, slot["mask"], pb, out=dst, ctas_per_sm=self.move_ctas)
+            move_planes(clip, sh, slot["mask"], bs, sh.y.shape[2] // bs, False, self.move_ctas)
+            move_planes(sh, fu, slot["mask"], bs, sh.y.shape[2] // bs, True, self.move_ctas)
             slot["done"].record()
         slot["used"] = True
         return slot

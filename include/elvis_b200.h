@@ -142,6 +142,17 @@ ELVIS_API int elvis_stretch(const elvis_plane* src, const elvis_plane* dst, int3
                   int32_t block_px, int32_t by, int32_t bx, int32_t shrunk_bx,
                   const uint8_t* mask, int32_t ctas_per_sm, elvis_stream_t stream);
 
+/* ---- a4-a7 for planar YUV 4:2:0 clips: Y, U and V in one launch (the block mask computed from
+ * luma applies to the co-located (block_size/2)^2 chroma blocks).  src_yuv / dst_yuv: arrays of
+ * three planes {Y, U, V}.  Needs block_size % 16 == 0, 16-byte aligned luma and 8-byte aligned
+ * chroma planes; returns ELVIS_ERR_UNSUPPORTED otherwise (use the per-plane entry points). */
+ELVIS_API int elvis_shrink_yuv420(const elvis_plane* src_yuv, const elvis_plane* dst_yuv, int32_t n_frames,
+                        int32_t block_size, int32_t by, int32_t bx, int32_t out_bx,
+                        const uint8_t* mask, int32_t ctas_per_sm, elvis_stream_t stream);
+ELVIS_API int elvis_stretch_yuv420(const elvis_plane* src_yuv, const elvis_plane* dst_yuv, int32_t n_frames,
+                         int32_t block_size, int32_t by, int32_t bx, int32_t shrunk_bx,
+                         const uint8_t* mask, int32_t ctas_per_sm, elvis_stream_t stream);
+
 /* ---- a8-a12: level maps from scores.  scores float64 (n), levels int32 (n). */
 ELVIS_API int elvis_levels_from_scores(const double* scores, int64_t n, int32_t rule, int32_t param,
                              int32_t* levels, elvis_stream_t stream);
