@@ -90,7 +90,7 @@ struct CombineParams {
     const void* tc;
     const void* norm;
     const uint8_t* background;
-    int32_t t_begin, t_count, is_first, is_last, smooth;
+    int32_t t_begin, t_count, is_first, is_last, smooth, chunk_len;
     int64_t frame;   // By * Bx
     double alpha, one_minus_alpha, beta, one_minus_beta;
     double* out;
@@ -112,25 +112,32 @@ template <typename T> __device__ __forceinline__ double removability_at(const Co
     return r;
 }
 
+// One thread owns one block position and walks a chunk of consecutive frames, so that the
+// un-smoothed value of frame t is computed once and carried in a register into frame t+1
+// (each value costs two correctly rounded fp64 divisions -- the kernel's whole cost).
 template <typename T> __global__ void __launch_bounds__(kThreads) combine_kernel(const CombineParams p) {
     const T* nm = static_cast<const T*>(p.norm);
     const double sc_lo = (double)nm[0], sc_hi = (double)nm[1], tc_lo = (double)nm[2], tc_hi = (double)nm[3];
     double lo = __longlong_as_double(0x7ff0000000000000LL), hi = __longlong_as_double(0xfff0000000000000LL);
-    const int64_t total = p.frame * p.t_count;
-    for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < total; g += (int64_t)gridDim.x * kThreads) {
-        const int tl = (int)(g / p.frame);
-        const int64_t i = g - (int64_t)tl * p.frame;
-        const int t = p.t_begin + tl;
-        const bool clip_last = p.is_last && tl == p.t_count - 1;
-        const bool clip_first = p.is_first && tl == 0;
-        double r = removability_at<T>(p, t, i, clip_last, sc_lo, sc_hi, tc_lo, tc_hi);
-        if (p.smooth && !clip_first) {                               // elvis.py:1206-1213
-            const double rp = removability_at<T>(p, t - 1, i, false, sc_lo, sc_hi, tc_lo, tc_hi);
-            r = __dadd_rn(__dmul_rn(p.beta, r), __dmul_rn(p.one_minus_beta, rp));
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int tl0 = blockIdx.y * p.chunk_len;
+    const int tl1 = min(p.t_count, tl0 + p.chunk_len);
+    if (i < p.frame && tl0 < tl1) {
+        double r_prev = 0.0;
+        if (p.smooth && !(p.is_first && tl0 == 0))
+            r_prev = removability_at<T>(p, p.t_begin + tl0 - 1, i, false, sc_lo, sc_hi, tc_lo, tc_hi);
+        for (int tl = tl0; tl < tl1; ++tl) {
+            const bool clip_last = p.is_last && tl == p.t_count - 1;
+            const bool clip_first = p.is_first && tl == 0;
+            const double r = removability_at<T>(p, p.t_begin + tl, i, clip_last, sc_lo, sc_hi, tc_lo, tc_hi);
+            double v = r;
+            if (p.smooth && !clip_first)                                 // elvis.py:1206-1213
+                v = __dadd_rn(__dmul_rn(p.beta, r), __dmul_rn(p.one_minus_beta, r_prev));
+            r_prev = r;
+            p.out[(int64_t)tl * p.frame + i] = v;
+            lo = fmin(lo, v);
+            hi = fmax(hi, v);
         }
-        p.out[g] = r;
-        lo = fmin(lo, r);
-        hi = fmax(hi, r);
     }
     block_minmax_commit(lo, hi, p.out_minmax);
 }
@@ -273,7 +280,14 @@ extern "C" int elvis_combine_removability(const void* sc, const void* tc, int32_
     cudaStream_t st = as_stream(stream);
     minmax_init<<<1, 32, 0, st>>>(out_minmax);
     ELVIS_CHECK_LAUNCH();
-    const int grid = grid_for(p.frame * t_count);
+    // enough CTAs for ~4 per SM; every chunk recomputes one carried value, so keep chunks >= 8 frames
+    const int gx = (int)((p.frame + kThreads - 1) / kThreads);
+    int chunks = (4 * kNumSMs + gx - 1) / gx;
+    if (chunks > (t_count + 7) / 8) chunks = (t_count + 7) / 8;
+    if (chunks < 1) chunks = 1;
+    p.chunk_len = (t_count + chunks - 1) / chunks;
+    chunks = (t_count + p.chunk_len - 1) / p.chunk_len;
+    const dim3 grid((unsigned)gx, (unsigned)chunks);
     if (dtype == ELVIS_F32)
         combine_kernel<float><<<grid, kThreads, 0, st>>>(p);
     else
