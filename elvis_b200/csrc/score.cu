@@ -29,6 +29,10 @@ __device__ constexpr float kW[8][8] = {
 };
 
 constexpr int kScoreThreads = 128;
+#ifndef ELVIS_SCORE_MIN_CTAS
+#define ELVIS_SCORE_MIN_CTAS 2
+#endif
+constexpr int kScoreMinCtas = ELVIS_SCORE_MIN_CTAS;   // resident CTAs per SM the register budget is sized for
 #ifndef ELVIS_PACKED_PAIRS
 #define ELVIS_PACKED_PAIRS 4
 #endif
@@ -56,7 +60,7 @@ __device__ __forceinline__ void load_tile(uint2 (&dst)[8], const uint8_t* p, int
 }
 
 template <int R, bool ALIGNED>
-__global__ void __launch_bounds__(kScoreThreads, 2) score_kernel(const ScoreParams p) {
+__global__ void __launch_bounds__(kScoreThreads, kScoreMinCtas) score_kernel(const ScoreParams p) {
     constexpr int TW = 32 / R;   // tiles per warp-tile row
     const int lane = threadIdx.x & 31;
     const int unit = blockIdx.x * (kScoreThreads / 32) + (threadIdx.x >> 5);
