@@ -205,11 +205,13 @@ def run_ours(args):
 
     # (2) the timed region: the same steps through the two-stream pipeline (scoring of clip i+1
     # overlaps shrink + stretch of clip i; every clip goes through the full serial path)
-    score_fn = None
-    if world > 1:
-        score_fn = lambda c, slot: sharding.sharded_removability(halo, T * world, BLOCK, ALPHA, BETA, rank, world)  # noqa: E731
+    score_fn = comm_fn = None
+    if world > 1:   # halo exchange ahead of time on the communication stream, all-reduces inside the score stage
+        comm_fn = lambda c: sharding.exchange_halo(halo, rank, world)  # noqa: E731
+        score_fn = lambda c, slot: sharding.sharded_removability(halo, T * world, BLOCK, ALPHA, BETA, rank, world,  # noqa: E731
+                                                                 exchange=False)
     pp = ElvisV1Pipelined(T, HEIGHT, WIDTH, BLOCK, SHRINK, ALPHA, BETA, dev, depth=args.depth, score_fn=score_fn,
-                          move_ctas_per_sm=args.move_ctas)
+                          move_ctas_per_sm=args.move_ctas, comm_fn=comm_fn)
     if args.serial:
         def run(n):
             for _ in range(n):

@@ -116,7 +116,7 @@ class ElvisV1Pipelined:
 
     def __init__(self, n_frames: int, height: int, width: int, block_size: int = 16, shrink_amount: float = 0.5,
                  alpha: float = 0.5, beta: float = 0.5, device="cuda", depth: int = 2, score_fn=None,
-                 move_ctas_per_sm: int = 3):
+                 move_ctas_per_sm: int = 3, comm_fn=None):
         self.pipe = ElvisV1(block_size, shrink_amount, alpha, beta)
         self.dev = torch.device(device)
         # footprint of the shrink/stretch kernels per SM while they share it with the scoring
@@ -132,6 +132,11 @@ class ElvisV1Pipelined:
         self.s_score = torch.cuda.Stream(self.dev, priority=0)
         self.s_move = torch.cuda.Stream(self.dev, priority=-1)
         self.score_fn = score_fn      # optional: clip, slot -> scores (e.g. the sharded scorer)
+        # optional: clip -> None, communication the scorer depends on (the halo exchange of the
+        # sharded path).  It runs on a third stream as soon as the clip is submitted, i.e. while
+        # the previous clip is still being scored, and the score stage waits for it.
+        self.comm_fn = comm_fn
+        self.s_comm = torch.cuda.Stream(self.dev, priority=-1) if comm_fn is not None else None
         self.slots = []
         for _ in range(depth):
             self.slots.append({
@@ -154,8 +159,17 @@ class ElvisV1Pipelined:
         self._next = (self._next + 1) % len(self.slots)
         ready = torch.cuda.Event()
         ready.record()                                   # inputs produced on the caller's stream
+        comm_done = None
+        if self.comm_fn is not None:
+            with torch.cuda.stream(self.s_comm):
+                self.s_comm.wait_event(ready)
+                self.comm_fn(clip)
+                comm_done = torch.cuda.Event()
+                comm_done.record()
         with torch.cuda.stream(self.s_score):
             self.s_score.wait_event(ready)
+            if comm_done is not None:
+                self.s_score.wait_event(comm_done)
             if slot["used"]:
                 self.s_score.wait_event(slot["done"])    # the slot's previous clip has left the move stage
             if self.score_fn is not None:

@@ -66,28 +66,37 @@ def exchange_halo(clip: HaloClip, rank: int, world: int, group=None) -> None:
         req.wait()
 
 
+_signs: dict = {}
+
+
 def allreduce_minmax(mm: torch.Tensor, world: int, group=None) -> torch.Tensor:
     """In-place exact all-reduce of interleaved {min, max, min, max, ...}: one MAX reduction
     of {-min, max, ...}."""
     if world == 1:
         return mm
-    sign = torch.ones_like(mm)
-    sign[0::2] = -1
-    v = mm * sign
-    dist.all_reduce(v, op=dist.ReduceOp.MAX, group=group)
-    mm.copy_(v * sign)
+    key = (mm.device, mm.dtype, mm.numel())
+    sign = _signs.get(key)
+    if sign is None:
+        sign = torch.ones_like(mm)
+        sign[0::2] = -1
+        _signs[key] = sign
+    mm.mul_(sign)
+    dist.all_reduce(mm, op=dist.ReduceOp.MAX, group=group)
+    mm.mul_(sign)
     return mm
 
 
 def sharded_removability(clip: HaloClip, n_frames_total: int, block_size: int, alpha: float, beta: float,
                          rank: int, world: int, background: Optional[torch.Tensor] = None, kernels=None,
-                         group=None) -> torch.Tensor:
+                         group=None, exchange: bool = True) -> torch.Tensor:
     """elvis-mode removability (elvis.py:1160-1220) of the owned frames -> (n, By, Bx) float64.
     background: optional uint8 (n+2, By, Bx) laid out like clip.buf (halo slots filled by the
-    caller when it has the neighbours' masks; only slot 0 is ever read)."""
+    caller when it has the neighbours' masks; only slot 0 is ever read).  exchange=False: the
+    caller has already run exchange_halo (e.g. ahead of time on a communication stream)."""
     if kernels is None:
         from . import ops as kernels
-    exchange_halo(clip, rank, world, group)
+    if exchange:
+        exchange_halo(clip, rank, world, group)
     ext, first = clip.extended(rank, world)
     sc, tc, norm = kernels.score_sc_tc(ext, block_size, minmax_range=(first, first + clip.n))
     allreduce_minmax(norm, world, group)
