@@ -267,7 +267,10 @@ def run_ours(args):
               "score_kernel_alone": {"ms": sc_ms, "gbs": ab["score"] * T / sc_ms / 1e6}}
     achieved = ab["score"] * T / sc_ms / 1e6
     roofline = {"bound": "hbm", "kernel": "score_kernel<2,true> (elvis_score_sc_tc)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch over the 120-frame clip,
+                # ncu --set full capture profiles/r1c_ncu_full_summary.csv (1.0037e9 + 0.0339e9)
+                "traffic": 1.0375e9 if T == FRAMES else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ab["score"] * T,
                 "whole_step": {"achieved": ab["total"] * T / ms_per_step / 1e6, "frac": ab["total"] * T / ms_per_step / 1e6 / peak,
                                "note": "all three stages, pipelined as timed"},

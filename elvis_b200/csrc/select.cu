@@ -108,24 +108,29 @@ __global__ void __launch_bounds__(256) select_rows_warp_kernel(
         int need = k;
         unsigned round = 0;
         while (need > 0) {
-            const int total = __reduce_add_sync(0xffffffffu, __popc(active));
+            // inclusive scan of the per-lane active counts
+            const int cnt = __popc(active);
+            int pre = cnt;
+#pragma unroll
+            for (int m = 1; m < 32; m <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, pre, m);
+                if (lane >= m) pre += o;
+            }
+            const int total = __shfl_sync(0xffffffffu, pre, 31);
             if (total <= need) {   // (== by the loop invariant) every remaining candidate is removed
                 selected |= active;
                 break;
             }
-            // pivot: first candidate of a pseudo-randomly chosen lane that still has one
-            // (reproducible; any candidate is a valid pivot, the choice only affects the round count)
-            const unsigned have = __ballot_sync(0xffffffffu, active != 0);
+            // pivot: the r-th active element, r pseudo-random but reproducible
             const unsigned h = ((unsigned)row * 2654435761u) ^ (round * 0x9E3779B9u + 0x7F4A7C15u);
-            const int nth = (int)__umulhi(h * 2246822519u, (unsigned)__popc(have));
-            const int src_lane = __fns(have, 0, nth + 1);
-            const bool mine = lane == src_lane;
+            const int r = (int)__umulhi(h * 2246822519u, (unsigned)total);
+            const bool mine = (pre - cnt <= r) && (r < pre);
+            const int src_lane = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
             unsigned long long pk = 0;
             int pslot = 0;
             if (mine) {
                 unsigned a = active;
-                // rotate the choice inside the lane as well
-                for (int skip = (int)((h >> 27) % (unsigned)__popc(active)); skip > 0; --skip) a &= a - 1;
+                for (int skip = r - (pre - cnt); skip > 0; --skip) a &= a - 1;   // drop the lowest set bits
                 pslot = __ffs(a) - 1;
 #pragma unroll
                 for (int j = 0; j < E; ++j)
