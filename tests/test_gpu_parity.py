@@ -416,3 +416,92 @@ def test_pipelined_equals_serial(dev):
     torch.cuda.synchronize()
     assert torch.equal(s1["mask"], ref[0][1]) and torch.equal(s2["mask"], ref[1][1])
     assert torch.equal(s1["full"].y, ref[0][3].y) and torch.equal(s2["full"].y, ref[1][3].y)
+
+
+@pytest.mark.parametrize("bs,T,amount", [(8, 3, 0.25), (32, 2, 0.5), (16, 1, 0.5), (16, 3, 0.0), (16, 2, 1.0), (16, 2, 7)])
+def test_planar_pipeline_edge_configs(dev, bs, T, amount):
+    """Other block sizes (4x4 / 16x16 chroma blocks -> per-plane kernels), single-frame clips (no
+    smoothing, elvis.py:1202), nothing / one block / an absolute count removed (elvis.py:1392-1396)."""
+    from elvis_b200.pipeline import ElvisV1, Yuv420
+    H, W = bs * 4, bs * 10
+    y, u, v = synth_yuv420(T, H, W, seed=bs + T)
+    clip = Yuv420(to_dev(y, dev), to_dev(u, dev), to_dev(v, dev))
+    scores, mask, shrunk, full = ElvisV1(bs, amount, 0.4, 0.5).run(clip)
+    scores, mask = scores.cpu().numpy(), mask.cpu().numpy()
+    rsc, rtc = spec_scoring.sc_tc(y, bs)
+    np.testing.assert_allclose(scores, P.combine_removability(rsc, rtc, 0.4, 0.5), rtol=RTOL, atol=1e-9)
+    k = P.blocks_to_remove_elvis(amount, W // bs)
+    assert np.array_equal(mask, P.select_rows(scores, k, P.REMOVE_HIGH)) and (mask.sum(-1) == k).all()
+    for name, plane, pb in (("y", y, bs), ("u", u, bs // 2), ("v", v, bs // 2)):
+        for t in range(T):
+            r_s = P.shrink_plane(plane[t], mask[t], pb)
+            assert np.array_equal(getattr(shrunk, name)[t].cpu().numpy(), r_s), (name, t)
+            assert np.array_equal(getattr(full, name)[t].cpu().numpy(), P.stretch_plane(r_s, mask[t], pb)), (name, t)
+
+
+def test_host_pipeline_matches_device_pipeline(dev):
+    """HostElvisV1 (pinned host buffers in/out, two streams) returns what ElvisV1 computes."""
+    import torch
+    from elvis_b200.pipeline import ElvisV1, HostElvisV1, Yuv420
+    T, H, W, bs = 4, 64, 160, 16
+    host = HostElvisV1(T, H, W, bs, 0.5, 0.5, 0.5, dev, depth=2)
+    outs = [host.host_buffers(pinned=True) for _ in range(2)]
+    clips, events = [], []
+    for i in range(3):
+        y, u, v = synth_yuv420(T, H, W, seed=40 + i)
+        i420 = torch.from_numpy(np.concatenate([y.reshape(T, -1), u.reshape(T, -1), v.reshape(T, -1)], axis=1)).pin_memory()
+        clips.append((y, u, v, i420))
+    for i, (y, u, v, i420) in enumerate(clips):
+        ev = host.process(i420, *outs[i % 2])
+        ev.synchronize()
+        shrunk_h, full_h, mask_h = outs[i % 2]
+        ref = ElvisV1(bs, 0.5, 0.5, 0.5).run(Yuv420(to_dev(y, dev), to_dev(u, dev), to_dev(v, dev)))
+        assert torch.equal(mask_h, ref[1].cpu())
+        sw = ref[2].y.shape[2]
+        s = Yuv420.from_i420(shrunk_h, H, sw)
+        f = Yuv420.from_i420(full_h, H, W)
+        for a, b in zip(s.planes, ref[2].planes):
+            assert torch.equal(a, b.cpu())
+        for a, b in zip(f.planes, ref[3].planes):
+            assert torch.equal(a, b.cpu())
+    assert host.h2d_bytes == T * H * W * 3 // 2
+
+
+def test_sharding_world_one_equals_local(dev):
+    """The sharded scorers with a single rank (no communication) equal the local pipeline."""
+    import torch
+    from elvis_b200 import sharding
+    from elvis_b200.pipeline import ElvisV1, Yuv420
+    T, H, W, bs = 5, 48, 96, 16
+    y, u, v = synth_yuv420(T, H, W, seed=77)
+    halo = sharding.HaloClip(T, H, W, dev)
+    halo.owned.copy_(to_dev(y, dev))
+    got = sharding.sharded_removability(halo, T, bs, 0.5, 0.5, 0, 1)
+    ref = ElvisV1(bs, 0.5, 0.5, 0.5).score(Yuv420(to_dev(y, dev), to_dev(u, dev), to_dev(v, dev)))
+    assert torch.equal(got, ref)
+    imp = sharding.sharded_importance(halo, bs, 0.5, 0.5, 0, 1).cpu().numpy()
+    rsc, rtc = spec_scoring.sc_tc(y, bs)
+    np.testing.assert_allclose(imp, P.importance_scores(rsc, rtc, 0.5, 0.5, np.ones_like(rsc)), rtol=RTOL, atol=1e-7)
+
+
+def test_api_errors_and_strided_inputs(dev):
+    import torch
+    from elvis_b200 import ops
+    y = to_dev(synth_luma(2, 32, 64, seed=1), dev)
+    with pytest.raises(Exception):
+        ops.score_sc_tc(y, 12)                        # unsupported block size
+    with pytest.raises(ValueError):
+        ops.shrink(y, torch.zeros((2, 2, 4), dtype=torch.uint8, device=dev), 12, 2)   # 32 % 12 != 0
+    with pytest.raises(TypeError):
+        ops.select_rows(torch.zeros((1, 2, 3), dtype=torch.float32, device=dev), 1)
+    # a non-contiguous (column-cropped) clip goes through the strided path of shrink/stretch
+    wide = to_dev(np.random.default_rng(0).integers(0, 256, (2, 32, 96), dtype=np.uint8), dev)
+    crop = wide[:, :, 16:80]
+    mask = (torch.rand((2, 2, 4), device=dev) > 0.5).to(torch.uint8)
+    mask[:, :, 0] = 0
+    mask[:, :, 1] = 1
+    mask[:, :, 2] = 0
+    mask[:, :, 3] = 1
+    s = ops.shrink(crop, mask, 16, 2)
+    for t in range(2):
+        assert np.array_equal(s[t].cpu().numpy(), P.shrink_plane(crop[t].cpu().numpy(), mask[t].cpu().numpy(), 16))
