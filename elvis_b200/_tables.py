@@ -130,3 +130,28 @@ def all_fast(pb: int, small_sizes: tuple) -> bool:
     blob = build(pb, tuple(small_sizes))
     st = level_stride(pb)
     return pb in (8, 16) and all(int(blob[i * st + 5]) == 1 for i in range(len(small_sizes)))
+
+
+def gaussian_kernels(max_level: int) -> np.ndarray:
+    """int32 (max_level + 1, 6 * max_level + 2): row L = {ksize, q[0..ksize)} -- cv2's 8.8
+    fixed-point Gaussian for sigma = L and ksize = (0, 0) on 8-bit images: the exact Gaussian,
+    normalised, times 256, rounded with error diffusion over the first half (centre included) and
+    mirrored, so that it sums to 256.  Row 0 is unused."""
+    stride = 6 * max_level + 2
+    tab = np.zeros((max_level + 1, stride), np.int32)
+    for level in range(1, max_level + 1):
+        ksize = int(round(level * 6 + 1)) | 1
+        r = ksize // 2
+        x = np.arange(-r, r + 1, dtype=np.float64)
+        k = np.exp(-(x * x) / (2.0 * level * level))
+        k /= k.sum()
+        carry = 0.0
+        q = np.zeros(ksize, np.int64)
+        for i in range(r + 1):
+            v = k[i] * 256 + carry
+            q[i] = math.floor(v + 0.5)
+            carry = v - q[i]
+        q[r + 1:] = q[:r][::-1]
+        tab[level, 0] = ksize
+        tab[level, 1:1 + ksize] = q
+    return tab

@@ -157,6 +157,15 @@ def filter_frame_gaussian(image: np.ndarray, frame_scores: np.ndarray, block_siz
     return out[0].cpu().numpy(), rounds[0].cpu().numpy()
 
 
+# ---------------------------------------------------------------- OpenCV client restorer (8f rank 1)
+def restore_blur_opencv_unsharp_mask(blurred_image: np.ndarray, blur_maps: np.ndarray, block_size: int) -> np.ndarray:
+    """elvis.py:2822-2867 -- per-block unsharp mask, radius = blur rounds, amount = rounds / 2."""
+    if blurred_image.shape[0] % block_size or blurred_image.shape[1] % block_size:
+        raise ValueError("Image dimensions must be divisible by block_size.")
+    levels = _to_dev(np.asarray(blur_maps), np.int32)[None]
+    return ops.restore_unsharp(_packed_clip(blurred_image), levels, block_size)[0].cpu().numpy()
+
+
 # ---------------------------------------------------------------- side channels
 def encode_strength_maps_to_npz(strength_maps: np.ndarray, output_path: str) -> None:
     """elvis.py:2247-2259 (uint8 maps, np.savez_compressed key `strength_maps`)."""

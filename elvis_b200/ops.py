@@ -19,7 +19,7 @@ from ._lib import (F32, F64, LEVELS_INVERTED_BINS, LEVELS_INVERTED_ROUND, LEVELS
 
 __all__ = ["score_sc_tc", "minmax", "combine_removability", "normalize_", "importance_scores", "select_rows",
            "shrink", "stretch", "move_yuv420", "levels_from_scores", "degrade_blur", "degrade_downsample", "dct_dampen",
-           "pack_mask_bits", "unpack_mask_bits", "pack_levels_2bit", "unpack_levels_2bit",
+           "restore_unsharp", "temporal_blend_", "pack_mask_bits", "unpack_mask_bits", "pack_levels_2bit", "unpack_levels_2bit",
            "REMOVE_HIGH", "REMOVE_LOW", "LEVELS_ROUND", "LEVELS_INVERTED_ROUND", "LEVELS_INVERTED_BINS"]
 
 
@@ -321,6 +321,35 @@ def dct_dampen(clip: torch.Tensor, strength: torch.Tensor, block_px: int, out: t
     src, dst = plane_of(clip), plane_of(out, "out")
     call("elvis_dct_dampen", C.byref(src), C.byref(dst), T, block_px, by, bx, _ptr(strength), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------ 8f rank 1
+_kernel_cache: dict = {}
+
+
+def restore_unsharp(clip: torch.Tensor, levels: torch.Tensor, block_px: int, halo: int = 0, max_level: int | None = None,
+                    out: torch.Tensor | None = None) -> torch.Tensor:
+    """Per-block unsharp mask (radius = level, amount = level / 2) -- the OpenCV client restorer.
+    max_level: largest level in the map (computed with a device sync when None)."""
+    T, by, bx, out = _degrade_args(clip, levels, block_px, torch.int32, out)
+    if max_level is None:
+        max_level = max(1, int(levels.max().item()))
+    key = (max_level, str(clip.device))
+    tab = _kernel_cache.get(key)
+    if tab is None:
+        tab = torch.from_numpy(_tables.gaussian_kernels(max_level)).to(clip.device)
+        _kernel_cache[key] = tab
+    src, dst = plane_of(clip), plane_of(out, "out")
+    call("elvis_restore_unsharp", C.byref(src), C.byref(dst), T, block_px, by, bx, _ptr(levels), int(halo), _ptr(tab),
+         max_level, tab.shape[1], _stream())
+    return out
+
+
+def temporal_blend_(clip: torch.Tensor, temporal_blend: float) -> torch.Tensor:
+    """In place: frame[t] = uint8(tb * frame[t-1] + (1 - tb) * frame[t]) for t >= 1."""
+    pl = plane_of(clip)
+    call("elvis_temporal_blend", C.byref(pl), clip.shape[0], float(temporal_blend), _stream())
+    return clip
 
 
 # ------------------------------------------------------------------------------ a13

@@ -91,3 +91,29 @@ def degrade_adaptive_blur(frame: np.ndarray, importance: np.ndarray, block_size:
     rounds = ops.levels_from_scores(imp, ops.LEVELS_INVERTED_ROUND, max_rounds)
     out = ops.degrade_blur(_packed_clip(frame), rounds, block_size)
     return out[0].cpu().numpy(), rounds[0].cpu().numpy()
+
+
+def restore_with_opencv_unsharp(frames: List[np.ndarray], degradation_maps: np.ndarray, block_size: int, halo: int = 0,
+                                temporal_blend: float = 0.0, **kwargs) -> List[np.ndarray]:
+    """utils.py:1320-1392: per-block unsharp mask driven by the level map, optional context halo
+    and temporal blending; the whole clip in one batch."""
+    if len(frames) == 0:
+        return []
+    clip = _to_dev(np.stack(frames), np.uint8)
+    by, bx = clip.shape[1] // block_size, clip.shape[2] // block_size
+    maps = np.zeros((len(frames), by, bx), np.int32)
+    for i in range(min(len(frames), len(degradation_maps))):
+        m = np.asarray(degradation_maps[i])
+        if m.shape != (by, bx):      # utils.py:1343-1345 (host-side nearest resize of the map)
+            import cv2
+            m = cv2.resize(m.astype(np.float32), (bx, by), interpolation=cv2.INTER_NEAREST).astype(np.int32)
+        maps[i] = m
+    out = ops.restore_unsharp(clip, _to_dev(maps), block_size, halo=halo, max_level=max(1, int(maps.max())))
+    if temporal_blend > 0:
+        ops.temporal_blend_(out, temporal_blend)
+    out = out.cpu().numpy()
+    return [out[i] for i in range(len(frames))]
+
+
+# utils.py:1253-1317: despite its name the reference's "lanczos" restorer runs the same unsharp mask
+restore_with_opencv_lanczos = restore_with_opencv_unsharp

@@ -184,6 +184,24 @@ ELVIS_API int elvis_dct_dampen(const elvis_plane* src, const elvis_plane* dst, i
                      int32_t block_px, int32_t by, int32_t bx, const float* strength,
                      elvis_stream_t stream);
 
+/* ---- 8f rank 1: OpenCV client restorer -- per-block unsharp mask (elvis.py:2822-2867
+ * restore_blur_opencv_unsharp_mask; utils.py:1253-1392 restore_with_opencv_lanczos /
+ * restore_with_opencv_unsharp).  levels: int32 (T, By, Bx); a block with level L > 0 becomes
+ * addWeighted(tile, 1 + L/2, GaussianBlur(tile, (0,0), L), -L/2) where tile = the block plus
+ * `halo` pixels of context clamped to the frame (utils.py:1227-1250); other pixels are copied.
+ * kernels: device table [max_level + 1][kernel_stride] of {ksize, q[ksize]} 8.8 fixed-point
+ * Gaussian kernels (elvis_b200/_tables.py:gaussian_kernels); levels above max_level use the
+ * last row.  src and dst must not overlap. */
+ELVIS_API int elvis_restore_unsharp(const elvis_plane* src, const elvis_plane* dst, int32_t n_frames,
+                          int32_t block_px, int32_t by, int32_t bx, const int32_t* levels,
+                          int32_t halo, const int32_t* kernels, int32_t max_level, int32_t kernel_stride,
+                          elvis_stream_t stream);
+
+/* In-place temporal blending of a clip (utils.py:1310-1311): for t >= 1,
+ * frame[t] = uint8(tb * frame[t-1] + (1 - tb) * frame[t]) in float64, frame[t-1] already blended. */
+ELVIS_API int elvis_temporal_blend(const elvis_plane* clip, int32_t n_frames, double temporal_blend,
+                         elvis_stream_t stream);
+
 /* ---- a13: side-channel packers.  Bit packing is np.packbits-compatible (elvis.py:4414):
  * flat over n values, MSB first, last byte zero padded.  The 2-bit level packer is new
  * (README.md:50 TODO): per row of bx levels, ceil(bx/4) bytes, level i in bits

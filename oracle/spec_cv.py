@@ -158,3 +158,49 @@ def resize_linear(small: np.ndarray, dsize: int) -> np.ndarray:
 def down_up(block: np.ndarray, small: int) -> np.ndarray:
     """AREA down to small x small then LINEAR up to the block size (elvis.py:2160-2163)."""
     return resize_linear(resize_area(block, small), block.shape[-1])
+
+
+# ------------------------------------------------- GaussianBlur(tile, (0, 0), sigma) + addWeighted
+def gaussian_kernel_q8(sigma: float) -> np.ndarray:
+    """cv2's 8.8 fixed-point Gaussian kernel for u8 images when ksize = (0, 0): ksize =
+    round(6 sigma + 1) | 1; exact Gaussian normalised to 1, scaled by 256 and rounded with
+    error diffusion over the first half (incl. the centre), then mirrored -- sums to 256.
+    (sigma = 1 gives [1, 14, 62, 102, 62, 14, 1]; pinned against cv2 in tests/test_oracle.py.)"""
+    ksize = int(round(sigma * 6 + 1)) | 1
+    r = ksize // 2
+    x = np.arange(-r, r + 1, dtype=np.float64)
+    k = np.exp(-x * x / (2.0 * sigma * sigma))
+    k /= k.sum()
+    q = np.zeros(ksize, np.int64)
+    err = 0.0
+    for i in range(r + 1):
+        v = k[i] * 256 + err
+        q[i] = int(np.floor(v + 0.5))
+        err = v - q[i]
+    q[r + 1:] = q[:r][::-1]
+    return q
+
+
+def gaussian_blur_sigma(tile: np.ndarray, sigma: float) -> np.ndarray:
+    """cv2.GaussianBlur(tile, (0, 0), sigma) on an isolated 2-D u8 tile (REFLECT_101 at its edges,
+    reflected as often as needed when the kernel is wider than the tile)."""
+    q = gaussian_kernel_q8(sigma)
+    r = len(q) // 2
+    h, w = tile.shape[-2:]
+    cols = np.array([[_reflect101(x + d, w) for d in range(-r, r + 1)] for x in range(w)])
+    rows = np.array([[_reflect101(y + d, h) for d in range(-r, r + 1)] for y in range(h)])
+    s = tile.astype(np.int64)
+    hp = (s[..., :, cols] * q).sum(axis=-1)
+    vp = (hp[..., rows, :] * q[:, None]).sum(axis=-2)
+    return ((vp + 32768) >> 16).astype(np.uint8)
+
+
+def unsharp(tile: np.ndarray, level: int) -> np.ndarray:
+    """cv2.addWeighted(tile, 1 + a, GaussianBlur(tile, (0,0), max(1, level)), -a, 0), a = level/2
+    (elvis.py:2852-2861, utils.py:1296-1300).  2*result = 2x + level*(x - blur) exactly, so the
+    float rounding of cv2 is a round-half-to-even of an integer over 2, then saturation."""
+    b = gaussian_blur_sigma(tile, max(1, int(level))).astype(np.int64)
+    n = 2 * tile.astype(np.int64) + int(level) * (tile.astype(np.int64) - b)
+    half = n >> 1                                   # floor(n / 2)
+    out = half + ((n & 1) & (half & 1))             # odd n: round to the even neighbour
+    return np.clip(out, 0, 255).astype(np.uint8)

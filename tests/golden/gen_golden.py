@@ -79,6 +79,16 @@ def main():
         g[f"a10_out_{bs}"], g[f"a10_map_{bs}"] = U.degrade_adaptive_downsample(im2, s, bs)
         g[f"a11_out_{bs}"], g[f"a11_map_{bs}"] = U.degrade_adaptive_blur(im2, s, bs)
 
+    # 8f rank 1 -- OpenCV client restorers (unsharp mask; halo + temporal blend variants)
+    rimg = rng.integers(0, 256, (48, 80, 3), dtype=np.uint8)
+    rmap = rng.integers(0, 11, (3, 5))
+    g.update(f1_img=rimg, f1_map=rmap, f1_out=E.restore_blur_opencv_unsharp_mask(rimg, rmap, 16))
+    rframes = np.stack([rng.integers(0, 256, (37, 53, 3), dtype=np.uint8) for _ in range(3)])
+    rmaps = rng.integers(0, 5, (3, 2, 3))
+    g.update(f1_frames=rframes, f1_maps=rmaps)
+    for tag, halo, tb in (("h0", 0, 0.0), ("h6b", 6, 0.2)):
+        g[f"f1_out_{tag}"] = np.stack(U.restore_with_opencv_unsharp(list(rframes), rmaps, 16, halo=halo, temporal_blend=tb))
+
     # a13 -- mask side channel (elvis.py:4412-4418)
     masks = (rng.random((3, 5, 7)) > 0.5).astype(np.int8)
     g["a13_masks"] = masks

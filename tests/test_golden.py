@@ -65,6 +65,11 @@ def _check_all(impl):
         assert np.array_equal(small, G[f"a6_small_{tag}"]), tag
         assert np.array_equal(impl.stretch_frame_row_only(small, mask, 8), G[f"a7_full_{tag}"]), tag
 
+    assert np.array_equal(impl.restore_blur_opencv_unsharp_mask(G["f1_img"], G["f1_map"], 16), G["f1_out"])
+    for tag, halo, tb in (("h0", 0, 0.0), ("h6b", 6, 0.2)):
+        got = impl.restore_with_opencv_unsharp(list(G["f1_frames"]), G["f1_maps"], 16, halo=halo, temporal_blend=tb)
+        assert np.array_equal(np.stack(got), G[f"f1_out_{tag}"]), tag
+
     for bs in (8, 16):
         s = G[f"a8_scores_{bs}"]
         for fn, key in (("filter_frame_downsample", "a8"), ("filter_frame_gaussian", "a9")):

@@ -505,3 +505,41 @@ def test_api_errors_and_strided_inputs(dev):
     s = ops.shrink(crop, mask, 16, 2)
     for t in range(2):
         assert np.array_equal(s[t].cpu().numpy(), P.shrink_plane(crop[t].cpu().numpy(), mask[t].cpu().numpy(), 16))
+
+
+# ---------------------------------------------------------------------------------- 8f rank 1
+@pytest.mark.parametrize("bs", [8, 16])
+def test_unsharp_restorer_elvis(dev, bs):
+    from elvis_b200 import elvis as E
+    rng = np.random.default_rng(bs + 100)
+    img = rng.integers(0, 256, (bs * 3, bs * 5, 3), dtype=np.uint8)
+    maps = rng.integers(0, 11, (3, 5))
+    maps[0, 0] = 0
+    assert np.array_equal(E.restore_blur_opencv_unsharp_mask(img, maps, bs), P.restore_blur_opencv_unsharp_mask(img, maps, bs))
+
+
+@pytest.mark.parametrize("halo,tb", [(0, 0.0), (4, 0.0), (8, 0.1), (0, 0.3), (20, 0.25)])
+def test_unsharp_restorer_utils(dev, halo, tb):
+    from elvis_b200 import utils as U
+    rng = np.random.default_rng(halo + 7)
+    frames = [rng.integers(0, 256, (53, 85, 3), dtype=np.uint8) for _ in range(4)]
+    maps = rng.integers(0, 5, (4, 3, 5))
+    got = U.restore_with_opencv_unsharp(frames, maps, 16, halo=halo, temporal_blend=tb)
+    ref = P.restore_with_opencv_unsharp(frames, maps, 16, halo, tb)
+    assert len(got) == 4 and all(np.array_equal(a, b) for a, b in zip(got, ref))
+    assert all(np.array_equal(a, b) for a, b in zip(U.restore_with_opencv_lanczos(frames, maps, 16, halo=halo, temporal_blend=tb), ref))
+    # fewer maps than frames: the rest is returned untouched (utils.py:1341)
+    got = U.restore_with_opencv_unsharp(frames, maps[:2], 16)
+    assert np.array_equal(got[3], frames[3]) and np.array_equal(got[2], frames[2])
+
+
+def test_unsharp_restorer_planar(dev):
+    from elvis_b200 import ops
+    y, u, _ = synth_yuv420(3, 64, 96, seed=12)
+    rng = np.random.default_rng(3)
+    lv = rng.integers(0, 5, (3, 4, 6)).astype(np.int32)
+    out_y = ops.restore_unsharp(to_dev(y, dev), to_dev(lv, dev), 16).cpu().numpy()
+    out_u = ops.restore_unsharp(to_dev(u, dev), to_dev(lv, dev), 8, halo=2).cpu().numpy()
+    for t in range(3):
+        assert np.array_equal(out_y[t], P.unsharp_plane(y[t], lv[t], 16))
+        assert np.array_equal(out_u[t], P.unsharp_plane(u[t], lv[t], 8, halo=2))

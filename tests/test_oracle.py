@@ -118,6 +118,38 @@ def test_port_matches_reference_v2_and_scores():
     assert np.array_equal(np.stack(U.calculate_importance_scores(None, 16, 0.3, 0.6, cx, f)), P.importance_scores(s, t, 0.3, 0.6, f))
 
 
+def test_sigma_gaussian_and_unsharp_bit_exact_vs_cv2():
+    rng = np.random.default_rng(5)
+    for level in range(1, 11):
+        for shape in ((16, 16), (8, 8), (24, 20), (16, 27)):
+            t = rng.integers(0, 256, shape, dtype=np.uint8)
+            bl = cv2.GaussianBlur(t, (0, 0), max(1, level))
+            assert np.array_equal(bl, spec_cv.gaussian_blur_sigma(t, max(1, level))), (level, shape)
+            ref = np.clip(cv2.addWeighted(t, 1.0 + level * 0.5, bl, -level * 0.5, 0), 0, 255).astype(np.uint8)
+            assert np.array_equal(ref, spec_cv.unsharp(t, level)), (level, shape)
+    from elvis_b200 import _tables as T
+    tab = T.gaussian_kernels(10)
+    for level in range(1, 11):
+        q = spec_cv.gaussian_kernel_q8(level)
+        assert q.sum() == 256 and tab[level, 0] == len(q) and np.array_equal(tab[level, 1:1 + len(q)], q)
+
+
+@needs_reference
+def test_port_matches_reference_restorers():
+    E, U = ref_import.load("elvis"), ref_import.load("utils")
+    rng = np.random.default_rng(6)
+    img = rng.integers(0, 256, (48, 80, 3), dtype=np.uint8)
+    maps = rng.integers(0, 5, (3, 5))
+    assert np.array_equal(E.restore_blur_opencv_unsharp_mask(img, maps, 16), P.restore_blur_opencv_unsharp_mask(img, maps, 16))
+    frames = [rng.integers(0, 256, (53, 85, 3), dtype=np.uint8) for _ in range(3)]
+    dm = rng.integers(0, 5, (3, 3, 5))
+    for halo, tb in ((0, 0.0), (8, 0.1), (20, 0.25)):
+        ref = U.restore_with_opencv_unsharp(frames, dm, 16, halo=halo, temporal_blend=tb)
+        ref2 = U.restore_with_opencv_lanczos(frames, dm, 16, halo=halo, temporal_blend=tb)
+        mine = P.restore_with_opencv_unsharp(frames, dm, 16, halo, tb)
+        assert all(np.array_equal(a, b) for a, b in zip(ref, mine)) and all(np.array_equal(a, b) for a, b in zip(ref2, mine))
+
+
 # ---------------------------------------------------------------------------- properties
 @settings(max_examples=40, deadline=None)
 @given(st.integers(1, 6), st.integers(2, 12), st.sampled_from([4, 8, 16]), st.floats(0, 0.99), st.integers(0, 2 ** 31))
