@@ -49,6 +49,7 @@ SIGNATURES = {
     "elvis_degrade_downsample": [_PP, _PP, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp],
     "elvis_dct_dampen": [_PP, _PP, _i32, _i32, _i32, _i32, _vp, _vp],
     "elvis_restore_unsharp": [_PP, _PP, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp],
+    "elvis_restore_lanczos": [_PP, _PP, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
     "elvis_temporal_blend": [_PP, _i32, _f64, _vp],
     "elvis_pack_mask_bits": [_vp, _i64, _vp, _vp],
     "elvis_unpack_mask_bits": [_vp, _i64, _vp, _vp],

@@ -13,8 +13,36 @@ import numpy as np
 KIND_COPY, KIND_2X2, KIND_INT, KIND_FRAC = 0, 1, 2, 3
 
 
-def level_stride(pb: int) -> int:
-    return 8 + (pb + 1) + 4 * pb + 8 * pb
+def level_stride(pb: int, lanczos: bool = False) -> int:
+    return 8 + (pb + 1) + 4 * pb + (16 if lanczos else 8) * pb
+
+
+def _lanczos4_taps(ssize: int, dsize: int):
+    """cv2 INTER_LANCZOS4 (u8): (dsize, 8) clamped source indices and 11-bit integer weights."""
+    s45 = 0.70710678118654752440084436210485
+    cs = ((1, 0), (-s45, -s45), (0, 1), (s45, -s45), (-1, 0), (s45, s45), (0, -1), (-s45, s45))
+    idx = np.zeros((dsize, 8), np.int32)
+    coef = np.zeros((dsize, 8), np.int32)
+    f32 = np.float32
+    for d in range(dsize):
+        pos = (d + 0.5) * (ssize / dsize) - 0.5
+        base = math.floor(pos)
+        x = f32(pos - base)
+        w = np.zeros(8, np.float32)
+        if x < np.finfo(np.float32).eps:
+            w[3] = 1
+        else:
+            y0 = f32(-(x + 3) * f32(np.pi) * f32(0.25))
+            s0, c0 = f32(np.sin(y0)), f32(np.cos(y0))
+            total = f32(0)
+            for i in range(8):
+                y = f32(-(x + 3 - i) * f32(np.pi) * f32(0.25))
+                w[i] = f32((cs[i][0] * s0 + cs[i][1] * c0) / (y * y))
+                total = f32(total + w[i])
+            w = (w * (f32(1.0) / total)).astype(np.float32)
+        coef[d] = np.clip(np.rint(w * f32(2048)), -32768, 32767).astype(np.int32)
+        idx[d] = np.clip(np.arange(base - 3, base + 5), 0, ssize - 1)
+    return idx, coef
 
 
 def fast_stride(pb: int) -> int:
@@ -64,10 +92,11 @@ def _area_entries(ssize: int, dsize: int):
 
 
 @lru_cache(maxsize=64)
-def build(pb: int, small_sizes: tuple) -> np.ndarray:
+def build(pb: int, small_sizes: tuple, lanczos: bool = False) -> np.ndarray:
     """int32 blob with one entry per level; small_sizes[level] is the side the block is
-    reduced to (== pb: the level copies the block)."""
-    stride = level_stride(pb)
+    reduced to (== pb: the level copies the block).  lanczos=True: the up-sampling taps are the
+    8-tap INTER_LANCZOS4 table instead of the two bilinear tap blocks (no fast part)."""
+    stride = level_stride(pb, lanczos)
     blob = np.zeros((len(small_sizes), stride), np.int32)
     for lv, small in enumerate(small_sizes):
         small = int(small)
@@ -91,6 +120,11 @@ def build(pb: int, small_sizes: tuple) -> np.ndarray:
             ent[:len(src), 0] = src
             ent[:len(src), 1] = alpha.view(np.int32)
         off = 8 + pb + 1 + 4 * pb
+        if lanczos:
+            idx, coef = _lanczos4_taps(small, pb)
+            e[off:off + 8 * pb] = idx.reshape(-1)
+            e[off + 8 * pb:off + 16 * pb] = coef.reshape(-1)
+            continue
         for horizontal in (True, False):
             i0, i1, c0, c1 = _linear_taps(small, pb, horizontal)
             e[off:off + pb] = i0
@@ -98,6 +132,8 @@ def build(pb: int, small_sizes: tuple) -> np.ndarray:
             e[off + 2 * pb:off + 3 * pb] = c0
             e[off + 3 * pb:off + 4 * pb] = c1
             off += 4 * pb
+    if lanczos:
+        return blob.reshape(-1)
     # fast-path tables (planar 8/16-pixel blocks, power-of-two reductions): when every 11-bit
     # horizontal coefficient of a level is a multiple of 64 the two taps of an output pixel
     # become byte weights over the (<= 8 byte) source row, so that

@@ -244,8 +244,12 @@ __global__ void __launch_bounds__(256) blur_fast_kernel(const BlockGeom g, const
 //   [8 .. 8+pb]            area_start[0..pb]  (entries of destination index d: [start[d], start[d+1]))
 //   then 2*pb entries x {src_index, float-bits alpha}
 //   then horizontal linear taps i0[pb] i1[pb] c0[pb] c1[pb], then vertical ones likewise.
-__host__ __device__ inline int level_stride(int pb) { return 8 + (pb + 1) + 2 * pb * 2 + 8 * pb; }
+// With LANCZOS the two bilinear tap blocks are replaced by ONE 8-tap table (cv2 INTER_LANCZOS4 for
+// u8: idx[pb][8] clamped source indices, coef[pb][8] 11-bit integer weights, used for both axes;
+// result = (sum + 2^21) >> 22, saturated) -- oracle/spec_cv.py:lanczos4_taps / resize_lanczos4.
+__host__ __device__ inline int level_stride(int pb, bool lanczos = false) { return 8 + (pb + 1) + 2 * pb * 2 + (lanczos ? 16 : 8) * pb; }
 
+template <bool LANCZOS>
 __global__ void __launch_bounds__(256) downsample_kernel(const BlockGeom g, const int32_t* __restrict__ levels,
                                                          const int32_t* __restrict__ tables, int n_levels, int warps_per_cta) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(256) downsample_kernel(const BlockGeom g, cons
         decode_unit(g, unit, t, by, bx, c);
         int lv = levels[((int64_t)t * g.By + by) * g.Bx + bx];
         lv = lv < 0 ? 0 : (lv >= n_levels ? n_levels - 1 : lv);
-        const int32_t* tab = tables + (size_t)lv * level_stride(pb);
+        const int32_t* tab = tables + (size_t)lv * level_stride(pb, LANCZOS);
         const int small = tab[0], kind = tab[1];
         const uint8_t* sp = g.src + (int64_t)t * g.src_frame + (int64_t)by * pb * g.src_row + ((int64_t)bx * pb) * g.C + c;
         uint8_t* dp = g.dst + (int64_t)t * g.dst_frame + (int64_t)by * pb * g.dst_row + ((int64_t)bx * pb) * g.C + c;
@@ -318,25 +322,46 @@ __global__ void __launch_bounds__(256) downsample_kernel(const BlockGeom g, cons
             }
         }
         __syncwarp();
-        // bilinear back up: horizontal pass into Bi[small][pb] (11-bit coefficients)
         const int32_t* lh = tab + 8 + (pb + 1) + 4 * pb;
-        const int32_t* lvt = lh + 4 * pb;
-        for (int i = lane; i < small * pb; i += 32) {
-            const int y = i / pb, d = i - y * pb;
-            Bi[i] = S[y * small + lh[d]] * lh[2 * pb + d] + S[y * small + lh[pb + d]] * lh[3 * pb + d];
-        }
-        __syncwarp();
-        for (int i = lane; i < n; i += 32) {
-            const int d2 = i / pb, d = i - d2 * pb;
-            const int r0 = Bi[lvt[d2] * pb + d] >> 4, r1 = Bi[lvt[pb + d2] * pb + d] >> 4;
-            int v = (((lvt[2 * pb + d2] * r0) >> 16) + ((lvt[3 * pb + d2] * r1) >> 16) + 2) >> 2;
-            v = v < 0 ? 0 : (v > 255 ? 255 : v);
-            dp[(int64_t)d2 * g.dst_row + d * g.C] = (uint8_t)v;
+        if (LANCZOS) {
+            const int32_t* idx = lh;
+            const int32_t* coef = lh + 8 * pb;
+            for (int i = lane; i < small * pb; i += 32) {        // horizontal 8-tap pass into Bi[small][pb]
+                const int y = i / pb, d = i - y * pb;
+                int acc = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc += S[y * small + idx[d * 8 + k]] * coef[d * 8 + k];
+                Bi[i] = acc;
+            }
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) {                 // vertical 8-tap pass, (sum + 2^21) >> 22
+                const int d2 = i / pb, d = i - d2 * pb;
+                int acc = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc += Bi[idx[d2 * 8 + k] * pb + d] * coef[d2 * 8 + k];
+                int v = (acc + (1 << 21)) >> 22;
+                v = v < 0 ? 0 : (v > 255 ? 255 : v);
+                dp[(int64_t)d2 * g.dst_row + d * g.C] = (uint8_t)v;
+            }
+        } else {
+            // bilinear back up: horizontal pass into Bi[small][pb] (11-bit coefficients)
+            const int32_t* lvt = lh + 4 * pb;
+            for (int i = lane; i < small * pb; i += 32) {
+                const int y = i / pb, d = i - y * pb;
+                Bi[i] = S[y * small + lh[d]] * lh[2 * pb + d] + S[y * small + lh[pb + d]] * lh[3 * pb + d];
+            }
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) {
+                const int d2 = i / pb, d = i - d2 * pb;
+                const int r0 = Bi[lvt[d2] * pb + d] >> 4, r1 = Bi[lvt[pb + d2] * pb + d] >> 4;
+                int v = (((lvt[2 * pb + d2] * r0) >> 16) + ((lvt[3 * pb + d2] * r1) >> 16) + 2) >> 2;
+                v = v < 0 ? 0 : (v > 255 ? 255 : v);
+                dp[(int64_t)d2 * g.dst_row + d * g.C] = (uint8_t)v;
+            }
         }
         __syncwarp();
     }
 }
-
 
 // ----------------------------------------------------------------- downsample, fast path
 // Planar planes, 16- or 8-pixel blocks, power-of-two reductions (the elvis 1x/2x/4x/8x(/16x)
@@ -678,7 +703,7 @@ extern "C" int elvis_degrade_downsample(const elvis_plane* src, const elvis_plan
     while (wpc > 1 && (size_t)wpc * n * 6 > 48 * 1024) wpc >>= 1;
     const size_t smem = (size_t)wpc * n * 6;
     const int64_t units = (int64_t)n_frames * by * bx * g.C;
-    downsample_kernel<<<grid_for_units(units, wpc), wpc * 32, smem, st>>>(g, levels, tables, n_levels, wpc);
+    downsample_kernel<false><<<grid_for_units(units, wpc), wpc * 32, smem, st>>>(g, levels, tables, n_levels, wpc);
     ELVIS_CHECK_LAUNCH();
     return ELVIS_OK;
 }
@@ -700,6 +725,24 @@ extern "C" int elvis_dct_dampen(const elvis_plane* src, const elvis_plane* dst, 
         dampen_kernel<true><<<grid, 128, 0, st>>>(g, strength);
     else
         dampen_kernel<false><<<grid, 128, 0, st>>>(g, strength);
+    ELVIS_CHECK_LAUNCH();
+    return ELVIS_OK;
+}
+
+extern "C" int elvis_restore_lanczos(const elvis_plane* src, const elvis_plane* dst, int32_t n_frames,
+                                     int32_t block_px, int32_t by, int32_t bx, const int32_t* levels,
+                                     const int32_t* tables, int32_t n_levels, elvis_stream_t stream) {
+    BlockGeom g;
+    if (int rc = make_geom(src, dst, n_frames, block_px, by, bx, g)) return rc;
+    if (!levels || !tables || n_levels <= 0) return ELVIS_ERR_INVALID_ARG;
+    if (block_px > 64) return ELVIS_ERR_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    if (int rc = copy_edges(g, st)) return rc;
+    const int n = block_px * block_px;
+    int wpc = 8;
+    while (wpc > 1 && (size_t)wpc * n * 6 > 48 * 1024) wpc >>= 1;
+    const int64_t units = (int64_t)n_frames * by * bx * g.C;
+    downsample_kernel<true><<<grid_for_units(units, wpc), wpc * 32, (size_t)wpc * n * 6, st>>>(g, levels, tables, n_levels, wpc);
     ELVIS_CHECK_LAUNCH();
     return ELVIS_OK;
 }

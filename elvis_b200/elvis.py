@@ -166,6 +166,20 @@ def restore_blur_opencv_unsharp_mask(blurred_image: np.ndarray, blur_maps: np.nd
     return ops.restore_unsharp(_packed_clip(blurred_image), levels, block_size)[0].cpu().numpy()
 
 
+def restore_downsample_opencv_lanczos(downsampled_image: np.ndarray, downscale_maps: np.ndarray, block_size: int) -> np.ndarray:
+    """elvis.py:2773-2820 -- per block with factor 2**level > 1: INTER_AREA down to
+    max(1, block_size // factor), INTER_LANCZOS4 back up."""
+    if downsampled_image.shape[0] % block_size or downsampled_image.shape[1] % block_size:
+        raise ValueError("Image dimensions must be divisible by block_size.")
+    maps = np.asarray(downscale_maps)
+    top = max(0, int(maps.max())) if maps.size else 0
+    if top == 0:                       # elvis.py:2793-2795: nothing was downsampled
+        return downsampled_image
+    smalls = [block_size] + [max(1, block_size // (2 ** lv)) for lv in range(1, top + 1)]
+    levels = _to_dev(np.clip(maps, 0, top), np.int32)[None]
+    return ops.restore_lanczos(_packed_clip(downsampled_image), levels, block_size, smalls)[0].cpu().numpy()
+
+
 # ---------------------------------------------------------------- side channels
 def encode_strength_maps_to_npz(strength_maps: np.ndarray, output_path: str) -> None:
     """elvis.py:2247-2259 (uint8 maps, np.savez_compressed key `strength_maps`)."""

@@ -19,7 +19,7 @@ from ._lib import (F32, F64, LEVELS_INVERTED_BINS, LEVELS_INVERTED_ROUND, LEVELS
 
 __all__ = ["score_sc_tc", "minmax", "combine_removability", "normalize_", "importance_scores", "select_rows",
            "shrink", "stretch", "move_yuv420", "levels_from_scores", "degrade_blur", "degrade_downsample", "dct_dampen",
-           "restore_unsharp", "temporal_blend_", "pack_mask_bits", "unpack_mask_bits", "pack_levels_2bit", "unpack_levels_2bit",
+           "restore_unsharp", "restore_lanczos", "temporal_blend_", "pack_mask_bits", "unpack_mask_bits", "pack_levels_2bit", "unpack_levels_2bit",
            "REMOVE_HIGH", "REMOVE_LOW", "LEVELS_ROUND", "LEVELS_INVERTED_ROUND", "LEVELS_INVERTED_BINS"]
 
 
@@ -294,11 +294,11 @@ def degrade_blur(clip: torch.Tensor, rounds: torch.Tensor, block_px: int, out: t
 _table_cache: dict = {}
 
 
-def _device_tables(block_px: int, small_sizes: tuple, device) -> torch.Tensor:
-    key = (block_px, small_sizes, str(device))
+def _device_tables(block_px: int, small_sizes: tuple, device, lanczos: bool = False) -> torch.Tensor:
+    key = (block_px, small_sizes, str(device), lanczos)
     t = _table_cache.get(key)
     if t is None:
-        t = torch.from_numpy(_tables.build(block_px, small_sizes).copy()).to(device)
+        t = torch.from_numpy(_tables.build(block_px, small_sizes, lanczos).copy()).to(device)
         _table_cache[key] = t
     return t
 
@@ -342,6 +342,17 @@ def restore_unsharp(clip: torch.Tensor, levels: torch.Tensor, block_px: int, hal
     src, dst = plane_of(clip), plane_of(out, "out")
     call("elvis_restore_unsharp", C.byref(src), C.byref(dst), T, block_px, by, bx, _ptr(levels), int(halo), _ptr(tab),
          max_level, tab.shape[1], _stream())
+    return out
+
+
+def restore_lanczos(clip: torch.Tensor, levels: torch.Tensor, block_px: int, small_sizes, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Per block: INTER_AREA down to small_sizes[level], INTER_LANCZOS4 back up (elvis.py:2773-2820)."""
+    T, by, bx, out = _degrade_args(clip, levels, block_px, torch.int32, out)
+    small_sizes = tuple(int(s) for s in small_sizes)
+    tab = _device_tables(block_px, small_sizes, clip.device, lanczos=True)
+    src, dst = plane_of(clip), plane_of(out, "out")
+    call("elvis_restore_lanczos", C.byref(src), C.byref(dst), T, block_px, by, bx, _ptr(levels), _ptr(tab),
+         len(small_sizes), _stream())
     return out
 
 

@@ -197,6 +197,13 @@ ELVIS_API int elvis_restore_unsharp(const elvis_plane* src, const elvis_plane* d
                           int32_t halo, const int32_t* kernels, int32_t max_level, int32_t kernel_stride,
                           elvis_stream_t stream);
 
+/* restore_downsample_opencv_lanczos (elvis.py:2773-2820): per block with level > 0, INTER_AREA
+ * down to the level's small size and INTER_LANCZOS4 back up.  tables: the blob of
+ * elvis_b200/_tables.py:build(..., lanczos=True). */
+ELVIS_API int elvis_restore_lanczos(const elvis_plane* src, const elvis_plane* dst, int32_t n_frames,
+                          int32_t block_px, int32_t by, int32_t bx, const int32_t* levels,
+                          const int32_t* tables, int32_t n_levels, elvis_stream_t stream);
+
 /* In-place temporal blending of a clip (utils.py:1310-1311): for t >= 1,
  * frame[t] = uint8(tb * frame[t-1] + (1 - tb) * frame[t]) in float64, frame[t-1] already blended. */
 ELVIS_API int elvis_temporal_blend(const elvis_plane* clip, int32_t n_frames, double temporal_blend,

@@ -204,3 +204,45 @@ def unsharp(tile: np.ndarray, level: int) -> np.ndarray:
     half = n >> 1                                   # floor(n / 2)
     out = half + ((n & 1) & (half & 1))             # odd n: round to the even neighbour
     return np.clip(out, 0, 255).astype(np.uint8)
+
+
+# -------------------------------------------------------------------------- INTER_LANCZOS4
+def lanczos4_taps(ssize: int, dsize: int):
+    """Source indices (dsize, 8) and 11-bit integer coefficients (dsize, 8) of cv2's u8
+    INTER_LANCZOS4 resize: float32 Lanczos-4 weights (cv2's sin/cos recurrence), normalised,
+    times 2048, rounded to short; source indices clamped to the image."""
+    s45 = 0.70710678118654752440084436210485
+    cs = np.array([[1, 0], [-s45, -s45], [0, 1], [s45, -s45], [-1, 0], [s45, s45], [0, -1], [-s45, s45]], np.float64)
+    scale = float(ssize) / float(dsize)
+    idx = np.zeros((dsize, 8), np.int32)
+    coef = np.zeros((dsize, 8), np.int32)
+    for d in range(dsize):
+        fx = (d + 0.5) * scale - 0.5
+        sx = int(np.floor(fx))
+        x = np.float32(fx - sx)
+        c = np.zeros(8, np.float32)
+        if x < np.finfo(np.float32).eps:
+            c[3] = 1
+        else:
+            y0 = np.float32(-(x + 3) * np.float32(np.pi) * np.float32(0.25))
+            s0, c0 = np.float32(np.sin(y0)), np.float32(np.cos(y0))
+            total = np.float32(0)
+            for i in range(8):
+                y = np.float32(-(x + 3 - i) * np.float32(np.pi) * np.float32(0.25))
+                c[i] = np.float32((cs[i][0] * s0 + cs[i][1] * c0) / (y * y))
+                total = np.float32(total + c[i])
+            c = (c * (np.float32(1.0) / total)).astype(np.float32)
+        coef[d] = np.clip(np.rint(c * np.float32(2048)), -32768, 32767).astype(np.int32)
+        idx[d] = np.clip(np.arange(sx - 3, sx + 5), 0, ssize - 1)
+    return idx, coef
+
+
+def resize_lanczos4(small: np.ndarray, dsize: int) -> np.ndarray:
+    """cv2.resize(small, (dsize, dsize), interpolation=cv2.INTER_LANCZOS4) for square u8 blocks
+    (..., s, s): 8-tap horizontal pass in int32, 8-tap vertical pass, (acc + 2^21) >> 22, saturate."""
+    ssize = small.shape[-1]
+    idx, coef = lanczos4_taps(ssize, dsize)
+    s = small.astype(np.int64)
+    rows = (s[..., :, idx] * coef).sum(axis=-1)                                  # (..., ssize, dsize)
+    out = (rows[..., idx, :] * coef[:, :, None]).sum(axis=-2)                    # (..., dsize, dsize)
+    return np.clip((out + (1 << 21)) >> 22, 0, 255).astype(np.uint8)

@@ -543,3 +543,14 @@ def test_unsharp_restorer_planar(dev):
     for t in range(3):
         assert np.array_equal(out_y[t], P.unsharp_plane(y[t], lv[t], 16))
         assert np.array_equal(out_u[t], P.unsharp_plane(u[t], lv[t], 8, halo=2))
+
+
+@pytest.mark.parametrize("bs", [8, 16, 32])
+def test_lanczos_restorer_elvis(dev, bs):
+    from elvis_b200 import elvis as E
+    rng = np.random.default_rng(bs + 200)
+    img = rng.integers(0, 256, (bs * 3, bs * 5, 3), dtype=np.uint8)
+    maps = rng.integers(0, 7, (3, 5))
+    assert np.array_equal(E.restore_downsample_opencv_lanczos(img, maps, bs), P.restore_downsample_opencv_lanczos(img, maps, bs))
+    zero = np.zeros((3, 5), int)
+    assert E.restore_downsample_opencv_lanczos(img, zero, bs) is img

@@ -134,6 +134,18 @@ def test_sigma_gaussian_and_unsharp_bit_exact_vs_cv2():
         assert q.sum() == 256 and tab[level, 0] == len(q) and np.array_equal(tab[level, 1:1 + len(q)], q)
 
 
+def test_lanczos4_bit_exact_vs_cv2():
+    rng = np.random.default_rng(8)
+    from elvis_b200 import _tables as T
+    for bs, small in ((16, 8), (16, 4), (16, 2), (16, 1), (8, 4), (8, 2), (8, 1), (32, 8), (12, 6), (24, 3)):
+        s = rng.integers(0, 256, (4, small, small), dtype=np.uint8)
+        mine = spec_cv.resize_lanczos4(s, bs)
+        for i in range(4):
+            assert np.array_equal(cv2.resize(s[i], (bs, bs), interpolation=cv2.INTER_LANCZOS4), mine[i]), (bs, small)
+        a, b = T._lanczos4_taps(small, bs), spec_cv.lanczos4_taps(small, bs)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
 @needs_reference
 def test_port_matches_reference_restorers():
     E, U = ref_import.load("elvis"), ref_import.load("utils")
@@ -141,6 +153,10 @@ def test_port_matches_reference_restorers():
     img = rng.integers(0, 256, (48, 80, 3), dtype=np.uint8)
     maps = rng.integers(0, 5, (3, 5))
     assert np.array_equal(E.restore_blur_opencv_unsharp_mask(img, maps, 16), P.restore_blur_opencv_unsharp_mask(img, maps, 16))
+    for bs in (8, 16):
+        im = rng.integers(0, 256, (bs * 3, bs * 5, 3), dtype=np.uint8)
+        lm = rng.integers(0, 6, (3, 5))
+        assert np.array_equal(E.restore_downsample_opencv_lanczos(im, lm, bs), P.restore_downsample_opencv_lanczos(im, lm, bs))
     frames = [rng.integers(0, 256, (53, 85, 3), dtype=np.uint8) for _ in range(3)]
     dm = rng.integers(0, 5, (3, 3, 5))
     for halo, tb in ((0, 0.0), (8, 0.1), (20, 0.25)):
