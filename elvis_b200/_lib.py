@@ -55,6 +55,10 @@ SIGNATURES = {
     "elvis_unpack_mask_bits": [_vp, _i64, _vp, _vp],
     "elvis_pack_levels_2bit": [_vp, _i64, _i32, _vp, _vp],
     "elvis_unpack_levels_2bit": [_vp, _i64, _i32, _vp, _vp],
+    "elvis_rowcol_plan": [_vp, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
+    "elvis_rowcol_expand": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp],
+    "elvis_invert_block_map": [_vp, _i32, _i64, _vp, _i64, _vp],
+    "elvis_gather_blocks": [_PP, _PP, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp],
 }
 EXPORTS = ["elvis_abi_version", "elvis_error_string", "elvis_last_cuda_error", *SIGNATURES]
 

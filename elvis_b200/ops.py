@@ -401,3 +401,98 @@ def unpack_levels_2bit(packed: torch.Tensor, bx: int) -> torch.Tensor:
     out = torch.empty(tuple(p.shape[:-1]) + (bx,), dtype=torch.int32, device=p.device)
     call("elvis_unpack_levels_2bit", _ptr(p), rows, bx, _ptr(out), _stream())
     return out
+
+
+# ---------------------------------------------------------------- row+column shrink (8f rank 2)
+def rowcol_dims(by: int, bx: int, target: int):
+    """Pass structure of utils.py:790-836 / 893-948, which depends on the grid size and the
+    removal target only -> (final_by, final_bx, blocks removed per pass)."""
+    counts = []
+    removed = 0
+    while removed < target and by > 0 and bx > 0:
+        n = min(by, target - removed)
+        counts.append(n)
+        removed += n
+        if n == by:
+            bx -= 1
+        if removed >= target or bx <= 0:
+            break
+        n = min(bx, target - removed)
+        counts.append(n)
+        removed += n
+        if n == bx:
+            by -= 1
+    return by, bx, counts
+
+
+def rowcol_plan(importance: torch.Tensor, target: int):
+    """importance (T, By, Bx) float64 -> (mask uint8 (T, By, Bx), position int32 (T, By, Bx),
+    pass_indices int32 (T, P, max(By, Bx)), pass_counts int32 (T, P), meta int32 (T, 4))."""
+    _check_cuda(importance, torch.float64, "importance")
+    if importance.dim() != 3:
+        raise ValueError("importance must be (T, By, Bx)")
+    importance = importance.contiguous()
+    T, by, bx = importance.shape
+    dev = importance.device
+    max_passes = by + bx + 2
+    keys = torch.empty((T, by, bx), dtype=torch.int64, device=dev)
+    pos = torch.empty((T, by, bx), dtype=torch.int32, device=dev)
+    mask = torch.empty((T, by, bx), dtype=torch.uint8, device=dev)
+    pidx = torch.zeros((T, max_passes, max(by, bx)), dtype=torch.int32, device=dev)
+    pcnt = torch.zeros((T, max_passes), dtype=torch.int32, device=dev)
+    meta = torch.zeros((T, 4), dtype=torch.int32, device=dev)
+    call("elvis_rowcol_plan", _ptr(importance), T, by, bx, int(target), _ptr(keys), _ptr(pos), _ptr(mask), _ptr(pidx),
+         _ptr(pcnt), max_passes, _ptr(meta), _stream())
+    return mask, pos, pidx, pcnt, meta
+
+
+def rowcol_expand(pass_indices: torch.Tensor, pass_counts: torch.Tensor, shrunk_by: int, shrunk_bx: int) -> torch.Tensor:
+    """pass_indices (T, P, L) / pass_counts (T, P) int32 -> grid int32 (T, shrunk_by + #column
+    passes, shrunk_bx + #row passes) of shrunk linear block indices, -1 = black block."""
+    _check_cuda(pass_indices, torch.int32, "pass_indices")
+    _check_cuda(pass_counts, torch.int32, "pass_counts")
+    T, P, L = pass_indices.shape
+    gh, gw = shrunk_by + P // 2, shrunk_bx + (P + 1) // 2
+    grid = torch.empty((T, gh, gw), dtype=torch.int32, device=pass_indices.device)
+    if grid.numel() == 0:
+        return grid
+    call("elvis_rowcol_expand", _ptr(pass_indices.contiguous()), _ptr(pass_counts.contiguous()), T, P, max(L, 1), shrunk_by,
+         shrunk_bx, _ptr(grid), gh, gw, _stream())
+    return grid
+
+
+def invert_block_map(block_map: torch.Tensor, inverse_per_frame: int) -> torch.Tensor:
+    """block_map (T, n) int32 of target indices -> (T, inverse_per_frame) int32: the last entry
+    pointing at each target, -1 where none does."""
+    _check_cuda(block_map, torch.int32, "block_map")
+    block_map = block_map.contiguous()
+    T, n = block_map.shape
+    inv = torch.empty((T, inverse_per_frame), dtype=torch.int32, device=block_map.device)
+    call("elvis_invert_block_map", _ptr(block_map), T, n, _ptr(inv), inverse_per_frame, _stream())
+    return inv
+
+
+def gather_blocks(clip: torch.Tensor, block_map: torch.Tensor, block_px: int, dst_by: int, dst_bx: int,
+                  out: torch.Tensor | None = None) -> torch.Tensor:
+    """out block (j, i) of frame t = clip block block_map[t, j, i] (linear over the clip's block
+    grid) or zeros for negative entries.  block_map: (T, rows >= dst_by, pitch >= dst_bx) int32."""
+    _check_cuda(block_map, torch.int32, "block_map")
+    if block_map.dim() != 3 or block_map.stride(2) != 1 or block_map.stride(0) != block_map.shape[1] * block_map.stride(1):
+        block_map = block_map.contiguous()
+    T = block_map.shape[0]
+    if clip.shape[0] != T:
+        raise ValueError("clip and block_map disagree on the frame count")
+    src_by, src_bx = clip.shape[1] // block_px, clip.shape[2] // block_px
+    shape = (T, dst_by * block_px, dst_bx * block_px) + tuple(clip.shape[3:])
+    if out is None:
+        out = torch.empty(shape, dtype=torch.uint8, device=clip.device)
+    elif tuple(out.shape) != shape:
+        raise ValueError(f"out must be {shape}")
+    if out.numel() == 0:
+        return out
+    if src_by == 0 or src_bx == 0:
+        return out.zero_()
+    src, dst = plane_of(clip), plane_of(out, "out")
+    call("elvis_gather_blocks", C.byref(src), C.byref(dst), T, block_px, dst_by, dst_bx, src_by, src_bx, _ptr(block_map),
+         block_map.shape[1], block_map.stride(1), _stream())
+    return out

@@ -64,6 +64,83 @@ def stretch_frame_row_only(shrunk_frame: np.ndarray, removal_mask: np.ndarray, b
     return ops.stretch(clip, mask, block_size)[0].cpu().numpy()
 
 
+# ---------------------------------------------------------------- row+column shrink (8f rank 2)
+def _rowcol_shrink(frame: np.ndarray, importance: np.ndarray, block_size: int, shrink_amount: float):
+    h, w = frame.shape[:2]
+    by, bx = h // block_size, w // block_size
+    target = int(by * bx * shrink_amount)
+    fby, fbx, counts = ops.rowcol_dims(by, bx, target)
+    imp = _to_dev(np.asarray(importance, np.float64)[:by, :bx])[None]
+    mask, pos, pidx, pcnt, _ = ops.rowcol_plan(imp, target)
+    clip = _packed_clip(frame)[:, :by * block_size, :bx * block_size]
+    shrunk = ops.gather_blocks(clip, pos, block_size, fby, fbx)
+    return shrunk[0].cpu().numpy(), mask[0].cpu().numpy().astype(bool), pos[0, :fby, :fbx], pidx[0], counts, bx
+
+
+def shrink_frame_position_map(frame: np.ndarray, importance: np.ndarray, block_size: int,
+                              shrink_amount: float) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """utils.py:763-836 -> (shrunken, removal_mask bool, position_map (by', bx', 2) of
+    (orig_y, orig_x))."""
+    shrunk, mask, pos, _, _, bx = _rowcol_shrink(frame, importance, block_size, shrink_amount)
+    lin = pos.cpu().numpy().astype(np.int64)
+    return shrunk, mask, np.stack([lin // bx, lin % bx], axis=-1)
+
+
+def stretch_frame_position_map(shrunk_frame: np.ndarray, removal_mask: np.ndarray, position_map: np.ndarray,
+                               block_size: int) -> np.ndarray:
+    """utils.py:839-858: every shrunk block back to position_map[j, i]; on duplicates the last one
+    in row-major order wins, as in the reference's loop."""
+    by, bx = np.shape(removal_mask)
+    sby, sbx = shrunk_frame.shape[0] // block_size, shrunk_frame.shape[1] // block_size
+    if shrunk_frame.shape[0] != sby * block_size or shrunk_frame.shape[1] != sbx * block_size:
+        raise ValueError("cannot reshape shrunk frame into whole blocks")       # utils.py:846 reshape
+    pm = np.asarray(position_map)[:sby, :sbx].astype(np.int64)
+    if pm.size and (pm[..., 0].min() < -by or pm[..., 0].max() >= by or pm[..., 1].min() < -bx or pm[..., 1].max() >= bx):
+        raise IndexError("position_map points outside the original block grid")
+    lin = (pm[..., 0] % by) * bx + pm[..., 1] % bx if pm.size else np.zeros((sby, sbx), np.int64)
+    if sby == 0 or sbx == 0:
+        return np.zeros((by * block_size, bx * block_size) + shrunk_frame.shape[2:], shrunk_frame.dtype)
+    inv = ops.invert_block_map(_to_dev(lin.reshape(1, -1), np.int32), by * bx).view(1, by, bx)
+    return ops.gather_blocks(_packed_clip(shrunk_frame), inv, block_size, by, bx)[0].cpu().numpy()
+
+
+def shrink_frame_removal_indices(frame: np.ndarray, importance: np.ndarray, block_size: int,
+                                 shrink_amount: float) -> Tuple[np.ndarray, np.ndarray, list]:
+    """utils.py:862-948 -> (shrunken, removal_mask bool, removal_indices: int32 arrays, row
+    passes at even positions, column passes at odd ones)."""
+    shrunk, mask, _, pidx, counts, _ = _rowcol_shrink(frame, importance, block_size, shrink_amount)
+    pidx = pidx.cpu().numpy()
+    return shrunk, mask, [pidx[i, :n].copy() for i, n in enumerate(counts)]
+
+
+def stretch_frame_removal_indices(shrunk_frame: np.ndarray, removal_indices: list, orig_blocks_y: int, orig_blocks_x: int,
+                                  block_size: int) -> np.ndarray:
+    """utils.py:951-1018: replay the passes in reverse, black blocks at the recorded positions,
+    crop to the original size."""
+    sby, sbx = shrunk_frame.shape[0] // block_size, shrunk_frame.shape[1] // block_size
+    if shrunk_frame.shape[0] != sby * block_size or shrunk_frame.shape[1] != sbx * block_size:
+        raise ValueError("cannot reshape shrunk frame into whole blocks")       # utils.py:958 reshape
+    P = len(removal_indices)
+    L = max([len(a) for a in removal_indices] + [1])
+    pidx = np.zeros((1, P, L), np.int32)
+    pcnt = np.zeros((1, P), np.int32)
+    for i, a in enumerate(removal_indices):
+        pidx[0, i, :len(a)] = np.asarray(a, np.int32)
+        pcnt[0, i] = len(a)
+    gh, gw = sby + P // 2, sbx + (P + 1) // 2
+    tail = shrunk_frame.shape[2:]
+    if gh == 0 or gw == 0:
+        return np.zeros((gh * block_size, gw * block_size) + tail, shrunk_frame.dtype)[:orig_blocks_y * block_size, :orig_blocks_x * block_size]
+    if sby == 0 or sbx == 0:
+        full = np.zeros((gh * block_size, gw * block_size) + tail, shrunk_frame.dtype)
+    elif P == 0:
+        full = shrunk_frame
+    else:
+        grid = ops.rowcol_expand(_to_dev(pidx), _to_dev(pcnt), sby, sbx)
+        full = ops.gather_blocks(_packed_clip(shrunk_frame), grid, block_size, gh, gw)[0].cpu().numpy()
+    return full[:orig_blocks_y * block_size, :orig_blocks_x * block_size]
+
+
 def _block_importance(importance: np.ndarray, by: int, bx: int) -> np.ndarray:
     importance = np.asarray(importance)
     if importance.shape != (by, bx):   # utils.py:1127-1128 (host-side map resize, rarely taken)

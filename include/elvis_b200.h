@@ -220,6 +220,41 @@ ELVIS_API int elvis_pack_levels_2bit(const int32_t* levels, int64_t rows, int32_
 ELVIS_API int elvis_unpack_levels_2bit(const uint8_t* packed, int64_t rows, int32_t bx, int32_t* levels,
                              elvis_stream_t stream);
 
+/* ---- 8f rank 2: row+column shrink (utils.py:763-1018).
+ * elvis_rowcol_plan simulates shrink_frame_position_map / shrink_frame_removal_indices
+ * (utils.py:763-830, 874-949) on block indices only: alternating row / column passes, each removing
+ * the first-minimum block of every row (column) and shifting the rest, until target_removals
+ * blocks are gone.  Per frame it writes
+ *   position      (by, bx) int32, pitch bx: original linear block index y*bx+x now sitting at each
+ *                 cell of the final (meta[1], meta[2]) grid (cells outside it are stale),
+ *   mask          (by, bx) uint8: 1 = removed,
+ *   pass_indices  (max_passes, max(by,bx)) int32 and pass_counts (max_passes): the reference's
+ *                 removal_indices list, even entries row passes, odd entries column passes,
+ *   meta          {n_passes, final_by, final_bx, removed}.
+ * scratch_keys: n_frames*by*bx uint64.  max_passes >= by + bx + 2 always suffices. */
+ELVIS_API int elvis_rowcol_plan(const double* importance, int32_t n_frames, int32_t by, int32_t bx, int64_t target_removals,
+                      uint64_t* scratch_keys, int32_t* position, uint8_t* mask, int32_t* pass_indices,
+                      int32_t* pass_counts, int32_t max_passes, int32_t* meta, elvis_stream_t stream);
+
+/* stretch_frame_removal_indices (utils.py:951-1018): replays the recorded passes in reverse on a
+ * grid of shrunk-block indices; grid (n_frames, grid_h, grid_w) int32 receives, for the final
+ * (shrunk_by + #column passes, shrunk_bx + #row passes) region, the shrunk linear index
+ * y*shrunk_bx+x to copy or -1 for a black block.  pass_indices is (n_frames, n_passes, lmax). */
+ELVIS_API int elvis_rowcol_expand(const int32_t* pass_indices, const int32_t* pass_counts, int32_t n_frames, int32_t n_passes,
+                        int32_t lmax, int32_t shrunk_by, int32_t shrunk_bx, int32_t* grid, int32_t grid_h,
+                        int32_t grid_w, elvis_stream_t stream);
+
+/* stretch_frame_position_map's scatter order (utils.py:851-855): inverse[t][orig] = the LAST
+ * row-major entry index i with map[t][i] == orig, -1 where no entry points. */
+ELVIS_API int elvis_invert_block_map(const int32_t* map, int32_t n_frames, int64_t entries_per_frame, int32_t* inverse,
+                           int64_t inverse_per_frame, elvis_stream_t stream);
+
+/* dst block (j, i) of frame t <- src block map[t][j][i] (linear index over a grid src_bx wide), or
+ * zeros when the entry is negative.  map is (n_frames, map_rows, map_pitch) int32. */
+ELVIS_API int elvis_gather_blocks(const elvis_plane* src, const elvis_plane* dst, int32_t n_frames, int32_t block_px,
+                        int32_t dst_by, int32_t dst_bx, int32_t src_by, int32_t src_bx, const int32_t* map,
+                        int32_t map_rows, int32_t map_pitch, elvis_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,21 @@ def main():
     g["a13_masks"] = masks
     g["a13_packed"] = np.packbits(masks.astype(np.uint8))
 
+    # 8f rank 2 -- row+column shrink variants (utils.py:763-1018); ties and a partial last pass
+    img3 = rng.integers(0, 256, (51, 70, 3), dtype=np.uint8)
+    g["f2_img"] = img3
+    for tag, amount in (("q30", 0.3), ("q55", 0.55), ("q85", 0.85)):
+        imp = np.round(rng.random((6, 8)) * 8) / 8
+        g[f"f2_imp_{tag}"] = imp
+        small, mask, pmap = U.shrink_frame_position_map(img3, imp, 8, amount)
+        g[f"f2_small_{tag}"], g[f"f2_mask_{tag}"], g[f"f2_pmap_{tag}"] = small, mask, pmap
+        g[f"f2_full_pm_{tag}"] = U.stretch_frame_position_map(small, mask, pmap, 8)
+        small2, mask2, passes = U.shrink_frame_removal_indices(img3, imp, 8, amount)
+        assert np.array_equal(small, small2) and np.array_equal(mask, mask2)
+        g[f"f2_npass_{tag}"] = np.array([len(a) for a in passes], np.int32)
+        g[f"f2_passes_{tag}"] = np.concatenate(passes).astype(np.int32)
+        g[f"f2_full_ri_{tag}"] = U.stretch_frame_removal_indices(small2, passes, 6, 8, 8)
+
     out = os.path.join(HERE, "reference_vectors.npz")
     np.savez_compressed(out, **g)
     print(f"wrote {out}: {len(g)} arrays, {os.path.getsize(out) / 1024:.1f} KiB")

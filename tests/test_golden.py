@@ -65,6 +65,17 @@ def _check_all(impl):
         assert np.array_equal(small, G[f"a6_small_{tag}"]), tag
         assert np.array_equal(impl.stretch_frame_row_only(small, mask, 8), G[f"a7_full_{tag}"]), tag
 
+    for tag, amount in (("q30", 0.3), ("q55", 0.55), ("q85", 0.85)):
+        small, mask, pmap = impl.shrink_frame_position_map(G["f2_img"], G[f"f2_imp_{tag}"], 8, amount)
+        assert mask.dtype == bool and np.array_equal(mask, G[f"f2_mask_{tag}"]), tag
+        assert np.array_equal(small, G[f"f2_small_{tag}"]) and np.array_equal(pmap, G[f"f2_pmap_{tag}"]), tag
+        assert np.array_equal(impl.stretch_frame_position_map(small, mask, pmap, 8), G[f"f2_full_pm_{tag}"]), tag
+        small2, mask2, passes = impl.shrink_frame_removal_indices(G["f2_img"], G[f"f2_imp_{tag}"], 8, amount)
+        assert np.array_equal(small2, small) and np.array_equal(mask2, mask), tag
+        assert [len(a) for a in passes] == G[f"f2_npass_{tag}"].tolist(), tag
+        assert all(a.dtype == np.int32 for a in passes) and np.array_equal(np.concatenate(passes), G[f"f2_passes_{tag}"]), tag
+        assert np.array_equal(impl.stretch_frame_removal_indices(small2, passes, 6, 8, 8), G[f"f2_full_ri_{tag}"]), tag
+
     assert np.array_equal(impl.restore_blur_opencv_unsharp_mask(G["f1_img"], G["f1_map"], 16), G["f1_out"])
     for tag, halo, tb in (("h0", 0, 0.0), ("h6b", 6, 0.2)):
         got = impl.restore_with_opencv_unsharp(list(G["f1_frames"]), G["f1_maps"], 16, halo=halo, temporal_blend=tb)

@@ -195,6 +195,64 @@ def test_row_only_shrink_stretch(dev, H, W, bs, shrink):
     assert np.array_equal(U.stretch_frame_row_only(g_img, g_mask, bs), P.stretch_frame_row_only(r_img, r_mask, bs))
 
 
+@pytest.mark.parametrize("H,W,bs,shrink", [(64, 96, 16, 0.5), (51, 85, 8, 0.3), (80, 128, 16, 0.9), (80, 128, 16, 0.0),
+                                          (40, 64, 8, 0.62), (16, 128, 16, 0.5), (128, 16, 16, 0.5), (48, 48, 8, 1.0),
+                                          (272, 480, 4, 0.45), (360, 640, 8, 0.5)])
+def test_rowcol_shrink_stretch(dev, H, W, bs, shrink):
+    """8f rank 2 (utils.py:763-1018): both bookkeeping variants, through the mirrors."""
+    from elvis_b200 import utils as U
+    rng = np.random.default_rng(H * W + bs)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    by, bx = H // bs, W // bs
+    imp = np.round(rng.random((by, bx)) * 16) / 16 if bs > 4 else rng.random((by, bx))
+    g = U.shrink_frame_position_map(img, imp, bs, shrink)
+    r = P.shrink_frame_position_map(img, imp, bs, shrink)
+    assert g[1].dtype == bool and np.array_equal(g[1], r[1])
+    assert g[2].shape == r[2].shape and np.array_equal(g[2], r[2])
+    assert g[0].shape == r[0].shape and np.array_equal(g[0], r[0])
+    assert np.array_equal(U.stretch_frame_position_map(*g, bs), P.stretch_frame_position_map(*r, bs))
+    g = U.shrink_frame_removal_indices(img, imp, bs, shrink)
+    r = P.shrink_frame_removal_indices(img, imp, bs, shrink)
+    assert np.array_equal(g[0], r[0]) and np.array_equal(g[1], r[1]) and len(g[2]) == len(r[2])
+    assert all(a.dtype == np.int32 and np.array_equal(a, b) for a, b in zip(g[2], r[2]))
+    assert np.array_equal(U.stretch_frame_removal_indices(g[0], g[2], by, bx, bs),
+                          P.stretch_frame_removal_indices(r[0], r[2], by, bx, bs))
+    if g[2]:
+        bad = [a[:max(1, len(a) - 2)] + 3 for a in g[2]]
+        assert np.array_equal(U.stretch_frame_removal_indices(g[0], bad, by, bx, bs),
+                              P.stretch_frame_removal_indices(r[0], bad, by, bx, bs))
+
+
+def test_rowcol_position_map_duplicates_last_wins(dev):
+    """stretch_frame_position_map scatters in row-major order (utils.py:851-855): a later shrunk
+    block overwrites an earlier one aimed at the same original position."""
+    from elvis_b200 import utils as U
+    rng = np.random.default_rng(5)
+    small = rng.integers(0, 256, (24, 32, 3), dtype=np.uint8)
+    pm = rng.integers(0, 4, (3, 4, 2))
+    mask = np.zeros((4, 4), bool)
+    assert np.array_equal(U.stretch_frame_position_map(small, mask, pm, 8), P.stretch_frame_position_map(small, mask, pm, 8))
+
+
+def test_rowcol_plan_batched_matches_per_frame(dev):
+    """The plan kernel runs one CTA per frame: a clip gives the per-frame results."""
+    from elvis_b200 import ops
+    rng = np.random.default_rng(9)
+    imp = rng.random((5, 17, 30))
+    target = int(17 * 30 * 0.4)
+    mask, pos, pidx, pcnt, meta = ops.rowcol_plan(torch.from_numpy(imp).to(dev), target)
+    fby, fbx, counts = ops.rowcol_dims(17, 30, target)
+    for t in range(5):
+        m, pm, passes = P.rowcol_plan(imp[t], 0.4)
+        assert meta[t].tolist() == [len(passes), fby, fbx, target]
+        assert np.array_equal(mask[t].cpu().numpy().astype(bool), m)
+        lin = pos[t, :fby, :fbx].cpu().numpy()
+        assert np.array_equal(np.stack([lin // 30, lin % 30], -1), pm)
+        assert pcnt[t, :len(passes)].tolist() == counts == [len(a) for a in passes]
+        for i, a in enumerate(passes):
+            assert np.array_equal(pidx[t, i, :len(a)].cpu().numpy(), a)
+
+
 def test_planar_pipeline_matches_per_plane_oracle(dev):
     """Planar YUV 4:2:0: mask from luma scores, applied to chroma at half block size."""
     from elvis_b200.pipeline import ElvisV1, Yuv420

@@ -86,6 +86,30 @@ def test_port_matches_reference_v1():
 
 
 @needs_reference
+def test_port_matches_reference_rowcol():
+    """8f rank 2: utils.py:763-1018, incl. ties, partial passes, crop and 1-wide grids."""
+    U = ref_import.load("utils")
+    rng = np.random.default_rng(7)
+    for (H, W, bs, sh) in [(64, 96, 16, 0.5), (51, 85, 8, 0.3), (80, 128, 16, 0.9), (80, 128, 16, 0.0), (40, 64, 8, 0.62),
+                           (16, 128, 16, 0.5), (128, 16, 16, 0.5), (48, 48, 8, 1.0)]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        imp = np.round(rng.random((H // bs, W // bs)) * 8) / 8
+        r, m = U.shrink_frame_position_map(img, imp, bs, sh), P.shrink_frame_position_map(img, imp, bs, sh)
+        assert all(np.array_equal(a, b) for a, b in zip(r, m)), (H, W, bs, sh)
+        assert np.array_equal(U.stretch_frame_position_map(*r, bs), P.stretch_frame_position_map(*m, bs))
+        r, m = U.shrink_frame_removal_indices(img, imp, bs, sh), P.shrink_frame_removal_indices(img, imp, bs, sh)
+        assert np.array_equal(r[0], m[0]) and np.array_equal(r[1], m[1]) and len(r[2]) == len(m[2])
+        assert all(np.array_equal(a, b) and a.dtype == b.dtype for a, b in zip(r[2], m[2]))
+        by, bx = H // bs, W // bs
+        assert np.array_equal(U.stretch_frame_removal_indices(r[0], r[2], by, bx, bs),
+                              P.stretch_frame_removal_indices(m[0], m[2], by, bx, bs))
+        # malformed side info: short / out-of-range records are clamped the same way
+        bad = [a[:max(1, len(a) - 2)] + 3 for a in r[2]]
+        assert np.array_equal(U.stretch_frame_removal_indices(r[0], bad, by, bx, bs),
+                              P.stretch_frame_removal_indices(m[0], bad, by, bx, bs))
+
+
+@needs_reference
 def test_port_matches_reference_v2_and_scores():
     from _ref_drive import run_reference_removability
     E, U = ref_import.load("elvis"), ref_import.load("utils")
