@@ -207,24 +207,37 @@ struct GatherParams {
     int32_t dby, dbx, src_bx, src_blocks, pb, row_bytes_per_block;
 };
 
+template <typename V>
+__device__ __forceinline__ V zero_vec();
+template <> __device__ __forceinline__ uint8_t zero_vec<uint8_t>() { return 0; }
+template <> __device__ __forceinline__ uint16_t zero_vec<uint16_t>() { return 0; }
+template <> __device__ __forceinline__ uint32_t zero_vec<uint32_t>() { return 0; }
+template <> __device__ __forceinline__ uint2 zero_vec<uint2>() { return make_uint2(0, 0); }
+template <> __device__ __forceinline__ uint4 zero_vec<uint4>() { return make_uint4(0, 0, 0, 0); }
+
+// One CTA per (frame, destination block row): thread x walks the row's vector units, thread y the
+// pixel rows of the block, so a warp reads/writes contiguous runs of a block row.
+template <typename V>
 __global__ void __launch_bounds__(256) gather_blocks_kernel(const GatherParams p) {
     const int t = blockIdx.x / p.dby, j = blockIdx.x % p.dby;
     const int32_t* mrow = p.map + ((int64_t)t * p.map_rows + j) * p.map_pitch;
-    const int64_t row_bytes = (int64_t)p.dbx * p.row_bytes_per_block;
-    const uint8_t* sframe = p.src + (int64_t)t * p.src_frame;
-    uint8_t* drow0 = p.dst + (int64_t)t * p.dst_frame + (int64_t)j * p.pb * p.dst_row;
-    for (int64_t e = threadIdx.x; e < row_bytes * p.pb; e += 256) {
-        const int r = (int)(e / row_bytes);
-        const int64_t xb = e - r * row_bytes;
-        const int i = (int)(xb / p.row_bytes_per_block);
-        const int off = (int)(xb - (int64_t)i * p.row_bytes_per_block);
+    const int upb = p.row_bytes_per_block / (int)sizeof(V);        // vector units per block row
+    const int cols = p.dbx * upb;
+    const int64_t srow = p.src_row / (int64_t)sizeof(V), drow = p.dst_row / (int64_t)sizeof(V);
+    const V* sframe = reinterpret_cast<const V*>(p.src + (int64_t)t * p.src_frame);
+    V* dbase = reinterpret_cast<V*>(p.dst + (int64_t)t * p.dst_frame + (int64_t)j * p.pb * p.dst_row);
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    for (int c = tx; c < cols; c += 64) {
+        const int i = c / upb, u = c - i * upb;
         const int32_t s = mrow[i];
-        uint8_t v = 0;
-        if (s >= 0 && s < p.src_blocks) {
-            const int sy = s / p.src_bx, sx = s - sy * p.src_bx;
-            v = sframe[((int64_t)sy * p.pb + r) * p.src_row + (int64_t)sx * p.row_bytes_per_block + off];
+        const bool live = s >= 0 && s < p.src_blocks;
+        const int sy = live ? s / p.src_bx : 0, sx = live ? s - sy * p.src_bx : 0;
+        const V* sp = sframe + (int64_t)sy * p.pb * srow + (int64_t)sx * upb + u;
+        for (int r = ty; r < p.pb; r += 4) {
+            V v = zero_vec<V>();
+            if (live) v = sp[(int64_t)r * srow];
+            dbase[(int64_t)r * drow + c] = v;
         }
-        drow0[(int64_t)r * p.dst_row + xb] = v;
     }
 }
 
@@ -314,7 +327,18 @@ extern "C" int elvis_gather_blocks(const elvis_plane* src, const elvis_plane* ds
     p.src_blocks = src_by * src_bx;
     p.pb = block_px;
     p.row_bytes_per_block = block_px * src->channels;
-    gather_blocks_kernel<<<(unsigned)((int64_t)n_frames * dst_by), 256, 0, as_stream(stream)>>>(p);
+    int unit = vector_unit(src, p.row_bytes_per_block);
+    const int unit_dst = vector_unit(dst, p.row_bytes_per_block);
+    if (unit_dst < unit) unit = unit_dst;
+    const unsigned grid = (unsigned)((int64_t)n_frames * dst_by);
+    cudaStream_t st = as_stream(stream);
+    switch (unit) {
+        case 16: gather_blocks_kernel<uint4><<<grid, 256, 0, st>>>(p); break;
+        case 8: gather_blocks_kernel<uint2><<<grid, 256, 0, st>>>(p); break;
+        case 4: gather_blocks_kernel<uint32_t><<<grid, 256, 0, st>>>(p); break;
+        case 2: gather_blocks_kernel<uint16_t><<<grid, 256, 0, st>>>(p); break;
+        default: gather_blocks_kernel<uint8_t><<<grid, 256, 0, st>>>(p); break;
+    }
     ELVIS_CHECK_LAUNCH();
     return ELVIS_OK;
 }

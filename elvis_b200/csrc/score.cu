@@ -309,6 +309,7 @@ extern "C" int elvis_score_sc_tc(const elvis_plane* y, int32_t n_frames, const u
     p.mm_end = mm_end;
     p.inv_area = 1.0f / (float)(block_size * block_size);
     p.magic = 0x4B000000u;
+    p.magic16 = 0x64006400u;
 
     // Implementation choice.  Default: the CUDA-core kernel (packed-fp32 butterflies, cp.async
     // ring) -- on B200 it is the fastest of the three (profiles/).  ELVIS_SCORE_IMPL = mma | tma
@@ -317,10 +318,11 @@ extern "C" int elvis_score_sc_tc(const elvis_plane* y, int32_t n_frames, const u
     auto al = [&](int a) {
         return aligned_to(p.y, a) && p.frame_stride % a == 0 && p.row_stride % a == 0 && (!prev_halo || aligned_to(prev_halo, a));
     };
-    enum { SIMT, MMA_DIRECT, MMA_TMA } impl = SIMT;
+    enum { SIMT, MMA_DIRECT, MMA_TMA, UMMA } impl = SIMT;
     if (const char* e = getenv("ELVIS_SCORE_IMPL")) {
         if (!strcmp(e, "mma") && block_size == 16 && al(4)) impl = MMA_DIRECT;
         else if (!strcmp(e, "tma") && block_size == 16 && al(16)) impl = MMA_TMA;
+        else if (!strcmp(e, "umma") && al(8)) impl = UMMA;
     }
     int override_len = 0;
     if (const char* e = getenv("ELVIS_SCORE_CHUNK")) override_len = atoi(e);
@@ -329,6 +331,10 @@ extern "C" int elvis_score_sc_tc(const elvis_plane* y, int32_t n_frames, const u
         const int R = block_size / 8;
         tiles = (long)By * ((Bx * R * R + 31) / 32);
         resident = (long)kNumSMs * 8;               // warps
+    } else if (impl == UMMA) {
+        const int R = block_size / 8;
+        tiles = ((long)By * ((Bx * R * R + 31) / 32) + 3) / 4;
+        resident = (long)kNumSMs * 2;               // CTAs of 4 worker warps
     } else {
         tiles = (long)((Bx + 7) / 8) * ((By + 2) / 3);
         resident = (long)kNumSMs * 2;               // CTAs
@@ -343,5 +349,6 @@ extern "C" int elvis_score_sc_tc(const elvis_plane* y, int32_t n_frames, const u
         ELVIS_CHECK_LAUNCH();
     }
     if (impl == SIMT) return launch_score_simt(p, block_size, al(8), st);
+    if (impl == UMMA) return launch_score_umma(p, block_size, st);
     return launch_score_mma(p, y->height, y->width, impl == MMA_TMA, st);
 }

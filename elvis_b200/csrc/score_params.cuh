@@ -17,11 +17,14 @@ struct ScoreParams {
     int32_t mm_begin, mm_end;
     float inv_area;
     uint32_t magic;     // 0x4B000000, passed at run time (see byte_as_biased_float)
+    uint32_t magic16;   // 0x64006400: the fp16 analogue, used by the tcgen05 kernel
 };
 
 // implemented in score.cu (CUDA cores, any supported block size) and score_mma.cu
 // (tensor cores + TMA, 16x16 blocks)
 int launch_score_simt(ScoreParams p, int block_size, bool aligned8, cudaStream_t st);
 int launch_score_mma(ScoreParams p, int plane_h, int plane_w, bool use_tma, cudaStream_t st);
+// score_umma.cu: tcgen05 tensor cores, A operand in tensor memory (planes 8-byte aligned)
+int launch_score_umma(ScoreParams p, int block_size, cudaStream_t st);
 
 }  // namespace elvis

@@ -240,6 +240,7 @@ def test_rowcol_plan_batched_matches_per_frame(dev):
     rng = np.random.default_rng(9)
     imp = rng.random((5, 17, 30))
     target = int(17 * 30 * 0.4)
+    import torch
     mask, pos, pidx, pcnt, meta = ops.rowcol_plan(torch.from_numpy(imp).to(dev), target)
     fby, fbx, counts = ops.rowcol_dims(17, 30, target)
     for t in range(5):
@@ -406,7 +407,7 @@ def test_select_rows_sorted_and_adversarial_rows(dev):
             assert np.array_equal(ops.select_rows(to_dev(rows, dev), k, pol).cpu().numpy(), P.select_rows(rows, k, pol))
 
 
-@pytest.mark.parametrize("impl", ["simt", "mma", "tma"])
+@pytest.mark.parametrize("impl", ["simt", "mma", "tma", "umma"])
 @pytest.mark.parametrize("H,W,T", [(48, 128, 5), (64, 96, 7), (112, 400, 9), (1080, 1920, 3), (16, 16, 2)])
 def test_score_impls_agree_with_spec(dev, monkeypatch, impl, H, W, T):
     """The CUDA-core kernel, the tensor-core kernel with direct loads and the tensor-core
@@ -436,7 +437,7 @@ def test_score_tightness(dev, monkeypatch):
     from elvis_b200 import ops
     y = synth_luma(12, 96, 256, seed=77)
     rsc, rtc = spec_scoring.sc_tc(y, 16)
-    for impl in ("simt", "mma", "tma"):
+    for impl in ("simt", "mma", "tma", "umma"):
         monkeypatch.setenv("ELVIS_SCORE_IMPL", impl)
         sc, tc, _ = ops.score_sc_tc(to_dev(y, dev), 16)
         e_sc = np.abs(sc.cpu().numpy() - rsc).max() / np.abs(rsc).max()
