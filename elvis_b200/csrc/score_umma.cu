@@ -14,8 +14,10 @@
 // the tile's 8 luma rows through a private cp.async ring (as the CUDA-core kernel does), expands
 // the 64 bytes to fp16 with PRMT + one HADD2 per pair, and writes them straight into the A
 // operand in TENSOR MEMORY (tcgen05.st) -- A never touches shared memory, whose bandwidth would
-// otherwise bound the MMA (SS-mode re-reads A per instruction).  Warp 4 issues the MMAs and
-// commits them to an mbarrier; the worker then reads its lane of D back (tcgen05.ld) and does
+// otherwise bound the MMA (SS-mode re-reads A per instruction).  One lane of the warp whose turn
+// it is (they rotate per frame; a fifth warp would cost every CTA a sixth warp's registers)
+// issues the MMAs once all 128 rows have arrived and commits them to an mbarrier; each worker
+// then reads its lane of D back (tcgen05.ld) and does
 // the weighted |C| and |C - C_prev| sums that are SC and TC.  A and D are double buffered, so
 // the expansion of frame t+1 and the sums of frame t-1 overlap the MMAs of frame t.  Per tile
 // the CUDA cores issue ~260 instructions instead of the ~900 of the butterfly kernel.
@@ -28,7 +30,7 @@ namespace {
 #include "score_umma_tables.inc"
 
 constexpr int kWorkers = 128;            // worker threads = TMEM lanes = tiles per MMA
-constexpr int kUmmaThreads = 160;        // + the MMA warp
+constexpr int kUmmaThreads = kWorkers;
 constexpr int kUmmaRing = 4;             // cp.async ring depth (frames)
 constexpr uint32_t kTmemCols = 256;      // A[2] x 32 + D[2] x 64 columns, rounded to a power of two
 constexpr uint32_t kColA = 0, kColD = 64;
@@ -79,7 +81,7 @@ __device__ __forceinline__ uint64_t b_descriptor(uint32_t smem_addr) {
 }
 
 template <int R>
-__global__ void __maxnreg__(200) score_umma_kernel(const ScoreParams p) {
+__global__ void __launch_bounds__(kUmmaThreads, 2) score_umma_kernel(const ScoreParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -101,7 +103,7 @@ __global__ void __maxnreg__(200) score_umma_kernel(const ScoreParams p) {
     const int t_start = has_prev ? t0 - 1 : t0;
     const int n_iter = t1 - t_start;
 
-    if (warp == 4) {
+    if (warp == 0) {
         if (lane == 0) {
             mbar_init(bar_a, kWorkers);
             mbar_init(bar_a + 8, kWorkers);
@@ -121,24 +123,7 @@ __global__ void __maxnreg__(200) score_umma_kernel(const ScoreParams p) {
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + kOffTmem);
 
-    if (warp == 4) {
-        // ---- MMA issuer
-        const uint64_t b_hi = b_descriptor(base + kOffB), b_lo = b_descriptor(base + kOffB + 8192);
-        for (int it = 0; it < n_iter; ++it) {
-            const uint32_t buf = it & 1;
-            mbar_wait(bar_a + 8 * buf, (it >> 1) & 1);      // A(it) written; D(it-2) drained by every worker
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t d_tmem = tmem + kColD + 64 * buf, a_tmem = tmem + kColA + 32 * buf;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_hi + 2 * k, k > 0);   // 16 fp16 = 8 columns = 32 B
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_lo + 2 * k, 1);
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_d + 8 * buf) : "memory");
-            }
-            __syncwarp();
-        }
-    } else {
+    {
         // ---- workers
         const int unit = group * 4 + warp;
         const bool unit_ok = unit < per_chunk;
@@ -152,6 +137,7 @@ __global__ void __maxnreg__(200) score_umma_kernel(const ScoreParams p) {
         const int64_t tile_off = (int64_t)(by * R + tr) * 8 * p.row_stride + (int64_t)tile_col * 8;
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
         const uint32_t bias = p.magic16;     // 0x64006400: bytes become fp16 1024 + b under PRMT
+        const uint64_t b_hi = b_descriptor(base + kOffB), b_lo = b_descriptor(base + kOffB + 8192);
 
         auto prefetch = [&](int slot, int t) {
             if (valid && t < t1) {
@@ -188,7 +174,23 @@ __global__ void __maxnreg__(200) score_umma_kernel(const ScoreParams p) {
             tmem_st32(tmem + lane_base + kColA + 32 * (it & 1), a);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
-            mbar_arrive(bar_a + 8 * (it & 1));
+            const uint32_t buf = it & 1;
+            mbar_arrive(bar_a + 8 * buf);
+            if (warp == (it & 3)) {
+                // this warp's turn to issue: all 128 rows of A(it) are in tensor memory, and every
+                // worker has drained D(it - 2) (its tcgen05.ld precedes this arrive in program order)
+                mbar_wait(bar_a + 8 * buf, (it >> 1) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t d_tmem = tmem + kColD + 64 * buf, a_tmem = tmem + kColA + 32 * buf;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_hi + 2 * k, k > 0);   // 16 fp16 = 8 columns = 32 B
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_lo + 2 * k, 1);
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_d + 8 * buf) : "memory");
+                }
+                __syncwarp();
+            }
         };
 
         float smin = __int_as_float(0x7f800000), smax = 0.f, tmin = __int_as_float(0x7f800000), tmax = 0.f;
@@ -285,7 +287,7 @@ __global__ void __maxnreg__(200) score_umma_kernel(const ScoreParams p) {
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
 }
 
 template <int R>
@@ -293,6 +295,9 @@ int launch_umma(const ScoreParams& p, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(score_umma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem);
+        if (e != cudaSuccess) return cuda_fail(e);
+        // two CTAs per SM need ~104 KB of shared memory: ask for the large carve-out
+        e = cudaFuncSetAttribute(score_umma_kernel<R>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return cuda_fail(e);
         configured = true;
     }
