@@ -322,7 +322,7 @@ extern "C" int elvis_score_sc_tc(const elvis_plane* y, int32_t n_frames, const u
     if (const char* e = getenv("ELVIS_SCORE_IMPL")) {
         if (!strcmp(e, "mma") && block_size == 16 && al(4)) impl = MMA_DIRECT;
         else if (!strcmp(e, "tma") && block_size == 16 && al(16)) impl = MMA_TMA;
-        else if (!strcmp(e, "umma") && al(8)) impl = UMMA;
+        else if (!strcmp(e, "umma") && al(16)) impl = UMMA;
     }
     int override_len = 0;
     if (const char* e = getenv("ELVIS_SCORE_CHUNK")) override_len = atoi(e);
@@ -333,8 +333,8 @@ extern "C" int elvis_score_sc_tc(const elvis_plane* y, int32_t n_frames, const u
         resident = (long)kNumSMs * 8;               // warps
     } else if (impl == UMMA) {
         const int R = block_size / 8;
-        tiles = ((long)By * ((Bx * R * R + 31) / 32) + 3) / 4;
-        resident = (long)kNumSMs * 2;               // CTAs of 4 worker warps
+        tiles = ((long)By * ((Bx * R * R + 31) / 32) + 7) / 8;
+        resident = (long)kNumSMs;                   // CTAs of 8 worker warps
     } else {
         tiles = (long)((Bx + 7) / 8) * ((By + 2) / 3);
         resident = (long)kNumSMs * 2;               // CTAs
@@ -349,6 +349,10 @@ extern "C" int elvis_score_sc_tc(const elvis_plane* y, int32_t n_frames, const u
         ELVIS_CHECK_LAUNCH();
     }
     if (impl == SIMT) return launch_score_simt(p, block_size, al(8), st);
-    if (impl == UMMA) return launch_score_umma(p, block_size, st);
+    if (impl == UMMA) {
+        const int rc = launch_score_umma(p, block_size, y->height, y->width, st);
+        if (rc != ELVIS_ERR_UNSUPPORTED) return rc;
+        return launch_score_simt(p, block_size, al(8), st);
+    }
     return launch_score_mma(p, y->height, y->width, impl == MMA_TMA, st);
 }

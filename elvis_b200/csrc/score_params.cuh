@@ -24,7 +24,7 @@ struct ScoreParams {
 // (tensor cores + TMA, 16x16 blocks)
 int launch_score_simt(ScoreParams p, int block_size, bool aligned8, cudaStream_t st);
 int launch_score_mma(ScoreParams p, int plane_h, int plane_w, bool use_tma, cudaStream_t st);
-// score_umma.cu: tcgen05 tensor cores, A operand in tensor memory (planes 8-byte aligned)
-int launch_score_umma(ScoreParams p, int block_size, cudaStream_t st);
+// score_umma.cu: tcgen05 tensor cores, TMA ring, A operand in tensor memory (planes 16-byte aligned)
+int launch_score_umma(ScoreParams p, int block_size, int plane_h, int plane_w, cudaStream_t st);
 
 }  // namespace elvis

@@ -3,39 +3,58 @@
 // presley.py:202).
 //
 // Formulation.  The 2-D DCT of a flattened tile is a 64 x 64 matrix product, C = X . B^T with
-// B[n][p] = a(u,r) a(v,c).  128 tiles form one M = 128 operand, so one frame step of a CTA is
+// B[n][p] = a(u,r) a(v,c).  128 tiles form one M = 128 operand, so one frame step of a group is
 //     D[128 x 64] (fp32, TMEM) = A[128 x 64] (fp16, TMEM) . (Bhi + Blo)^T (fp16, shared)
 // issued as 2 x 4 tcgen05.mma (M128 N64 K16) by one thread.  Pixels minus 128 are exact in fp16
 // and B is split hi + lo (|B - hi - lo| < 2^-22), so the products are exact and the result has
 // fp32-accumulation accuracy.  C_t is computed afresh for every frame -- no running sum, so
 // SC / TC do not depend on how the clip is chunked.
 //
-// Roles.  Worker thread m of 128 owns tile m = TMEM lane m through a run of frames: it streams
-// the tile's 8 luma rows through a private cp.async ring (as the CUDA-core kernel does), expands
-// the 64 bytes to fp16 with PRMT + one HADD2 per pair, and writes them straight into the A
-// operand in TENSOR MEMORY (tcgen05.st) -- A never touches shared memory, whose bandwidth would
-// otherwise bound the MMA (SS-mode re-reads A per instruction).  One lane of the warp whose turn
-// it is (they rotate per frame; a fifth warp would cost every CTA a sixth warp's registers)
-// issues the MMAs once all 128 rows have arrived and commits them to an mbarrier; each worker
-// then reads its lane of D back (tcgen05.ld) and does
-// the weighted |C| and |C - C_prev| sums that are SC and TC.  A and D are double buffered, so
-// the expansion of frame t+1 and the sums of frame t-1 overlap the MMAs of frame t.  Per tile
-// the CUDA cores issue ~260 instructions instead of the ~900 of the butterfly kernel.
+// Roles.  A CTA is two groups of 128 worker threads, an MMA warp and a TMA warp.
+//   * TMA warp, one lane per worker warp: streams the luma through a shared-memory ring -- one
+//     3-D box (8R rows x 256/R bytes x 1 frame, R = block_size / 8) per worker warp and frame,
+//     kUmmaRing frames deep, full / empty mbarriers per group and ring slot.  (cp.async from
+//     the workers costs ~60 instructions of address arithmetic per tile -- profiles/r1d.)
+//   * MMA warp, one lane: issues a group's MMAs once its 128 rows of A have arrived and commits
+//     them to an mbarrier.  (Issuing from a worker warp puts the ~300-cycle issue on every
+//     frame's critical path, and so does sharing the lane with the TMA issue.)
+//   * Worker thread m owns tile m = TMEM lane m through a run of frames: it reads the tile's 8
+//     rows from the ring, expands the 64 bytes to fp16 (PRMT + one HADD2 per pair) and writes
+//     them straight into the A operand in TENSOR MEMORY (tcgen05.st) -- A never touches shared
+//     memory again, whose bandwidth would otherwise bound the MMA (SS-mode re-reads A per
+//     instruction).  It then reads its lane of D back (tcgen05.ld) and does the weighted |C|
+//     and |C - C_prev| sums that are SC and TC.
+// A and D are double buffered, so the expansion of frame t+1 and the sums of frame t-1 overlap
+// the MMAs of frame t.
 #include "score_params.cuh"
+#include <cuda.h>
 #include <cuda_fp16.h>
+#include <cstring>
 
 namespace elvis {
 namespace {
 
 #include "score_umma_tables.inc"
 
-constexpr int kWorkers = 128;            // worker threads = TMEM lanes = tiles per MMA
-constexpr int kUmmaThreads = kWorkers;
-constexpr int kUmmaRing = 4;             // cp.async ring depth (frames)
-constexpr uint32_t kTmemCols = 256;      // A[2] x 32 + D[2] x 64 columns, rounded to a power of two
+constexpr int kGroupLanes = 128;         // worker threads of a group = TMEM lanes = tiles per MMA
+constexpr int kGroups = 2;               // groups per CTA, each with its own A / D buffers and barriers
+constexpr int kWorkers = kGroups * kGroupLanes;
+constexpr int kUnitsPerCta = kWorkers / 32;
+constexpr int kUmmaThreads = kWorkers + 64;   // + the MMA warp and the TMA warp
+#ifndef ELVIS_UMMA_RING
+#define ELVIS_UMMA_RING 6
+#endif
+constexpr int kUmmaRing = ELVIS_UMMA_RING;    // TMA ring depth (frames)
+constexpr uint32_t kBoxBytes = 2048;     // one warp unit of one frame: 32 tiles x 64 bytes
+constexpr uint32_t kGroupCols = 256;     // per group: A[2] x 32 + D[2] x 64 columns, rounded to a power of two
+constexpr uint32_t kTmemCols = kGroups * kGroupCols;
 constexpr uint32_t kColA = 0, kColD = 64;
-constexpr uint32_t kOffB = 0, kOffRing = 16384, kOffBar = kOffRing + kUmmaRing * 8 * kWorkers * 8, kOffTmem = kOffBar + 32;
+constexpr uint32_t kOffB = 0, kOffRing = 16384;
+constexpr uint32_t kOffBar = kOffRing + kGroups * kUmmaRing * 4 * kBoxBytes;
+constexpr uint32_t kBarStride = 32 + 16 * kUmmaRing;   // per group: a_full[2] +0, d_full[2] +16, ring_full[] +32, ring_empty[] after
+constexpr uint32_t kOffTmem = kOffBar + kGroups * kBarStride;
 constexpr uint32_t kUmmaSmem = kOffTmem + 16 + 1024;   // + slack to align the base to 1024 B (128 B swizzle atom)
+constexpr uint32_t kBarEmpty = 32 + 8 * kUmmaRing;
 // instruction descriptor: D fp32, A/B fp16 K-major, N = 64, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -46,6 +65,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     while (!done) {
@@ -55,6 +77,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int t, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(t), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -81,35 +108,44 @@ __device__ __forceinline__ uint64_t b_descriptor(uint32_t smem_addr) {
 }
 
 template <int R>
-__global__ void __launch_bounds__(kUmmaThreads, 2) score_umma_kernel(const ScoreParams p) {
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_constant__ CUtensorMap tm_halo, const ScoreParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw);
-    uint2* ring = reinterpret_cast<uint2*>(sm + kOffRing);   // [kUmmaRing][8][kWorkers]
-    const uint32_t bar_a = base + kOffBar, bar_d = bar_a + 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kMmaWarp = kWorkers / 32, kTmaWarp = kMmaWarp + 1;
+    constexpr int TW = 32 / R;             // tiles per warp-unit row
+    constexpr int kPitch = 256 / R;        // bytes per row of a warp unit's box (8R rows)
 
-    // one CTA = 4 warp units (each R x 32/R tiles of one block row) of ONE temporal chunk, so that
-    // its workers and the MMA warp step through the same frames
-    constexpr int TW = 32 / R;
+    // one CTA = 8 warp units (each R x 32/R tiles of one block row) of ONE temporal chunk, so that
+    // its workers and the two service warps step through the same frames
     const int per_chunk = p.By * p.tiles_x;
-    const int groups = (per_chunk + 3) / 4;
-    const int chunk = blockIdx.x / groups;
-    const int group = blockIdx.x - chunk * groups;
+    const int ctas_per_chunk = (per_chunk + kUnitsPerCta - 1) / kUnitsPerCta;
+    const int chunk = blockIdx.x / ctas_per_chunk;
+    const int first_unit = (blockIdx.x - chunk * ctas_per_chunk) * kUnitsPerCta;
     const int t0 = chunk * p.chunk_len;
     const int t1 = min(p.T, t0 + p.chunk_len);
     const bool has_prev = (t0 > 0) || (p.halo != nullptr);
     const int t_start = has_prev ? t0 - 1 : t0;
     const int n_iter = t1 - t_start;
 
-    if (warp == 0) {
+    if (warp == kMmaWarp) {
         if (lane == 0) {
-            mbar_init(bar_a, kWorkers);
-            mbar_init(bar_a + 8, kWorkers);
-            mbar_init(bar_d, 1);
-            mbar_init(bar_d + 8, 1);
+            for (int g = 0; g < kGroups; ++g) {
+                const uint32_t bar = base + kOffBar + kBarStride * g;
+                mbar_init(bar, kGroupLanes);
+                mbar_init(bar + 8, kGroupLanes);
+                mbar_init(bar + 16, 1);
+                mbar_init(bar + 24, 1);
+                for (int s = 0; s < kUmmaRing; ++s) {
+                    mbar_init(bar + 32 + 8 * s, 1);
+                    mbar_init(bar + kBarEmpty + 8 * s, kGroupLanes);
+                }
+            }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_clip) : "memory");
         }
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + kOffTmem), "r"(kTmemCols) : "memory");
@@ -123,9 +159,58 @@ __global__ void __launch_bounds__(kUmmaThreads, 2) score_umma_kernel(const Score
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + kOffTmem);
 
-    {
+    if (warp == kMmaWarp) {
+        // ---- MMA issue (one lane)
+        if (lane == 0) {
+            const uint64_t b_hi = b_descriptor(base + kOffB), b_lo = b_descriptor(base + kOffB + 8192);
+            for (int it = 0; it < n_iter; ++it) {
+                const uint32_t buf = it & 1;
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) {
+                    const uint32_t bar = base + kOffBar + kBarStride * g;
+                    // all 128 rows of A(it) are in tensor memory, and every worker of the group has
+                    // drained D(it - 2) (its tcgen05.ld precedes its arrive in program order)
+                    mbar_wait(bar + 8 * buf, (it >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem + kGroupCols * g + kColD + 64 * buf, a_tmem = tmem + kGroupCols * g + kColA + 32 * buf;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_hi + 2 * k, k > 0);   // 16 fp16 = 8 columns = 32 B
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_lo + 2 * k, 1);
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar + 16 + 8 * buf) : "memory");
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == kTmaWarp) {
+        // ---- TMA ring: lane l feeds worker warp l
+        const int unit = first_unit + lane;
+        if (lane < kUnitsPerCta && unit < per_chunk) {
+            const int g = lane >> 2;
+            const int n_valid = min(4, per_chunk - (first_unit + 4 * g));     // boxes per frame of this group
+            const int by = unit / p.tiles_x, tx = unit - by * p.tiles_x;
+            const int x = tx * kPitch, y = by * 8 * R;
+            const uint32_t bar = base + kOffBar + kBarStride * g;
+            const uint32_t dst0 = base + kOffRing + ((g * kUmmaRing) * 4 + (lane & 3)) * kBoxBytes;
+            int slot = 0;
+            uint32_t phase = 0;
+            for (int f = 0; f < n_iter; ++f) {
+                if (f >= kUmmaRing) mbar_wait(bar + kBarEmpty + 8 * slot, phase ^ 1);   // frame f - kUmmaRing has been read
+                const int t = t_start + f;
+                if ((lane & 3) == 0) mbar_arrive_expect_tx(bar + 32 + 8 * slot, (uint32_t)n_valid * kBoxBytes);
+                tma_load_3d(dst0 + slot * (4 * kBoxBytes), t < 0 ? &tm_halo : &tm_clip, x, y, max(t, 0), bar + 32 + 8 * slot);
+                if (++slot == kUmmaRing) {
+                    slot = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+        __syncwarp();
+    } else {
         // ---- workers
-        const int unit = group * 4 + warp;
+        const int grp = warp >> 2;
+        const uint32_t bar_a = base + kOffBar + kBarStride * grp, bar_d = bar_a + 16, bar_ring = bar_a + 32, bar_empty = bar_a + kBarEmpty;
+        const int unit = first_unit + warp;
         const bool unit_ok = unit < per_chunk;
         const int by = unit_ok ? unit / p.tiles_x : 0;
         const int tx = unit_ok ? unit - by * p.tiles_x : 0;
@@ -134,32 +219,22 @@ __global__ void __launch_bounds__(kUmmaThreads, 2) score_umma_kernel(const Score
         const bool valid = unit_ok && tile_col < p.Bx * R;
         const bool leader = valid && tr == 0 && (tcx % R) == 0;
         const int bxi = tile_col / R;
-        const int64_t tile_off = (int64_t)(by * R + tr) * 8 * p.row_stride + (int64_t)tile_col * 8;
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        const uint32_t lane_base = ((uint32_t)((warp & 3) * 32) << 16) + kGroupCols * grp;   // a warp reaches lanes 32 (warp % 4) ..
         const uint32_t bias = p.magic16;     // 0x64006400: bytes become fp16 1024 + b under PRMT
-        const uint64_t b_hi = b_descriptor(base + kOffB), b_lo = b_descriptor(base + kOffB + 8192);
+        // this thread's tile inside its warp unit's box, ring slot 0
+        const uint32_t tile_smem = base + kOffRing + ((grp * kUmmaRing) * 4 + (warp & 3)) * kBoxBytes + tr * 8 * kPitch + tcx * 8;
 
-        auto prefetch = [&](int slot, int t) {
-            if (valid && t < t1) {
-                const uint8_t* src = (t < 0 ? p.halo : p.y + (int64_t)t * p.frame_stride) + tile_off;
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const uint32_t dst = smem_u32(&ring[(slot * 8 + r) * kWorkers + threadIdx.x]);
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + r * p.row_stride) : "memory");
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
+        int slot = 0;
+        uint32_t ring_phase = 0;
         auto produce = [&](int it) {
-            prefetch((it + kUmmaRing - 1) % kUmmaRing, t_start + it + kUmmaRing - 1);
-            asm volatile("cp.async.wait_group 3;" ::: "memory");
-            static_assert(kUmmaRing == 4, "wait_group immediate");
-            const int slot = it % kUmmaRing;
             uint32_t a[32];
             const __half2 off = __floats2half2_rn(1152.f, 1152.f);   // 1024 (PRMT bias) + 128 (centering)
+            if (unit_ok) mbar_wait(bar_ring + 8 * slot, ring_phase);
+            const uint32_t src = tile_smem + slot * (4 * kBoxBytes);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                const uint2 w = valid ? ring[(slot * 8 + r) * kWorkers + threadIdx.x] : make_uint2(0u, 0u);
+                uint2 w = make_uint2(0u, 0u);
+                if (unit_ok) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "r"(src + r * kPitch));
                 uint32_t e[4];
                 asm("prmt.b32 %0, %1, %2, 0x7150;" : "=r"(e[0]) : "r"(w.x), "r"(bias));
                 asm("prmt.b32 %0, %1, %2, 0x7352;" : "=r"(e[1]) : "r"(w.x), "r"(bias));
@@ -174,60 +249,57 @@ __global__ void __launch_bounds__(kUmmaThreads, 2) score_umma_kernel(const Score
             tmem_st32(tmem + lane_base + kColA + 32 * (it & 1), a);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
-            const uint32_t buf = it & 1;
-            mbar_arrive(bar_a + 8 * buf);
-            if (warp == (it & 3)) {
-                // this warp's turn to issue: all 128 rows of A(it) are in tensor memory, and every
-                // worker has drained D(it - 2) (its tcgen05.ld precedes this arrive in program order)
-                mbar_wait(bar_a + 8 * buf, (it >> 1) & 1);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t d_tmem = tmem + kColD + 64 * buf, a_tmem = tmem + kColA + 32 * buf;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_hi + 2 * k, k > 0);   // 16 fp16 = 8 columns = 32 B
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_lo + 2 * k, 1);
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_d + 8 * buf) : "memory");
-                }
-                __syncwarp();
+            mbar_arrive(bar_empty + 8 * slot);     // the store above consumed every byte read from the slot
+            mbar_arrive(bar_a + 8 * (it & 1));
+            if (++slot == kUmmaRing) {
+                slot = 0;
+                ring_phase ^= 1;
             }
         };
 
         float smin = __int_as_float(0x7f800000), smax = 0.f, tmin = __int_as_float(0x7f800000), tmax = 0.f;
-        // c <- coefficients of frame t_start + it; pr = those of the frame before
-        auto consume = [&](int it, float2 (&c)[32], const float2 (&pr)[32]) {
-            mbar_wait(bar_d + 8 * (it & 1), (it >> 1) & 1);
-            tc_fence_after();
-            uint32_t v0[32], v1[32];
-            const uint32_t d_addr = tmem + lane_base + kColD + 64 * (it & 1);
-            tmem_ld32(d_addr, v0);
-            tmem_ld32(d_addr + 32, v1);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // weighted |C| and |C - P| over coefficient rows U0 .. U0+3 (16 float2 = 32 TMEM columns)
+        auto half_sums = [&](const int U0, const float2 (&c)[16], const float2 (&pr)[16], float& s_out, float& d_out) {
+            float s_part[4], d_part[4];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                c[i] = make_float2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
-                c[16 + i] = make_float2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
-            }
-            float s_part[8], d_part[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < 4; ++u) {
                 float s = 0.f, d = 0.f;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int i = u * 4 + j;
+                    const int i = u * 4 + j, n = (U0 + u) * 8 + 2 * j;
                     const float2 df = __ffma2_rn(pr[i], make_float2(-1.f, -1.f), c[i]);   // C_t - C_{t-1}, one rounding
-                    if (i != 0) {                                                          // DC carries no texture energy
-                        s = fmaf(fabsf(c[i].x), kUmmaW[2 * i], s);
-                        d = fmaf(fabsf(df.x), kUmmaW[2 * i], d);
+                    if (n != 0) {                                                          // DC carries no texture energy
+                        s = fmaf(fabsf(c[i].x), kUmmaW[n], s);
+                        d = fmaf(fabsf(df.x), kUmmaW[n], d);
                     }
-                    s = fmaf(fabsf(c[i].y), kUmmaW[2 * i + 1], s);
-                    d = fmaf(fabsf(df.y), kUmmaW[2 * i + 1], d);
+                    s = fmaf(fabsf(c[i].y), kUmmaW[n + 1], s);
+                    d = fmaf(fabsf(df.y), kUmmaW[n + 1], d);
                 }
                 s_part[u] = s;
                 d_part[u] = d;
             }
-            float s = ((s_part[0] + s_part[1]) + (s_part[2] + s_part[3])) + ((s_part[4] + s_part[5]) + (s_part[6] + s_part[7]));
-            float d = ((d_part[0] + d_part[1]) + (d_part[2] + d_part[3])) + ((d_part[4] + d_part[5]) + (d_part[6] + d_part[7]));
+            s_out = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
+            d_out = (d_part[0] + d_part[1]) + (d_part[2] + d_part[3]);
+        };
+        // (c_lo, c_hi) <- coefficients of frame t_start + it; (p_lo, p_hi) = those of the frame before.
+        // Two halves of 32 columns keep 96 instead of 128 coefficient registers live.
+        auto consume = [&](int it, float2 (&c_lo)[16], float2 (&c_hi)[16], const float2 (&p_lo)[16], const float2 (&p_hi)[16]) {
+            mbar_wait(bar_d + 8 * (it & 1), (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t d_addr = tmem + lane_base + kColD + 64 * (it & 1);
+            uint32_t v[32];
+            float s0, d0, s1, d1;
+            tmem_ld32(d_addr, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 16; ++i) c_lo[i] = make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+            half_sums(0, c_lo, p_lo, s0, d0);
+            tmem_ld32(d_addr + 32, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 16; ++i) c_hi[i] = make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+            half_sums(4, c_hi, p_hi, s1, d1);
+            float s = s0 + s1, d = d0 + d1;
 #pragma unroll
             for (int m = 1; m < R; m <<= 1) {
                 s += __shfl_xor_sync(0xffffffffu, s, m);
@@ -254,18 +326,16 @@ __global__ void __launch_bounds__(kUmmaThreads, 2) score_umma_kernel(const Score
             }
         };
 
-        float2 ca[32], cb[32];
+        float2 ca_lo[16], ca_hi[16], cb_lo[16], cb_hi[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) cb[i] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int s = 0; s < kUmmaRing - 1; ++s) prefetch(s, t_start + s);
+        for (int i = 0; i < 16; ++i) cb_lo[i] = cb_hi[i] = make_float2(0.f, 0.f);
         produce(0);
         for (int it = 0; it < n_iter; it += 2) {
             if (it + 1 < n_iter) produce(it + 1);
-            consume(it, ca, cb);
+            consume(it, ca_lo, ca_hi, cb_lo, cb_hi);
             if (it + 1 >= n_iter) break;
             if (it + 2 < n_iter) produce(it + 2);
-            consume(it + 1, cb, ca);
+            consume(it + 1, cb_lo, cb_hi, ca_lo, ca_hi);
         }
 
         if (p.mm != nullptr) {
@@ -287,38 +357,71 @@ __global__ void __launch_bounds__(kUmmaThreads, 2) score_umma_kernel(const Score
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &st) != cudaSuccess ||
+            st != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// (W, H, T) uint8 tensor, box = one warp unit (256/R bytes x 8R rows x 1 frame), zero fill out of bounds
+bool make_unit_map(CUtensorMap* m, const uint8_t* ptr, int W, int H, int T, int64_t row_stride, int64_t frame_stride, int R) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T};
+    cuuint64_t strides[2] = {(cuuint64_t)row_stride, (cuuint64_t)(T > 1 ? frame_stride : row_stride * H)};
+    cuuint32_t box[3] = {(cuuint32_t)(256 / R), (cuuint32_t)(8 * R), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(ptr), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int R>
-int launch_umma(const ScoreParams& p, cudaStream_t st) {
+int launch_umma(const ScoreParams& p, const CUtensorMap& tm_clip, const CUtensorMap& tm_halo, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(score_umma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem);
         if (e != cudaSuccess) return cuda_fail(e);
-        // two CTAs per SM need ~104 KB of shared memory: ask for the large carve-out
-        e = cudaFuncSetAttribute(score_umma_kernel<R>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return cuda_fail(e);
         configured = true;
     }
-    const int groups = (p.By * p.tiles_x + 3) / 4;
-    score_umma_kernel<R><<<groups * p.n_chunks, kUmmaThreads, kUmmaSmem, st>>>(p);
+    const int ctas_per_chunk = (p.By * p.tiles_x + kUnitsPerCta - 1) / kUnitsPerCta;
+    score_umma_kernel<R><<<ctas_per_chunk * p.n_chunks, kUmmaThreads, kUmmaSmem, st>>>(tm_clip, tm_halo, p);
     ELVIS_CHECK_LAUNCH();
     return ELVIS_OK;
 }
 
 }  // namespace
 
-int launch_score_umma(ScoreParams p, int block_size, cudaStream_t st) {
+// Returns ELVIS_ERR_UNSUPPORTED when the driver cannot encode tensor maps (the caller then uses
+// the CUDA-core kernel).  Plane, strides and halo must be 16-byte aligned.
+int launch_score_umma(ScoreParams p, int block_size, int plane_h, int plane_w, cudaStream_t st) {
     const int R = block_size / 8;
     const int TW = 32 / R;
     p.tiles_x = (p.Bx * R + TW - 1) / TW;
     p.tiles_y = p.By;
     p.magic16 = 0x64006400u;
+    CUtensorMap tm_clip, tm_halo;
+    memset(&tm_clip, 0, sizeof(tm_clip));
+    memset(&tm_halo, 0, sizeof(tm_halo));
+    if (!make_unit_map(&tm_clip, p.y, plane_w, plane_h, p.T, p.row_stride, p.frame_stride, R)) return ELVIS_ERR_UNSUPPORTED;
+    if (!make_unit_map(&tm_halo, p.halo ? p.halo : p.y, plane_w, plane_h, 1, p.row_stride, p.frame_stride, R)) return ELVIS_ERR_UNSUPPORTED;
     switch (R) {
-        case 1: return launch_umma<1>(p, st);
-        case 2: return launch_umma<2>(p, st);
-        default: return launch_umma<4>(p, st);
+        case 1: return launch_umma<1>(p, tm_clip, tm_halo, st);
+        case 2: return launch_umma<2>(p, tm_clip, tm_halo, st);
+        default: return launch_umma<4>(p, tm_clip, tm_halo, st);
     }
 }
 
