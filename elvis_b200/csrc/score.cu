@@ -310,6 +310,8 @@ extern "C" int elvis_score_sc_tc(const elvis_plane* y, int32_t n_frames, const u
     p.inv_area = 1.0f / (float)(block_size * block_size);
     p.magic = 0x4B000000u;
     p.magic16 = 0x64006400u;
+    p.dbg = 0;
+    if (const char* e = getenv("ELVIS_UMMA_DBG")) p.dbg = (uint32_t)atoi(e);
 
     // Implementation choice.  Default: the CUDA-core kernel (packed-fp32 butterflies, cp.async
     // ring) -- on B200 it is the fastest of the three (profiles/).  ELVIS_SCORE_IMPL = mma | tma

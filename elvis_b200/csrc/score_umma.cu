@@ -24,8 +24,10 @@
 //     memory again, whose bandwidth would otherwise bound the MMA (SS-mode re-reads A per
 //     instruction).  It then reads its lane of D back (tcgen05.ld) and does the weighted |C|
 //     and |C - C_prev| sums that are SC and TC.
-// A and D are double buffered, so the expansion of frame t+1 and the sums of frame t-1 overlap
-// the MMAs of frame t.
+// A is double and D triple buffered in tensor memory: the expansion of frame t+1 and the sums
+// of frame t-1 overlap the MMAs of frame t, and D(t-1) is still there when D(t) is read, so the
+// workers keep no coefficients in registers between frames (which left ptxas no room to
+// interleave the FMA chains -- profiles/r1d).
 #include "score_params.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -46,15 +48,15 @@ constexpr int kUmmaThreads = kWorkers + 64;   // + the MMA warp and the TMA warp
 #endif
 constexpr int kUmmaRing = ELVIS_UMMA_RING;    // TMA ring depth (frames)
 constexpr uint32_t kBoxBytes = 2048;     // one warp unit of one frame: 32 tiles x 64 bytes
-constexpr uint32_t kGroupCols = 256;     // per group: A[2] x 32 + D[2] x 64 columns, rounded to a power of two
+constexpr uint32_t kGroupCols = 256;     // per group: A[2] x 32 + D[3] x 64 columns
 constexpr uint32_t kTmemCols = kGroups * kGroupCols;
 constexpr uint32_t kColA = 0, kColD = 64;
 constexpr uint32_t kOffB = 0, kOffRing = 16384;
 constexpr uint32_t kOffBar = kOffRing + kGroups * kUmmaRing * 4 * kBoxBytes;
-constexpr uint32_t kBarStride = 32 + 16 * kUmmaRing;   // per group: a_full[2] +0, d_full[2] +16, ring_full[] +32, ring_empty[] after
+constexpr uint32_t kBarStride = 40 + 16 * kUmmaRing;   // per group: a_full[2] +0, d_full[3] +16, ring_full[] +40, ring_empty[] after
 constexpr uint32_t kOffTmem = kOffBar + kGroups * kBarStride;
 constexpr uint32_t kUmmaSmem = kOffTmem + 16 + 1024;   // + slack to align the base to 1024 B (128 B swizzle atom)
-constexpr uint32_t kBarEmpty = 32 + 8 * kUmmaRing;
+constexpr uint32_t kBarFull = 40, kBarEmpty = kBarFull + 8 * kUmmaRing;
 // instruction descriptor: D fp32, A/B fp16 K-major, N = 64, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -78,6 +80,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     }
 }
+// service warps: back off between polls so that the spin does not take issue slots from workers
+__device__ __forceinline__ void mbar_wait_sleepy(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t done = 0;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if (ns) __nanosleep(ns);
+    }
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int t, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -89,8 +104,8 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&a)[32]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]), "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(a[14]), "r"(a[15]), "r"(a[16]), "r"(a[17]), "r"(a[18]), "r"(a[19]), "r"(a[20]), "r"(a[21]), "r"(a[22]), "r"(a[23]), "r"(a[24]), "r"(a[25]), "r"(a[26]), "r"(a[27]), "r"(a[28]), "r"(a[29]), "r"(a[30]), "r"(a[31]) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) : "r"(taddr) : "memory");
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr) : "memory");
 }
 
 // D[tmem] (+)= A[tmem] . B[smem]^T
@@ -139,8 +154,9 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
                 mbar_init(bar + 8, kGroupLanes);
                 mbar_init(bar + 16, 1);
                 mbar_init(bar + 24, 1);
+                mbar_init(bar + 32, 1);
                 for (int s = 0; s < kUmmaRing; ++s) {
-                    mbar_init(bar + 32 + 8 * s, 1);
+                    mbar_init(bar + kBarFull + 8 * s, 1);
                     mbar_init(bar + kBarEmpty + 8 * s, kGroupLanes);
                 }
             }
@@ -163,23 +179,34 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
         // ---- MMA issue (one lane)
         if (lane == 0) {
             const uint64_t b_hi = b_descriptor(base + kOffB), b_lo = b_descriptor(base + kOffB + 8192);
+            uint32_t dbuf = 0, dphase = 0;
             for (int it = 0; it < n_iter; ++it) {
                 const uint32_t buf = it & 1;
 #pragma unroll
                 for (int g = 0; g < kGroups; ++g) {
                     const uint32_t bar = base + kOffBar + kBarStride * g;
-                    // all 128 rows of A(it) are in tensor memory, and every worker of the group has
-                    // drained D(it - 2) (its tcgen05.ld precedes its arrive in program order)
-                    mbar_wait(bar + 8 * buf, (it >> 1) & 1);
+                    // all 128 rows of A(it) are in tensor memory, and every worker of the group is
+                    // done with D(it - 3), which it last read as the "previous frame" of it - 2
+                    // (those tcgen05.ld precede its arrive in program order)
+                    mbar_wait_sleepy(bar + 8 * buf, (it >> 1) & 1, (p.dbg & 2) ? 64u : 0u);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem + kGroupCols * g + kColD + 64 * buf, a_tmem = tmem + kGroupCols * g + kColA + 32 * buf;
+                    const uint32_t d_tmem = tmem + kGroupCols * g + kColD + 64 * dbuf, a_tmem = tmem + kGroupCols * g + kColA + 32 * buf;
+                    if (!(p.dbg & 16)) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_hi + 2 * k, k > 0);   // 16 fp16 = 8 columns = 32 B
+                        for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_hi + 2 * k, k > 0);   // 16 fp16 = 8 columns = 32 B
+                    }
+                    if (!(p.dbg & 24)) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_lo + 2 * k, 1);
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar + 16 + 8 * buf) : "memory");
+                        for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_lo + 2 * k, 1);
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar + 16 + 8 * dbuf) : "memory");
+                }
+                if (++dbuf == 3) {
+                    dbuf = 0;
+                    dphase ^= 1;
                 }
             }
+            (void)dphase;
         }
         __syncwarp();
     } else if (warp == kTmaWarp) {
@@ -195,10 +222,10 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
             int slot = 0;
             uint32_t phase = 0;
             for (int f = 0; f < n_iter; ++f) {
-                if (f >= kUmmaRing) mbar_wait(bar + kBarEmpty + 8 * slot, phase ^ 1);   // frame f - kUmmaRing has been read
+                if (f >= kUmmaRing) mbar_wait_sleepy(bar + kBarEmpty + 8 * slot, phase ^ 1, (p.dbg & 2) ? 256u : 0u);   // frame f - kUmmaRing has been read
                 const int t = t_start + f;
-                if ((lane & 3) == 0) mbar_arrive_expect_tx(bar + 32 + 8 * slot, (uint32_t)n_valid * kBoxBytes);
-                tma_load_3d(dst0 + slot * (4 * kBoxBytes), t < 0 ? &tm_halo : &tm_clip, x, y, max(t, 0), bar + 32 + 8 * slot);
+                if ((lane & 3) == 0) mbar_arrive_expect_tx(bar + kBarFull + 8 * slot, (uint32_t)n_valid * kBoxBytes);
+                tma_load_3d(dst0 + slot * (4 * kBoxBytes), t < 0 ? &tm_halo : &tm_clip, x, y, max(t, 0), bar + kBarFull + 8 * slot);
                 if (++slot == kUmmaRing) {
                     slot = 0;
                     phase ^= 1;
@@ -209,7 +236,7 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
     } else {
         // ---- workers
         const int grp = warp >> 2;
-        const uint32_t bar_a = base + kOffBar + kBarStride * grp, bar_d = bar_a + 16, bar_ring = bar_a + 32, bar_empty = bar_a + kBarEmpty;
+        const uint32_t bar_a = base + kOffBar + kBarStride * grp, bar_d = bar_a + 16, bar_ring = bar_a + kBarFull, bar_empty = bar_a + kBarEmpty;
         const int unit = first_unit + warp;
         const bool unit_ok = unit < per_chunk;
         const int by = unit_ok ? unit / p.tiles_x : 0;
@@ -247,9 +274,12 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
                 }
             }
             tmem_st32(tmem + lane_base + kColA + 32 * (it & 1), a);
+        };
+        // second half of produce: publish A(it) once the asynchronous store has landed
+        auto publish = [&](int it) {
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
-            mbar_arrive(bar_empty + 8 * slot);     // the store above consumed every byte read from the slot
+            mbar_arrive(bar_empty + 8 * slot);     // the store consumed every byte read from the slot
             mbar_arrive(bar_a + 8 * (it & 1));
             if (++slot == kUmmaRing) {
                 slot = 0;
@@ -258,48 +288,49 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
         };
 
         float smin = __int_as_float(0x7f800000), smax = 0.f, tmin = __int_as_float(0x7f800000), tmax = 0.f;
-        // weighted |C| and |C - P| over coefficient rows U0 .. U0+3 (16 float2 = 32 TMEM columns)
-        auto half_sums = [&](const int U0, const float2 (&c)[16], const float2 (&pr)[16], float& s_out, float& d_out) {
-            float s_part[4], d_part[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                float s = 0.f, d = 0.f;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i = u * 4 + j, n = (U0 + u) * 8 + 2 * j;
-                    const float2 df = __ffma2_rn(pr[i], make_float2(-1.f, -1.f), c[i]);   // C_t - C_{t-1}, one rounding
-                    if (n != 0) {                                                          // DC carries no texture energy
-                        s = fmaf(fabsf(c[i].x), kUmmaW[n], s);
-                        d = fmaf(fabsf(df.x), kUmmaW[n], d);
-                    }
-                    s = fmaf(fabsf(c[i].y), kUmmaW[n + 1], s);
-                    d = fmaf(fabsf(df.y), kUmmaW[n + 1], d);
-                }
-                s_part[u] = s;
-                d_part[u] = d;
-            }
-            s_out = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
-            d_out = (d_part[0] + d_part[1]) + (d_part[2] + d_part[3]);
-        };
-        // (c_lo, c_hi) <- coefficients of frame t_start + it; (p_lo, p_hi) = those of the frame before.
-        // Two halves of 32 columns keep 96 instead of 128 coefficient registers live.
-        auto consume = [&](int it, float2 (&c_lo)[16], float2 (&c_hi)[16], const float2 (&p_lo)[16], const float2 (&p_hi)[16]) {
-            mbar_wait(bar_d + 8 * (it & 1), (it >> 1) & 1);
+        // The coefficients of the previous frame are not kept in registers: D is triple buffered
+        // and D(it - 1) is still in tensor memory when D(it) is read.  Columns come in 4 chunks
+        // of 16 (two coefficient rows); the loads of chunk k + 1 are in flight during the sums of
+        // chunk k.  8 independent FMA chains, fixed order => deterministic.
+        uint32_t dbuf = 0, dphase = 0;
+        auto consume = [&](int it, int pending) {
+            if (pending >= 0 && !(p.dbg & 4)) publish(pending);
+            mbar_wait(bar_d + 8 * dbuf, dphase);
             tc_fence_after();
-            const uint32_t d_addr = tmem + lane_base + kColD + 64 * (it & 1);
-            uint32_t v[32];
-            float s0, d0, s1, d1;
-            tmem_ld32(d_addr, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const uint32_t cur = tmem + lane_base + kColD + 64 * dbuf;
+            const uint32_t prv = tmem + lane_base + kColD + 64 * (dbuf == 0 ? 2 : dbuf - 1);
+            float sa[4] = {0.f, 0.f, 0.f, 0.f}, da[4] = {0.f, 0.f, 0.f, 0.f};
+            uint32_t vc[2][16], vp[2][16];
+            tmem_ld16(cur, vc[0]);
+            tmem_ld16(prv, vp[0]);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) c_lo[i] = make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-            half_sums(0, c_lo, p_lo, s0, d0);
-            tmem_ld32(d_addr + 32, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int k = 0; k < 4; ++k) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (k < 3) {
+                    tmem_ld16(cur + 16 * (k + 1), vc[(k + 1) & 1]);
+                    tmem_ld16(prv + 16 * (k + 1), vp[(k + 1) & 1]);
+                }
+                if (k == 1 && pending >= 0 && (p.dbg & 4)) publish(pending);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) c_hi[i] = make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-            half_sums(4, c_hi, p_hi, s1, d1);
-            float s = s0 + s1, d = d0 + d1;
+                for (int i = 0; i < 8; ++i) {
+                    const int n = 16 * k + 2 * i;          // coefficient index of the pair
+                    const float2 c = make_float2(__uint_as_float(vc[k & 1][2 * i]), __uint_as_float(vc[k & 1][2 * i + 1]));
+                    const float2 q = make_float2(__uint_as_float(vp[k & 1][2 * i]), __uint_as_float(vp[k & 1][2 * i + 1]));
+                    const float2 df = __ffma2_rn(q, make_float2(-1.f, -1.f), c);   // C_t - C_{t-1}, one rounding
+                    if (n != 0) {                                                   // DC carries no texture energy
+                        sa[i & 3] = fmaf(fabsf(c.x), kUmmaW[n], sa[i & 3]);
+                        da[i & 3] = fmaf(fabsf(df.x), kUmmaW[n], da[i & 3]);
+                    }
+                    sa[(i + 2) & 3] = fmaf(fabsf(c.y), kUmmaW[n + 1], sa[(i + 2) & 3]);
+                    da[(i + 2) & 3] = fmaf(fabsf(df.y), kUmmaW[n + 1], da[(i + 2) & 3]);
+                }
+            }
+            if (++dbuf == 3) {
+                dbuf = 0;
+                dphase ^= 1;
+            }
+            float s = (sa[0] + sa[1]) + (sa[2] + sa[3]);
+            float d = (da[0] + da[1]) + (da[2] + da[3]);
 #pragma unroll
             for (int m = 1; m < R; m <<= 1) {
                 s += __shfl_xor_sync(0xffffffffu, s, m);
@@ -313,6 +344,7 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
             const int t = t_start + it;
             if (t >= t0 && leader) {
                 const float scv = s * p.inv_area;
+                // the first frame without a halo has no predecessor (and D(-1) is uninitialised)
                 const float tcv = (t == 0 && p.halo == nullptr) ? 0.f : d * p.inv_area;
                 const int64_t o = ((int64_t)t * p.By + by) * p.Bx + bxi;
                 p.sc[o] = scv;
@@ -326,16 +358,13 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
             }
         };
 
-        float2 ca_lo[16], ca_hi[16], cb_lo[16], cb_hi[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) cb_lo[i] = cb_hi[i] = make_float2(0.f, 0.f);
         produce(0);
-        for (int it = 0; it < n_iter; it += 2) {
-            if (it + 1 < n_iter) produce(it + 1);
-            consume(it, ca_lo, ca_hi, cb_lo, cb_hi);
-            if (it + 1 >= n_iter) break;
-            if (it + 2 < n_iter) produce(it + 2);
-            consume(it + 1, cb_lo, cb_hi, ca_lo, ca_hi);
+        publish(0);
+#pragma unroll 1
+        for (int it = 0; it < n_iter; ++it) {
+            const bool more = it + 1 < n_iter;
+            if (more) produce(it + 1);
+            consume(it, more ? it + 1 : -1);
         }
 
         if (p.mm != nullptr) {
