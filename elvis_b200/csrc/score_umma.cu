@@ -10,39 +10,40 @@
 // fp32-accumulation accuracy.  C_t is computed afresh for every frame -- no running sum, so
 // SC / TC do not depend on how the clip is chunked.
 //
-// Roles.  A CTA is two groups of 128 worker threads, an MMA warp and a TMA warp.
-//   * TMA warp, one lane per worker warp: streams the luma through a shared-memory ring -- one
-//     3-D box (8R rows x 256/R bytes x 1 frame, R = block_size / 8) per worker warp and frame,
-//     kUmmaRing frames deep, full / empty mbarriers per group and ring slot.  (cp.async from
-//     the workers costs ~60 instructions of address arithmetic per tile -- profiles/r1d.)
-//   * MMA warp, one lane: issues a group's MMAs once its 128 rows of A have arrived and commits
-//     them to an mbarrier.  (Issuing from a worker warp puts the ~300-cycle issue on every
-//     frame's critical path, and so does sharing the lane with the TMA issue.)
-//   * Worker thread m owns tile m = TMEM lane m through a run of frames: it reads the tile's 8
-//     rows from the ring, expands the 64 bytes to fp16 (PRMT + one HADD2 per pair) and writes
-//     them straight into the A operand in TENSOR MEMORY (tcgen05.st) -- A never touches shared
-//     memory again, whose bandwidth would otherwise bound the MMA (SS-mode re-reads A per
-//     instruction).  It then reads its lane of D back (tcgen05.ld) and does the weighted |C|
-//     and |C - C_prev| sums that are SC and TC.
-// A is double and D triple buffered in tensor memory: the expansion of frame t+1 and the sums
-// of frame t-1 overlap the MMAs of frame t, and D(t-1) is still there when D(t) is read, so the
-// workers keep no coefficients in registers between frames (which left ptxas no room to
-// interleave the FMA chains -- profiles/r1d).
+// Roles.  A CTA is two groups of 128 tiles.  Tile m of a group is TMEM lane m; it is served by
+// TWO worker threads (lane m % 32 of warps q and q + 4, q = m / 32 -- both reach lanes 32q..),
+// which walk it through a run of frames:
+//   * both read half of the tile's 8 luma rows from a shared-memory ring, expand the 32 bytes
+//     to fp16 (PRMT + one HADD2 per pair) and write them straight into the A operand in TENSOR
+//     MEMORY (tcgen05.st) -- A never touches shared memory again, whose bandwidth would
+//     otherwise bound the MMA (SS-mode re-reads A per instruction);
+//   * after the MMAs the SC thread reads the tile's lane of D back (tcgen05.ld) and sums
+//     w |C_t|; the TC thread reads D(t) and D(t-1) and sums w |C_t - C_{t-1}|.  D is triple
+//     buffered, so the previous frame's coefficients are still in tensor memory and no thread
+//     carries coefficients in registers between frames.
+// Lane 0 of every SC warp also runs the TMA ring of its 32 tiles: one 3-D box (8R rows x 256/R
+// bytes x 1 frame, R = block_size / 8) per frame, kUmmaRing frames deep, full / empty mbarriers
+// per ring slot.  A 17th warp issues a group's MMAs (one lane) once its 8 worker warps have
+// published A and commits them to an mbarrier.  With 4 worker warps per scheduler the fixed
+// latencies of a frame step (mbarrier waits, tcgen05.st / ld round trips, shuffles) overlap;
+// with the 2 per scheduler of a thread-per-tile layout they were ~50 % of the time
+// (profiles/r1d).
 #include "score_params.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cstring>
+#include <type_traits>
 
 namespace elvis {
 namespace {
 
 #include "score_umma_tables.inc"
 
-constexpr int kGroupLanes = 128;         // worker threads of a group = TMEM lanes = tiles per MMA
-constexpr int kGroups = 2;               // groups per CTA, each with its own A / D buffers and barriers
-constexpr int kWorkers = kGroups * kGroupLanes;
-constexpr int kUnitsPerCta = kWorkers / 32;
-constexpr int kUmmaThreads = kWorkers + 64;   // + the MMA warp and the TMA warp
+constexpr int kGroups = 2;               // groups of 128 tiles per CTA, each with its own A / D buffers
+constexpr int kUnitsPerCta = kGroups * 4;     // warp units (32 tiles) per CTA
+constexpr int kWorkerWarps = 2 * kUnitsPerCta;   // an SC warp and a TC warp per unit
+constexpr int kMmaWarp = kWorkerWarps;
+constexpr int kUmmaThreads = (kWorkerWarps + 1) * 32;
 #ifndef ELVIS_UMMA_RING
 #define ELVIS_UMMA_RING 6
 #endif
@@ -52,11 +53,12 @@ constexpr uint32_t kGroupCols = 256;     // per group: A[2] x 32 + D[3] x 64 col
 constexpr uint32_t kTmemCols = kGroups * kGroupCols;
 constexpr uint32_t kColA = 0, kColD = 64;
 constexpr uint32_t kOffB = 0, kOffRing = 16384;
-constexpr uint32_t kOffBar = kOffRing + kGroups * kUmmaRing * 4 * kBoxBytes;
-constexpr uint32_t kBarStride = 40 + 16 * kUmmaRing;   // per group: a_full[2] +0, d_full[3] +16, ring_full[] +40, ring_empty[] after
-constexpr uint32_t kOffTmem = kOffBar + kGroups * kBarStride;
+constexpr uint32_t kOffBar = kOffRing + kUnitsPerCta * kUmmaRing * kBoxBytes;
+constexpr uint32_t kGroupBar = 40;       // per group: a_full[2] +0, d_full[3] +16
+constexpr uint32_t kUnitBar = 16 * kUmmaRing;   // per unit: ring_full[] +0, ring_empty[] +8 kUmmaRing
+constexpr uint32_t kOffUnitBar = kOffBar + kGroups * kGroupBar;
+constexpr uint32_t kOffTmem = kOffUnitBar + kUnitsPerCta * kUnitBar;
 constexpr uint32_t kUmmaSmem = kOffTmem + 16 + 1024;   // + slack to align the base to 1024 B (128 B swizzle atom)
-constexpr uint32_t kBarFull = 40, kBarEmpty = kBarFull + 8 * kUmmaRing;
 // instruction descriptor: D fp32, A/B fp16 K-major, N = 64, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -80,19 +82,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     }
 }
-// service warps: back off between polls so that the spin does not take issue slots from workers
-__device__ __forceinline__ void mbar_wait_sleepy(uint32_t bar, uint32_t parity, uint32_t ns) {
-    uint32_t done = 0;
-    for (;;) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) break;
-        if (ns) __nanosleep(ns);
-    }
-}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int t, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -101,11 +90,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&a)[32]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]), "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(a[14]), "r"(a[15]), "r"(a[16]), "r"(a[17]), "r"(a[18]), "r"(a[19]), "r"(a[20]), "r"(a[21]), "r"(a[22]), "r"(a[23]), "r"(a[24]), "r"(a[25]), "r"(a[26]), "r"(a[27]), "r"(a[28]), "r"(a[29]), "r"(a[30]), "r"(a[31]) : "memory");
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&a)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]), "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(a[14]), "r"(a[15]) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr) : "memory");
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) : "r"(taddr) : "memory");
 }
 
 // D[tmem] (+)= A[tmem] . B[smem]^T
@@ -130,12 +119,11 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int kMmaWarp = kWorkers / 32, kTmaWarp = kMmaWarp + 1;
     constexpr int TW = 32 / R;             // tiles per warp-unit row
     constexpr int kPitch = 256 / R;        // bytes per row of a warp unit's box (8R rows)
 
     // one CTA = 8 warp units (each R x 32/R tiles of one block row) of ONE temporal chunk, so that
-    // its workers and the two service warps step through the same frames
+    // all of its warps step through the same frames
     const int per_chunk = p.By * p.tiles_x;
     const int ctas_per_chunk = (per_chunk + kUnitsPerCta - 1) / kUnitsPerCta;
     const int chunk = blockIdx.x / ctas_per_chunk;
@@ -149,17 +137,18 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
     if (warp == kMmaWarp) {
         if (lane == 0) {
             for (int g = 0; g < kGroups; ++g) {
-                const uint32_t bar = base + kOffBar + kBarStride * g;
-                mbar_init(bar, kGroupLanes);
-                mbar_init(bar + 8, kGroupLanes);
-                mbar_init(bar + 16, 1);
+                const uint32_t bar = base + kOffBar + kGroupBar * g;
+                mbar_init(bar, 8);            // a_full: lane 0 of the group's 8 worker warps
+                mbar_init(bar + 8, 8);
+                mbar_init(bar + 16, 1);       // d_full: tcgen05.commit
                 mbar_init(bar + 24, 1);
                 mbar_init(bar + 32, 1);
-                for (int s = 0; s < kUmmaRing; ++s) {
-                    mbar_init(bar + kBarFull + 8 * s, 1);
-                    mbar_init(bar + kBarEmpty + 8 * s, kGroupLanes);
-                }
             }
+            for (int u = 0; u < kUnitsPerCta; ++u)
+                for (int s = 0; s < kUmmaRing; ++s) {
+                    mbar_init(base + kOffUnitBar + kUnitBar * u + 8 * s, 1);                   // ring_full: expect_tx
+                    mbar_init(base + kOffUnitBar + kUnitBar * u + 8 * (kUmmaRing + s), 2);     // ring_empty: both readers
+                }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_clip) : "memory");
         }
@@ -177,91 +166,85 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
 
     if (warp == kMmaWarp) {
         // ---- MMA issue (one lane)
-        if (lane == 0) {
+        if (lane == 0 && !(p.dbg & 32)) {
             const uint64_t b_hi = b_descriptor(base + kOffB), b_lo = b_descriptor(base + kOffB + 8192);
-            uint32_t dbuf = 0, dphase = 0;
+            uint32_t dbuf = 0;
             for (int it = 0; it < n_iter; ++it) {
                 const uint32_t buf = it & 1;
 #pragma unroll
                 for (int g = 0; g < kGroups; ++g) {
-                    const uint32_t bar = base + kOffBar + kBarStride * g;
+                    const uint32_t bar = base + kOffBar + kGroupBar * g;
                     // all 128 rows of A(it) are in tensor memory, and every worker of the group is
                     // done with D(it - 3), which it last read as the "previous frame" of it - 2
                     // (those tcgen05.ld precede its arrive in program order)
-                    mbar_wait_sleepy(bar + 8 * buf, (it >> 1) & 1, (p.dbg & 2) ? 64u : 0u);
+                    {   // back off between polls: the spin would take issue slots from the workers
+                        uint32_t done = 0;
+                        for (;;) {
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t"
+                                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                "selp.u32 %0, 1, 0, p;\n\t}"
+                                : "=r"(done) : "r"(bar + 8 * buf), "r"((uint32_t)(it >> 1) & 1u) : "memory");
+                            if (done) break;
+                            __nanosleep(32);
+                        }
+                    }
                     tc_fence_after();
                     const uint32_t d_tmem = tmem + kGroupCols * g + kColD + 64 * dbuf, a_tmem = tmem + kGroupCols * g + kColA + 32 * buf;
-                    if (!(p.dbg & 16)) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_hi + 2 * k, k > 0);   // 16 fp16 = 8 columns = 32 B
-                    }
-                    if (!(p.dbg & 24)) {
+                    for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_hi + 2 * k, k > 0);   // 16 fp16 = 8 columns = 32 B
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_lo + 2 * k, 1);
-                    }
+                    for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_lo + 2 * k, 1);
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar + 16 + 8 * dbuf) : "memory");
                 }
-                if (++dbuf == 3) {
-                    dbuf = 0;
-                    dphase ^= 1;
-                }
-            }
-            (void)dphase;
-        }
-        __syncwarp();
-    } else if (warp == kTmaWarp) {
-        // ---- TMA ring: lane l feeds worker warp l
-        const int unit = first_unit + lane;
-        if (lane < kUnitsPerCta && unit < per_chunk) {
-            const int g = lane >> 2;
-            const int n_valid = min(4, per_chunk - (first_unit + 4 * g));     // boxes per frame of this group
-            const int by = unit / p.tiles_x, tx = unit - by * p.tiles_x;
-            const int x = tx * kPitch, y = by * 8 * R;
-            const uint32_t bar = base + kOffBar + kBarStride * g;
-            const uint32_t dst0 = base + kOffRing + ((g * kUmmaRing) * 4 + (lane & 3)) * kBoxBytes;
-            int slot = 0;
-            uint32_t phase = 0;
-            for (int f = 0; f < n_iter; ++f) {
-                if (f >= kUmmaRing) mbar_wait_sleepy(bar + kBarEmpty + 8 * slot, phase ^ 1, (p.dbg & 2) ? 256u : 0u);   // frame f - kUmmaRing has been read
-                const int t = t_start + f;
-                if ((lane & 3) == 0) mbar_arrive_expect_tx(bar + kBarFull + 8 * slot, (uint32_t)n_valid * kBoxBytes);
-                tma_load_3d(dst0 + slot * (4 * kBoxBytes), t < 0 ? &tm_halo : &tm_clip, x, y, max(t, 0), bar + kBarFull + 8 * slot);
-                if (++slot == kUmmaRing) {
-                    slot = 0;
-                    phase ^= 1;
-                }
+                if (++dbuf == 3) dbuf = 0;
             }
         }
         __syncwarp();
     } else {
-        // ---- workers
-        const int grp = warp >> 2;
-        const uint32_t bar_a = base + kOffBar + kBarStride * grp, bar_d = bar_a + 16, bar_ring = bar_a + kBarFull, bar_empty = bar_a + kBarEmpty;
-        const int unit = first_unit + warp;
-        const bool unit_ok = unit < per_chunk;
-        const int by = unit_ok ? unit / p.tiles_x : 0;
-        const int tx = unit_ok ? unit - by * p.tiles_x : 0;
+        // ---- workers: warp = 8 grp + 4 role + q
+        const int grp = warp >> 3, role = (warp >> 2) & 1, q = warp & 3;
+        const int unit_local = grp * 4 + q;
+        const uint32_t bar_a = base + kOffBar + kGroupBar * grp, bar_d = bar_a + 16;
+        const uint32_t bar_full = base + kOffUnitBar + kUnitBar * unit_local, bar_empty = bar_full + 8 * kUmmaRing;
+        // warps past the end of the chunk redo its last unit (uniform control flow) and store nothing
+        const bool unit_ok = first_unit + unit_local < per_chunk;
+        const int unit = min(first_unit + unit_local, per_chunk - 1);
+        const int by = unit / p.tiles_x;
+        const int tx = unit - by * p.tiles_x;
         const int tr = lane / TW, tcx = lane % TW;
         const int tile_col = tx * TW + tcx;
         const bool valid = unit_ok && tile_col < p.Bx * R;
-        const bool leader = valid && tr == 0 && (tcx % R) == 0;
+        const bool leader = valid && tr == 0 && (tcx % R) == 0;   // valid implies unit_ok
         const int bxi = tile_col / R;
-        const uint32_t lane_base = ((uint32_t)((warp & 3) * 32) << 16) + kGroupCols * grp;   // a warp reaches lanes 32 (warp % 4) ..
+        const uint32_t lane_base = ((uint32_t)(q * 32) << 16) + kGroupCols * grp;   // a warp reaches lanes 32 (warp % 4) ..
         const uint32_t bias = p.magic16;     // 0x64006400: bytes become fp16 1024 + b under PRMT
-        // this thread's tile inside its warp unit's box, ring slot 0
-        const uint32_t tile_smem = base + kOffRing + ((grp * kUmmaRing) * 4 + (warp & 3)) * kBoxBytes + tr * 8 * kPitch + tcx * 8;
+        const uint32_t ring0 = base + kOffRing + unit_local * kUmmaRing * kBoxBytes;
+        // rows 4 role .. 4 role + 3 of this thread's tile inside the unit's box
+        const uint32_t tile_smem = ring0 + (tr * 8 + 4 * role) * kPitch + tcx * 8;
+        const bool loader = role == 0 && lane == 0;
+
+        auto load_frame = [&](int slot, int f) {       // loader lane only
+            const int t = t_start + f;
+            mbar_arrive_expect_tx(bar_full + 8 * slot, kBoxBytes);
+            tma_load_3d(ring0 + slot * kBoxBytes, t < 0 ? &tm_halo : &tm_clip, tx * kPitch, by * 8 * R, max(t, 0), bar_full + 8 * slot);
+        };
+        if (loader)
+            for (int f = 0; f < kUmmaRing && f < n_iter; ++f) load_frame(f, f);
 
         int slot = 0;
         uint32_t ring_phase = 0;
+        // expand this thread's 4 rows of frame `it` into its half of A's lane (asynchronous store)
         auto produce = [&](int it) {
-            uint32_t a[32];
+            uint32_t a[16];
             const __half2 off = __floats2half2_rn(1152.f, 1152.f);   // 1024 (PRMT bias) + 128 (centering)
-            if (unit_ok) mbar_wait(bar_ring + 8 * slot, ring_phase);
-            const uint32_t src = tile_smem + slot * (4 * kBoxBytes);
+            mbar_wait(bar_full + 8 * slot, ring_phase);
+            if (p.dbg & 32) return;     // probe: stream the ring only
+            const uint32_t src = tile_smem + slot * kBoxBytes;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                uint2 w = make_uint2(0u, 0u);
-                if (unit_ok) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "r"(src + r * kPitch));
+            for (int r = 0; r < 4; ++r) {
+                uint2 w;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "r"(src + r * kPitch));
                 uint32_t e[4];
                 asm("prmt.b32 %0, %1, %2, 0x7150;" : "=r"(e[0]) : "r"(w.x), "r"(bias));
                 asm("prmt.b32 %0, %1, %2, 0x7352;" : "=r"(e[1]) : "r"(w.x), "r"(bias));
@@ -273,113 +256,123 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
                     a[4 * r + j] = *reinterpret_cast<const uint32_t*>(&h);
                 }
             }
-            tmem_st32(tmem + lane_base + kColA + 32 * (it & 1), a);
+            tmem_st16(tmem + lane_base + kColA + 32 * (it & 1) + 16 * role, a);
         };
-        // second half of produce: publish A(it) once the asynchronous store has landed
+        // publish A(it) once the store has landed; release the ring slot; keep the ring full
         auto publish = [&](int it) {
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
-            mbar_arrive(bar_empty + 8 * slot);     // the store consumed every byte read from the slot
-            mbar_arrive(bar_a + 8 * (it & 1));
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar_a + 8 * (it & 1));
+                mbar_arrive(bar_empty + 8 * slot);   // the stores consumed every byte this warp read from the slot
+            }
+            if (loader && it >= 1 && it - 1 + kUmmaRing < n_iter) {
+                // refill the slot of the frame before: its other reader has had a whole frame step to finish
+                const int ps = slot == 0 ? kUmmaRing - 1 : slot - 1;
+                const uint32_t pphase = slot == 0 ? ring_phase ^ 1 : ring_phase;
+                mbar_wait(bar_empty + 8 * ps, pphase);
+                load_frame(ps, it - 1 + kUmmaRing);
+            }
             if (++slot == kUmmaRing) {
                 slot = 0;
                 ring_phase ^= 1;
             }
         };
 
-        float smin = __int_as_float(0x7f800000), smax = 0.f, tmin = __int_as_float(0x7f800000), tmax = 0.f;
-        // The coefficients of the previous frame are not kept in registers: D is triple buffered
-        // and D(it - 1) is still in tensor memory when D(it) is read.  Columns come in 4 chunks
-        // of 16 (two coefficient rows); the loads of chunk k + 1 are in flight during the sums of
-        // chunk k.  8 independent FMA chains, fixed order => deterministic.
+        float vmin = __int_as_float(0x7f800000), vmax = 0.f;     // of SC (role 0) or TC (role 1)
+        float* const out = role == 0 ? p.sc : p.tc;
+        // weighted sum of |x| over 32 TMEM columns (coefficient rows U0 .. U0 + 3) into 4 chains
+        auto abs_sums = [&](const int U0, const float2 (&x)[16], float (&acc)[4]) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int n = 8 * U0 + 2 * i;
+                if (n != 0) acc[i & 3] = fmaf(fabsf(x[i].x), kUmmaW[n], acc[i & 3]);   // DC carries no texture energy
+                acc[(i + 2) & 3] = fmaf(fabsf(x[i].y), kUmmaW[n + 1], acc[(i + 2) & 3]);
+            }
+        };
+        // ROLE 0: SC = sum w |C_t|.  ROLE 1: TC = sum w |C_t - C_{t-1}|, C_{t-1} = the D buffer
+        // written one frame earlier.  4 independent FMA chains, fixed order => deterministic.
         uint32_t dbuf = 0, dphase = 0;
-        auto consume = [&](int it, int pending) {
-            if (pending >= 0 && !(p.dbg & 4)) publish(pending);
+        auto consume = [&](int it, auto role_c) {
+            constexpr int ROLE = decltype(role_c)::value;
             mbar_wait(bar_d + 8 * dbuf, dphase);
             tc_fence_after();
             const uint32_t cur = tmem + lane_base + kColD + 64 * dbuf;
-            const uint32_t prv = tmem + lane_base + kColD + 64 * (dbuf == 0 ? 2 : dbuf - 1);
-            float sa[4] = {0.f, 0.f, 0.f, 0.f}, da[4] = {0.f, 0.f, 0.f, 0.f};
-            uint32_t vc[2][16], vp[2][16];
-            tmem_ld16(cur, vc[0]);
-            tmem_ld16(prv, vp[0]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            uint32_t v[32];
+            float2 x[16];
+            if (ROLE == 0) {
+                uint32_t v2[32];
+                tmem_ld32(cur, v);
+                tmem_ld32(cur + 32, v2);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (k < 3) {
-                    tmem_ld16(cur + 16 * (k + 1), vc[(k + 1) & 1]);
-                    tmem_ld16(prv + 16 * (k + 1), vp[(k + 1) & 1]);
-                }
-                if (k == 1 && pending >= 0 && (p.dbg & 4)) publish(pending);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int n = 16 * k + 2 * i;          // coefficient index of the pair
-                    const float2 c = make_float2(__uint_as_float(vc[k & 1][2 * i]), __uint_as_float(vc[k & 1][2 * i + 1]));
-                    const float2 q = make_float2(__uint_as_float(vp[k & 1][2 * i]), __uint_as_float(vp[k & 1][2 * i + 1]));
-                    const float2 df = __ffma2_rn(q, make_float2(-1.f, -1.f), c);   // C_t - C_{t-1}, one rounding
-                    if (n != 0) {                                                   // DC carries no texture energy
-                        sa[i & 3] = fmaf(fabsf(c.x), kUmmaW[n], sa[i & 3]);
-                        da[i & 3] = fmaf(fabsf(df.x), kUmmaW[n], da[i & 3]);
-                    }
-                    sa[(i + 2) & 3] = fmaf(fabsf(c.y), kUmmaW[n + 1], sa[(i + 2) & 3]);
-                    da[(i + 2) & 3] = fmaf(fabsf(df.y), kUmmaW[n + 1], da[(i + 2) & 3]);
+                for (int i = 0; i < 16; ++i) x[i] = make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                abs_sums(0, x, acc);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = make_float2(__uint_as_float(v2[2 * i]), __uint_as_float(v2[2 * i + 1]));
+                abs_sums(4, x, acc);
+            } else {
+                const uint32_t prv = tmem + lane_base + kColD + 64 * (dbuf == 0 ? 2 : dbuf - 1);
+                uint32_t q[32];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    tmem_ld32(cur + 32 * h, v);
+                    tmem_ld32(prv + 32 * h, q);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)   // C_t - C_{t-1}, one rounding
+                        x[i] = __ffma2_rn(make_float2(__uint_as_float(q[2 * i]), __uint_as_float(q[2 * i + 1])), make_float2(-1.f, -1.f),
+                                          make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])));
+                    abs_sums(4 * h, x, acc);
                 }
             }
             if (++dbuf == 3) {
                 dbuf = 0;
                 dphase ^= 1;
             }
-            float s = (sa[0] + sa[1]) + (sa[2] + sa[3]);
-            float d = (da[0] + da[1]) + (da[2] + da[3]);
+            float s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
 #pragma unroll
-            for (int m = 1; m < R; m <<= 1) {
-                s += __shfl_xor_sync(0xffffffffu, s, m);
-                d += __shfl_xor_sync(0xffffffffu, d, m);
-            }
+            for (int m = 1; m < R; m <<= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
 #pragma unroll
-            for (int m = TW; m < 32; m <<= 1) {
-                s += __shfl_xor_sync(0xffffffffu, s, m);
-                d += __shfl_xor_sync(0xffffffffu, d, m);
-            }
+            for (int m = TW; m < 32; m <<= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
             const int t = t_start + it;
             if (t >= t0 && leader) {
-                const float scv = s * p.inv_area;
                 // the first frame without a halo has no predecessor (and D(-1) is uninitialised)
-                const float tcv = (t == 0 && p.halo == nullptr) ? 0.f : d * p.inv_area;
-                const int64_t o = ((int64_t)t * p.By + by) * p.Bx + bxi;
-                p.sc[o] = scv;
-                p.tc[o] = tcv;
+                const float val = (ROLE == 1 && t == 0 && p.halo == nullptr) ? 0.f : s * p.inv_area;
+                out[((int64_t)t * p.By + by) * p.Bx + bxi] = val;
                 if (t >= p.mm_begin && t < p.mm_end) {
-                    smin = fminf(smin, scv);
-                    smax = fmaxf(smax, scv);
-                    tmin = fminf(tmin, tcv);
-                    tmax = fmaxf(tmax, tcv);
+                    vmin = fminf(vmin, val);
+                    vmax = fmaxf(vmax, val);
                 }
             }
         };
-
-        produce(0);
-        publish(0);
+        auto run = [&](auto role_c) {
+            produce(0);
+            publish(0);
 #pragma unroll 1
-        for (int it = 0; it < n_iter; ++it) {
-            const bool more = it + 1 < n_iter;
-            if (more) produce(it + 1);
-            consume(it, more ? it + 1 : -1);
-        }
+            for (int it = 0; it < n_iter; ++it) {
+                if (it + 1 < n_iter) {
+                    produce(it + 1);
+                    publish(it + 1);
+                }
+                if (!(p.dbg & 32)) consume(it, role_c);
+            }
+        };
+        if (role == 0) run(std::integral_constant<int, 0>{});
+        else run(std::integral_constant<int, 1>{});
 
         if (p.mm != nullptr) {
 #pragma unroll
             for (int m = 16; m > 0; m >>= 1) {
-                smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, m));
-                smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, m));
-                tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, m));
-                tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, m));
+                vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, m));
+                vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, m));
             }
             if (lane == 0) {
-                atomicMin(p.mm + 0, __float_as_uint(smin));
-                atomicMax(p.mm + 1, __float_as_uint(smax));
-                atomicMin(p.mm + 2, __float_as_uint(tmin));
-                atomicMax(p.mm + 3, __float_as_uint(tmax));
+                // non-negative floats order like their bit patterns
+                atomicMin(p.mm + 2 * role, __float_as_uint(vmin));
+                atomicMax(p.mm + 2 * role + 1, __float_as_uint(vmax));
             }
         }
     }
