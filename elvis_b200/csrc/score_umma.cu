@@ -21,13 +21,11 @@
 //     w |C_t|; the TC thread reads D(t) and D(t-1) and sums w |C_t - C_{t-1}|.  D is triple
 //     buffered, so the previous frame's coefficients are still in tensor memory and no thread
 //     carries coefficients in registers between frames.
-// Lane 0 of every SC warp also runs the TMA ring of its 32 tiles: one 3-D box (8R rows x 256/R
-// bytes x 1 frame, R = block_size / 8) per frame, kUmmaRing frames deep, full / empty mbarriers
-// per ring slot.  A 17th warp issues a group's MMAs (one lane) once its 8 worker warps have
-// published A and commits them to an mbarrier.  With 4 worker warps per scheduler the fixed
-// latencies of a frame step (mbarrier waits, tcgen05.st / ld round trips, shuffles) overlap;
-// with the 2 per scheduler of a thread-per-tile layout they were ~50 % of the time
-// (profiles/r1d).
+// Warp 16 issues a group's MMAs (one lane) once its 8 worker warps have published A and
+// commits them to an mbarrier.  Warp 17 runs the TMA ring, one lane per 32-tile unit: one 3-D
+// box (8R rows x 256/R bytes x 1 frame, R = block_size / 8) per frame, kUmmaRing frames deep,
+// full / empty mbarriers per ring slot.  The frame loop is unrolled by the ring depth so that
+// ring slot, A / D buffer and most mbarrier phases are compile-time constants.
 #include "score_params.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -43,7 +41,8 @@ constexpr int kGroups = 2;               // groups of 128 tiles per CTA, each wi
 constexpr int kUnitsPerCta = kGroups * 4;     // warp units (32 tiles) per CTA
 constexpr int kWorkerWarps = 2 * kUnitsPerCta;   // an SC warp and a TC warp per unit
 constexpr int kMmaWarp = kWorkerWarps;
-constexpr int kUmmaThreads = (kWorkerWarps + 1) * 32;
+constexpr int kTmaWarp = kWorkerWarps + 1;
+constexpr int kUmmaThreads = (kWorkerWarps + 2) * 32;
 #ifndef ELVIS_UMMA_RING
 #define ELVIS_UMMA_RING 6
 #endif
@@ -138,8 +137,8 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
         if (lane == 0) {
             for (int g = 0; g < kGroups; ++g) {
                 const uint32_t bar = base + kOffBar + kGroupBar * g;
-                mbar_init(bar, 8);            // a_full: lane 0 of the group's 8 worker warps
-                mbar_init(bar + 8, 8);
+                mbar_init(bar, 256);          // a_full: every thread of the group's 8 worker warps
+                mbar_init(bar + 8, 256);
                 mbar_init(bar + 16, 1);       // d_full: tcgen05.commit
                 mbar_init(bar + 24, 1);
                 mbar_init(bar + 32, 1);
@@ -147,7 +146,7 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
             for (int u = 0; u < kUnitsPerCta; ++u)
                 for (int s = 0; s < kUmmaRing; ++s) {
                     mbar_init(base + kOffUnitBar + kUnitBar * u + 8 * s, 1);                   // ring_full: expect_tx
-                    mbar_init(base + kOffUnitBar + kUnitBar * u + 8 * (kUmmaRing + s), 2);     // ring_empty: both readers
+                    mbar_init(base + kOffUnitBar + kUnitBar * u + 8 * (kUmmaRing + s), 64);    // ring_empty: both reader warps
                 }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_clip) : "memory");
@@ -201,6 +200,39 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
             }
         }
         __syncwarp();
+    } else if (warp == kTmaWarp) {
+        // ---- TMA ring: lane u feeds unit u (warps past the end of the chunk redo its last unit)
+        if (lane < kUnitsPerCta) {
+            const int unit = min(first_unit + lane, per_chunk - 1);
+            const int by = unit / p.tiles_x, tx = unit - by * p.tiles_x;
+            const int x = tx * kPitch, y = by * 8 * R;
+            const uint32_t bar_full = base + kOffUnitBar + kUnitBar * lane, bar_empty = bar_full + 8 * kUmmaRing;
+            const uint32_t dst0 = base + kOffRing + lane * kUmmaRing * kBoxBytes;
+            int slot = 0;
+            uint32_t phase = 0;
+            for (int f = 0; f < n_iter; ++f) {
+                if (f >= kUmmaRing) {            // frame f - kUmmaRing has been read by both warps
+                    uint32_t done = 0;
+                    for (;;) {
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t"
+                            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                            "selp.u32 %0, 1, 0, p;\n\t}"
+                            : "=r"(done) : "r"(bar_empty + 8 * slot), "r"(phase ^ 1u) : "memory");
+                        if (done) break;
+                        __nanosleep(64);
+                    }
+                }
+                const int t = t_start + f;
+                mbar_arrive_expect_tx(bar_full + 8 * slot, kBoxBytes);
+                tma_load_3d(dst0 + slot * kBoxBytes, t < 0 ? &tm_halo : &tm_clip, x, y, max(t, 0), bar_full + 8 * slot);
+                if (++slot == kUmmaRing) {
+                    slot = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+        __syncwarp();
     } else {
         // ---- workers: warp = 8 grp + 4 role + q
         const int grp = warp >> 3, role = (warp >> 2) & 1, q = warp & 3;
@@ -222,24 +254,17 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
         const uint32_t ring0 = base + kOffRing + unit_local * kUmmaRing * kBoxBytes;
         // rows 4 role .. 4 role + 3 of this thread's tile inside the unit's box
         const uint32_t tile_smem = ring0 + (tr * 8 + 4 * role) * kPitch + tcx * 8;
-        const bool loader = role == 0 && lane == 0;
+        float vmin = __int_as_float(0x7f800000), vmax = 0.f;     // of SC (role 0) or TC (role 1)
+        // output cursor of the leader lanes: element (t_start, by, bxi), one frame per step
+        float* out = (role == 0 ? p.sc : p.tc) + ((int64_t)t_start * p.By + by) * p.Bx + bxi;
+        const int64_t out_step = (int64_t)p.By * p.Bx;
 
-        auto load_frame = [&](int slot, int f) {       // loader lane only
-            const int t = t_start + f;
-            mbar_arrive_expect_tx(bar_full + 8 * slot, kBoxBytes);
-            tma_load_3d(ring0 + slot * kBoxBytes, t < 0 ? &tm_halo : &tm_clip, tx * kPitch, by * 8 * R, max(t, 0), bar_full + 8 * slot);
-        };
-        if (loader)
-            for (int f = 0; f < kUmmaRing && f < n_iter; ++f) load_frame(f, f);
-
-        int slot = 0;
-        uint32_t ring_phase = 0;
-        // expand this thread's 4 rows of frame `it` into its half of A's lane (asynchronous store)
-        auto produce = [&](int it) {
+        // expand this thread's 4 rows of the frame in ring slot SLOT into its half of A's lane BUF
+        // (asynchronous store), then publish it and release the slot
+        auto produce = [&](const int slot, const int buf, const uint32_t full_parity) {
             uint32_t a[16];
             const __half2 off = __floats2half2_rn(1152.f, 1152.f);   // 1024 (PRMT bias) + 128 (centering)
-            mbar_wait(bar_full + 8 * slot, ring_phase);
-            if (p.dbg & 32) return;     // probe: stream the ring only
+            mbar_wait(bar_full + 8 * slot, full_parity);
             const uint32_t src = tile_smem + slot * kBoxBytes;
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
@@ -256,32 +281,13 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
                     a[4 * r + j] = *reinterpret_cast<const uint32_t*>(&h);
                 }
             }
-            tmem_st16(tmem + lane_base + kColA + 32 * (it & 1) + 16 * role, a);
-        };
-        // publish A(it) once the store has landed; release the ring slot; keep the ring full
-        auto publish = [&](int it) {
+            tmem_st16(tmem + lane_base + kColA + 32 * buf + 16 * role, a);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(bar_a + 8 * (it & 1));
-                mbar_arrive(bar_empty + 8 * slot);   // the stores consumed every byte this warp read from the slot
-            }
-            if (loader && it >= 1 && it - 1 + kUmmaRing < n_iter) {
-                // refill the slot of the frame before: its other reader has had a whole frame step to finish
-                const int ps = slot == 0 ? kUmmaRing - 1 : slot - 1;
-                const uint32_t pphase = slot == 0 ? ring_phase ^ 1 : ring_phase;
-                mbar_wait(bar_empty + 8 * ps, pphase);
-                load_frame(ps, it - 1 + kUmmaRing);
-            }
-            if (++slot == kUmmaRing) {
-                slot = 0;
-                ring_phase ^= 1;
-            }
+            mbar_arrive(bar_a + 8 * buf);
+            mbar_arrive(bar_empty + 8 * slot);      // the store consumed every byte this thread read from the slot
         };
 
-        float vmin = __int_as_float(0x7f800000), vmax = 0.f;     // of SC (role 0) or TC (role 1)
-        float* const out = role == 0 ? p.sc : p.tc;
         // weighted sum of |x| over 32 TMEM columns (coefficient rows U0 .. U0 + 3) into 4 chains
         auto abs_sums = [&](const int U0, const float2 (&x)[16], float (&acc)[4]) {
 #pragma unroll
@@ -293,10 +299,9 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
         };
         // ROLE 0: SC = sum w |C_t|.  ROLE 1: TC = sum w |C_t - C_{t-1}|, C_{t-1} = the D buffer
         // written one frame earlier.  4 independent FMA chains, fixed order => deterministic.
-        uint32_t dbuf = 0, dphase = 0;
-        auto consume = [&](int it, auto role_c) {
+        auto consume = [&](const int t, const int dbuf, const uint32_t d_parity, auto role_c) {
             constexpr int ROLE = decltype(role_c)::value;
-            mbar_wait(bar_d + 8 * dbuf, dphase);
+            mbar_wait(bar_d + 8 * dbuf, d_parity);
             tc_fence_after();
             const uint32_t cur = tmem + lane_base + kColD + 64 * dbuf;
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -314,7 +319,7 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
                 for (int i = 0; i < 16; ++i) x[i] = make_float2(__uint_as_float(v2[2 * i]), __uint_as_float(v2[2 * i + 1]));
                 abs_sums(4, x, acc);
             } else {
-                const uint32_t prv = tmem + lane_base + kColD + 64 * (dbuf == 0 ? 2 : dbuf - 1);
+                const uint32_t prv = tmem + lane_base + kColD + 64 * ((dbuf + 2) % 3);
                 uint32_t q[32];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -328,36 +333,40 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
                     abs_sums(4 * h, x, acc);
                 }
             }
-            if (++dbuf == 3) {
-                dbuf = 0;
-                dphase ^= 1;
-            }
             float s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
 #pragma unroll
             for (int m = 1; m < R; m <<= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
 #pragma unroll
             for (int m = TW; m < 32; m <<= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-            const int t = t_start + it;
             if (t >= t0 && leader) {
                 // the first frame without a halo has no predecessor (and D(-1) is uninitialised)
                 const float val = (ROLE == 1 && t == 0 && p.halo == nullptr) ? 0.f : s * p.inv_area;
-                out[((int64_t)t * p.By + by) * p.Bx + bxi] = val;
+                *out = val;
                 if (t >= p.mm_begin && t < p.mm_end) {
                     vmin = fminf(vmin, val);
                     vmax = fmaxf(vmax, val);
                 }
             }
+            out += out_step;
         };
+        // Frame loop, unrolled by the ring depth (a multiple of 2 and 3): step i of a round works
+        // on ring slot (i + 1) % 6, A buffer (i + 1) & 1, D buffer i % 3.  Parities: ring and a_full
+        // barriers flip once per round (6 = kUmmaRing uses; 3 uses of each A buffer), d_full
+        // completes twice per round, so its parity is (i / 3) & 1.
+        static_assert(kUmmaRing == 6, "the unrolled frame loop assumes a ring of 6");
         auto run = [&](auto role_c) {
-            produce(0);
-            publish(0);
+            produce(0, 0, 0u);
+            uint32_t round_parity = 0;
 #pragma unroll 1
-            for (int it = 0; it < n_iter; ++it) {
-                if (it + 1 < n_iter) {
-                    produce(it + 1);
-                    publish(it + 1);
+            for (int it0 = 0; it0 < n_iter; it0 += 6) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    const int it = it0 + i;
+                    if (it >= n_iter) break;
+                    if (it + 1 < n_iter) produce((i + 1) % 6, (i + 1) & 1, i == 5 ? round_parity ^ 1u : round_parity);
+                    consume(t_start + it, i % 3, (uint32_t)(i / 3) & 1u, role_c);
                 }
-                if (!(p.dbg & 32)) consume(it, role_c);
+                round_parity ^= 1u;
             }
         };
         if (role == 0) run(std::integral_constant<int, 0>{});
