@@ -17,10 +17,12 @@
 //     to fp16 (PRMT + one HADD2 per pair) and write them straight into the A operand in TENSOR
 //     MEMORY (tcgen05.st) -- A never touches shared memory again, whose bandwidth would
 //     otherwise bound the MMA (SS-mode re-reads A per instruction);
-//   * after the MMAs the SC thread reads the tile's lane of D back (tcgen05.ld) and sums
-//     w |C_t|; the TC thread reads D(t) and D(t-1) and sums w |C_t - C_{t-1}|.  D is triple
-//     buffered, so the previous frame's coefficients are still in tensor memory and no thread
-//     carries coefficients in registers between frames.
+//   * after the MMAs each reads its half of the tile's lane of D(t) and of D(t-1) back
+//     (tcgen05.ld) and sums w |C_t| (SC) and w |C_t - C_{t-1}| (TC) over its 32 coefficients;
+//     the upper-half warp hands its block sums to the lower-half warp through shared memory
+//     and a 64-thread named barrier, and that one writes SC and TC.  D is triple buffered, so
+//     the previous frame's coefficients are still in tensor memory and no thread carries
+//     coefficients in registers between frames.
 // Warp 16 issues a group's MMAs (one lane) once its 8 worker warps have published A and
 // commits them to an mbarrier.  Warp 17 runs the TMA ring, one lane per 32-tile unit: one 3-D
 // box (8R rows x 256/R bytes x 1 frame, R = block_size / 8) per frame, kUmmaRing frames deep,
@@ -56,7 +58,8 @@ constexpr uint32_t kOffBar = kOffRing + kUnitsPerCta * kUmmaRing * kBoxBytes;
 constexpr uint32_t kGroupBar = 40;       // per group: a_full[2] +0, d_full[3] +16
 constexpr uint32_t kUnitBar = 16 * kUmmaRing;   // per unit: ring_full[] +0, ring_empty[] +8 kUmmaRing
 constexpr uint32_t kOffUnitBar = kOffBar + kGroups * kGroupBar;
-constexpr uint32_t kOffTmem = kOffUnitBar + kUnitsPerCta * kUnitBar;
+constexpr uint32_t kOffXchg = kOffUnitBar + kUnitsPerCta * kUnitBar;   // per unit: 2 x 32 float2 partial sums
+constexpr uint32_t kOffTmem = kOffXchg + kUnitsPerCta * 512;
 constexpr uint32_t kUmmaSmem = kOffTmem + 16 + 1024;   // + slack to align the base to 1024 B (128 B swizzle atom)
 // instruction descriptor: D fp32, A/B fp16 K-major, N = 64, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
@@ -164,38 +167,38 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + kOffTmem);
 
     if (warp == kMmaWarp) {
-        // ---- MMA issue (one lane)
-        if (lane == 0 && !(p.dbg & 32)) {
+        // ---- MMA issue: lane g serves group g
+        if (lane < kGroups) {
+            const int g = lane;
             const uint64_t b_hi = b_descriptor(base + kOffB), b_lo = b_descriptor(base + kOffB + 8192);
+            const uint32_t bar = base + kOffBar + kGroupBar * g;
             uint32_t dbuf = 0;
             for (int it = 0; it < n_iter; ++it) {
                 const uint32_t buf = it & 1;
-#pragma unroll
-                for (int g = 0; g < kGroups; ++g) {
-                    const uint32_t bar = base + kOffBar + kGroupBar * g;
-                    // all 128 rows of A(it) are in tensor memory, and every worker of the group is
-                    // done with D(it - 3), which it last read as the "previous frame" of it - 2
-                    // (those tcgen05.ld precede its arrive in program order)
-                    {   // back off between polls: the spin would take issue slots from the workers
-                        uint32_t done = 0;
-                        for (;;) {
-                            asm volatile(
-                                "{\n\t.reg .pred p;\n\t"
-                                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                                "selp.u32 %0, 1, 0, p;\n\t}"
-                                : "=r"(done) : "r"(bar + 8 * buf), "r"((uint32_t)(it >> 1) & 1u) : "memory");
-                            if (done) break;
-                            __nanosleep(32);
-                        }
+                // all 128 rows of A(it) are in tensor memory, and every worker of the group is
+                // done with D(it - 3), which it last read as the "previous frame" of it - 2
+                // (those tcgen05.ld precede its arrive in program order)
+                {   // back off between polls: the spin would take issue slots from the workers
+                    uint32_t done = 0;
+                    for (;;) {
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t"
+                            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                            "selp.u32 %0, 1, 0, p;\n\t}"
+                            : "=r"(done) : "r"(bar + 8 * buf), "r"((uint32_t)(it >> 1) & 1u) : "memory");
+                        if (done) break;
+                        __nanosleep(32);
                     }
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem + kGroupCols * g + kColD + 64 * dbuf, a_tmem = tmem + kGroupCols * g + kColA + 32 * buf;
+                }
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + kGroupCols * g + kColD + 64 * dbuf, a_tmem = tmem + kGroupCols * g + kColA + 32 * buf;
+                if (!(p.dbg & 4)) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_hi + 2 * k, k > 0);   // 16 fp16 = 8 columns = 32 B
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_lo + 2 * k, 1);
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar + 16 + 8 * dbuf) : "memory");
                 }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar + 16 + 8 * dbuf) : "memory");
                 if (++dbuf == 3) dbuf = 0;
             }
         }
@@ -254,10 +257,12 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
         const uint32_t ring0 = base + kOffRing + unit_local * kUmmaRing * kBoxBytes;
         // rows 4 role .. 4 role + 3 of this thread's tile inside the unit's box
         const uint32_t tile_smem = ring0 + (tr * 8 + 4 * role) * kPitch + tcx * 8;
-        float vmin = __int_as_float(0x7f800000), vmax = 0.f;     // of SC (role 0) or TC (role 1)
-        // output cursor of the leader lanes: element (t_start, by, bxi), one frame per step
-        float* out = (role == 0 ? p.sc : p.tc) + ((int64_t)t_start * p.By + by) * p.Bx + bxi;
+        float smin = __int_as_float(0x7f800000), smax = 0.f, tmin = __int_as_float(0x7f800000), tmax = 0.f;
+        // output cursors of the leader lanes: element (t_start, by, bxi), one frame per step
         const int64_t out_step = (int64_t)p.By * p.Bx;
+        float* out_sc = p.sc + ((int64_t)t_start * p.By + by) * p.Bx + bxi;
+        float* out_tc = p.tc + ((int64_t)t_start * p.By + by) * p.Bx + bxi;
+        float2* const xchg = reinterpret_cast<float2*>(sm + kOffXchg + unit_local * 512) + lane;
 
         // expand this thread's 4 rows of the frame in ring slot SLOT into its half of A's lane BUF
         // (asynchronous store), then publish it and release the slot
@@ -266,6 +271,11 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
             const __half2 off = __floats2half2_rn(1152.f, 1152.f);   // 1024 (PRMT bias) + 128 (centering)
             mbar_wait(bar_full + 8 * slot, full_parity);
             const uint32_t src = tile_smem + slot * kBoxBytes;
+            if (p.dbg & 2) {
+                mbar_arrive(bar_a + 8 * buf);
+                mbar_arrive(bar_empty + 8 * slot);
+                return;
+            }
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 uint2 w;
@@ -288,66 +298,66 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
             mbar_arrive(bar_empty + 8 * slot);      // the store consumed every byte this thread read from the slot
         };
 
-        // weighted sum of |x| over 32 TMEM columns (coefficient rows U0 .. U0 + 3) into 4 chains
-        auto abs_sums = [&](const int U0, const float2 (&x)[16], float (&acc)[4]) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int n = 8 * U0 + 2 * i;
-                if (n != 0) acc[i & 3] = fmaf(fabsf(x[i].x), kUmmaW[n], acc[i & 3]);   // DC carries no texture energy
-                acc[(i + 2) & 3] = fmaf(fabsf(x[i].y), kUmmaW[n + 1], acc[(i + 2) & 3]);
-            }
-        };
-        // ROLE 0: SC = sum w |C_t|.  ROLE 1: TC = sum w |C_t - C_{t-1}|, C_{t-1} = the D buffer
-        // written one frame earlier.  4 independent FMA chains, fixed order => deterministic.
-        auto consume = [&](const int t, const int dbuf, const uint32_t d_parity, auto role_c) {
+        // Each thread covers 32 of the tile's 64 coefficients (rows 4 role .. 4 role + 3): SC part
+        // = sum w |C_t|, TC part = sum w |C_t - C_{t-1}| with C_{t-1} = the D buffer written one
+        // frame earlier.  2 x 4 independent FMA chains, fixed order => deterministic.
+        auto consume = [&](const int t, const int dbuf, const uint32_t d_parity, const int xslot, auto role_c) {
             constexpr int ROLE = decltype(role_c)::value;
             mbar_wait(bar_d + 8 * dbuf, d_parity);
             tc_fence_after();
-            const uint32_t cur = tmem + lane_base + kColD + 64 * dbuf;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            uint32_t v[32];
-            float2 x[16];
+            uint32_t v[32], q[32];
+            tmem_ld32(tmem + lane_base + kColD + 64 * dbuf + 32 * ROLE, v);
+            tmem_ld32(tmem + lane_base + kColD + 64 * ((dbuf + 2) % 3) + 32 * ROLE, q);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float sa[4] = {0.f, 0.f, 0.f, 0.f}, da[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int n = 32 * ROLE + 2 * i;
+                const float2 c = make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                const float2 df = __ffma2_rn(make_float2(__uint_as_float(q[2 * i]), __uint_as_float(q[2 * i + 1])), make_float2(-1.f, -1.f), c);   // one rounding
+                if (n != 0) {                                    // DC carries no texture energy
+                    sa[i & 3] = fmaf(fabsf(c.x), kUmmaW[n], sa[i & 3]);
+                    da[i & 3] = fmaf(fabsf(df.x), kUmmaW[n], da[i & 3]);
+                }
+                sa[(i + 2) & 3] = fmaf(fabsf(c.y), kUmmaW[n + 1], sa[(i + 2) & 3]);
+                da[(i + 2) & 3] = fmaf(fabsf(df.y), kUmmaW[n + 1], da[(i + 2) & 3]);
+            }
+            float s = (sa[0] + sa[1]) + (sa[2] + sa[3]);
+            float d = (da[0] + da[1]) + (da[2] + da[3]);
+#pragma unroll
+            for (int m = 1; m < R; m <<= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, m);
+                d += __shfl_xor_sync(0xffffffffu, d, m);
+            }
+#pragma unroll
+            for (int m = TW; m < 32; m <<= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, m);
+                d += __shfl_xor_sync(0xffffffffu, d, m);
+            }
+            // the upper half hands its sums to the lower half through one of two slots: the write two
+            // frames later comes after the next barrier, which the reader reaches after this read
+            if (ROLE == 1) xchg[32 * xslot] = make_float2(s, d);
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + unit_local) : "memory");
             if (ROLE == 0) {
-                uint32_t v2[32];
-                tmem_ld32(cur, v);
-                tmem_ld32(cur + 32, v2);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int i = 0; i < 16; ++i) x[i] = make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-                abs_sums(0, x, acc);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) x[i] = make_float2(__uint_as_float(v2[2 * i]), __uint_as_float(v2[2 * i + 1]));
-                abs_sums(4, x, acc);
-            } else {
-                const uint32_t prv = tmem + lane_base + kColD + 64 * ((dbuf + 2) % 3);
-                uint32_t q[32];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    tmem_ld32(cur + 32 * h, v);
-                    tmem_ld32(prv + 32 * h, q);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)   // C_t - C_{t-1}, one rounding
-                        x[i] = __ffma2_rn(make_float2(__uint_as_float(q[2 * i]), __uint_as_float(q[2 * i + 1])), make_float2(-1.f, -1.f),
-                                          make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])));
-                    abs_sums(4 * h, x, acc);
+                const float2 o = xchg[32 * xslot];
+                s += o.x;
+                d += o.y;
+                if (t >= t0 && leader) {
+                    const float scv = s * p.inv_area;
+                    // the first frame without a halo has no predecessor (and D(-1) is uninitialised)
+                    const float tcv = (t == 0 && p.halo == nullptr) ? 0.f : d * p.inv_area;
+                    *out_sc = scv;
+                    *out_tc = tcv;
+                    if (t >= p.mm_begin && t < p.mm_end) {
+                        smin = fminf(smin, scv);
+                        smax = fmaxf(smax, scv);
+                        tmin = fminf(tmin, tcv);
+                        tmax = fmaxf(tmax, tcv);
+                    }
                 }
+                out_sc += out_step;
+                out_tc += out_step;
             }
-            float s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-#pragma unroll
-            for (int m = 1; m < R; m <<= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-#pragma unroll
-            for (int m = TW; m < 32; m <<= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-            if (t >= t0 && leader) {
-                // the first frame without a halo has no predecessor (and D(-1) is uninitialised)
-                const float val = (ROLE == 1 && t == 0 && p.halo == nullptr) ? 0.f : s * p.inv_area;
-                *out = val;
-                if (t >= p.mm_begin && t < p.mm_end) {
-                    vmin = fminf(vmin, val);
-                    vmax = fmaxf(vmax, val);
-                }
-            }
-            out += out_step;
         };
         // Frame loop, unrolled by the ring depth (a multiple of 2 and 3): step i of a round works
         // on ring slot (i + 1) % 6, A buffer (i + 1) & 1, D buffer i % 3.  Parities: ring and a_full
@@ -364,7 +374,7 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
                     const int it = it0 + i;
                     if (it >= n_iter) break;
                     if (it + 1 < n_iter) produce((i + 1) % 6, (i + 1) & 1, i == 5 ? round_parity ^ 1u : round_parity);
-                    consume(t_start + it, i % 3, (uint32_t)(i / 3) & 1u, role_c);
+                    if (!(p.dbg & 1)) consume(t_start + it, i % 3, (uint32_t)(i / 3) & 1u, i & 1, role_c);
                 }
                 round_parity ^= 1u;
             }
@@ -372,16 +382,20 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
         if (role == 0) run(std::integral_constant<int, 0>{});
         else run(std::integral_constant<int, 1>{});
 
-        if (p.mm != nullptr) {
+        if (p.mm != nullptr && role == 0) {
 #pragma unroll
             for (int m = 16; m > 0; m >>= 1) {
-                vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, m));
-                vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, m));
+                smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, m));
+                smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, m));
+                tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, m));
+                tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, m));
             }
             if (lane == 0) {
                 // non-negative floats order like their bit patterns
-                atomicMin(p.mm + 2 * role, __float_as_uint(vmin));
-                atomicMax(p.mm + 2 * role + 1, __float_as_uint(vmax));
+                atomicMin(p.mm + 0, __float_as_uint(smin));
+                atomicMax(p.mm + 1, __float_as_uint(smax));
+                atomicMin(p.mm + 2, __float_as_uint(tmin));
+                atomicMax(p.mm + 3, __float_as_uint(tmax));
             }
         }
     }
