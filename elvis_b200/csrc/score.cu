@@ -310,21 +310,24 @@ extern "C" int elvis_score_sc_tc(const elvis_plane* y, int32_t n_frames, const u
     p.inv_area = 1.0f / (float)(block_size * block_size);
     p.magic = 0x4B000000u;
     p.magic16 = 0x64006400u;
-    p.dbg = 0;
-    if (const char* e = getenv("ELVIS_UMMA_DBG")) p.dbg = (uint32_t)atoi(e);
 
-    // Implementation choice.  Default: the CUDA-core kernel (packed-fp32 butterflies, cp.async
-    // ring) -- on B200 it is the fastest of the three (profiles/).  ELVIS_SCORE_IMPL = mma | tma
-    // selects the tensor-core kernel with direct loads / with the TMA ring (16x16 blocks, plane
-    // 4- / 16-byte aligned); the tests exercise every path.
+    // Implementation choice (profiles/).  Default: the tcgen05 kernel (score_umma.cu:
+    // TMA ring, A operand and accumulators in tensor memory) when plane, strides and halo are
+    // 16-byte aligned and the clip is big enough to fill the machine; otherwise the CUDA-core
+    // kernel of this file (packed-fp32 butterflies, cp.async ring; any alignment).
+    // ELVIS_SCORE_IMPL = umma | simt | mma | tma forces one (mma / tma: the legacy mma.sync kernel
+    // with direct loads / with a TMA ring, 16x16 blocks only); the tests exercise every path.
     auto al = [&](int a) {
         return aligned_to(p.y, a) && p.frame_stride % a == 0 && p.row_stride % a == 0 && (!prev_halo || aligned_to(prev_halo, a));
     };
     enum { SIMT, MMA_DIRECT, MMA_TMA, UMMA } impl = SIMT;
+    const long warp_units = (long)By * ((Bx * (block_size / 8) * (block_size / 8) + 31) / 32);
+    if (al(16) && warp_units * n_frames >= 8L * kNumSMs * 4) impl = UMMA;
     if (const char* e = getenv("ELVIS_SCORE_IMPL")) {
         if (!strcmp(e, "mma") && block_size == 16 && al(4)) impl = MMA_DIRECT;
         else if (!strcmp(e, "tma") && block_size == 16 && al(16)) impl = MMA_TMA;
         else if (!strcmp(e, "umma") && al(16)) impl = UMMA;
+        else if (!strcmp(e, "simt")) impl = SIMT;
     }
     int override_len = 0;
     if (const char* e = getenv("ELVIS_SCORE_CHUNK")) override_len = atoi(e);

@@ -18,7 +18,6 @@ struct ScoreParams {
     float inv_area;
     uint32_t magic;     // 0x4B000000, passed at run time (see byte_as_biased_float)
     uint32_t magic16;   // 0x64006400: the fp16 analogue, used by the tcgen05 kernel
-    uint32_t dbg;       // ELVIS_UMMA_DBG experiment switches (tcgen05 kernel)
 };
 
 // implemented in score.cu (CUDA cores, any supported block size) and score_mma.cu

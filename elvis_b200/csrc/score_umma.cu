@@ -192,12 +192,10 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
                 }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem + kGroupCols * g + kColD + 64 * dbuf, a_tmem = tmem + kGroupCols * g + kColA + 32 * buf;
-                if (!(p.dbg & 4)) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_hi + 2 * k, k > 0);   // 16 fp16 = 8 columns = 32 B
+                for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_hi + 2 * k, k > 0);   // 16 fp16 = 8 columns = 32 B
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_lo + 2 * k, 1);
-                }
+                for (int k = 0; k < 4; ++k) umma_ts(d_tmem, a_tmem + 8 * k, b_lo + 2 * k, 1);
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar + 16 + 8 * dbuf) : "memory");
                 if (++dbuf == 3) dbuf = 0;
             }
@@ -271,11 +269,6 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
             const __half2 off = __floats2half2_rn(1152.f, 1152.f);   // 1024 (PRMT bias) + 128 (centering)
             mbar_wait(bar_full + 8 * slot, full_parity);
             const uint32_t src = tile_smem + slot * kBoxBytes;
-            if (p.dbg & 2) {
-                mbar_arrive(bar_a + 8 * buf);
-                mbar_arrive(bar_empty + 8 * slot);
-                return;
-            }
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 uint2 w;
@@ -374,7 +367,7 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
                     const int it = it0 + i;
                     if (it >= n_iter) break;
                     if (it + 1 < n_iter) produce((i + 1) % 6, (i + 1) & 1, i == 5 ? round_parity ^ 1u : round_parity);
-                    if (!(p.dbg & 1)) consume(t_start + it, i % 3, (uint32_t)(i / 3) & 1u, i & 1, role_c);
+                    consume(t_start + it, i % 3, (uint32_t)(i / 3) & 1u, i & 1, role_c);
                 }
                 round_parity ^= 1u;
             }

@@ -27,9 +27,15 @@ def to_dev(a, dev):
 
 
 # ---------------------------------------------------------------------------------- a1
-@pytest.mark.parametrize("bs,H,W,T", [(16, 64, 96, 7), (8, 40, 72, 5), (32, 64, 128, 4), (16, 48, 272, 30), (16, 1080, 1920, 3)])
-def test_sc_tc_vs_spec(dev, bs, H, W, T):
+IMPLS = ["umma", "simt"]      # tcgen05 kernel (default for large aligned clips) / CUDA-core kernel
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("bs,H,W,T", [(16, 64, 96, 7), (8, 40, 72, 5), (32, 64, 128, 4), (16, 48, 272, 30), (16, 1080, 1920, 3),
+                                      (8, 72, 1000, 14), (32, 96, 528, 13)])
+def test_sc_tc_vs_spec(dev, monkeypatch, impl, bs, H, W, T):
     from elvis_b200 import ops
+    monkeypatch.setenv("ELVIS_SCORE_IMPL", impl)
     y = synth_luma(T, H, W, seed=bs + T)
     sc, tc, mm = ops.score_sc_tc(to_dev(y, dev), bs)
     rsc, rtc = spec_scoring.sc_tc(y, bs)
@@ -41,8 +47,10 @@ def test_sc_tc_vs_spec(dev, bs, H, W, T):
     assert mm.tolist() == [sc.min(), sc.max(), tc.min(), tc.max()]
 
 
-def test_sc_tc_random_noise_and_static(dev):
+@pytest.mark.parametrize("impl", IMPLS)
+def test_sc_tc_random_noise_and_static(dev, monkeypatch, impl):
     from elvis_b200 import ops
+    monkeypatch.setenv("ELVIS_SCORE_IMPL", impl)
     rng = np.random.default_rng(5)
     y = rng.integers(0, 256, (6, 64, 64), dtype=np.uint8)
     y[3] = y[2]                      # a repeated frame: TC must be exactly 0
@@ -55,9 +63,11 @@ def test_sc_tc_random_noise_and_static(dev):
     assert np.all(tc.cpu().numpy()[3] == 0)
 
 
-def test_sc_tc_chunking_and_halo(dev, monkeypatch):
+@pytest.mark.parametrize("impl", IMPLS)
+def test_sc_tc_chunking_and_halo(dev, monkeypatch, impl):
     """Chunk boundaries and the sharding halo must not change any value."""
     from elvis_b200 import ops
+    monkeypatch.setenv("ELVIS_SCORE_IMPL", impl)
     y = synth_luma(21, 32, 64, seed=9)
     yd = to_dev(y, dev)
     monkeypatch.setenv("ELVIS_SCORE_CHUNK", "64")
@@ -69,6 +79,8 @@ def test_sc_tc_chunking_and_halo(dev, monkeypatch):
         np.testing.assert_allclose(a.cpu().numpy(), rsc, rtol=RTOL, atol=0)
     for a in (tc1, tc4):
         np.testing.assert_allclose(a.cpu().numpy(), rtc, rtol=RTOL, atol=0)
+    if impl == "umma":      # coefficients are computed afresh per frame: chunking cannot change a bit
+        assert np.array_equal(sc1.cpu().numpy(), sc4.cpu().numpy()) and np.array_equal(tc1.cpu().numpy(), tc4.cpu().numpy())
     # halo: frames 8.. scored alone with frame 7 as prev_halo == the tail of the full run
     sch, tch, mm = ops.score_sc_tc(yd[8:], 16, prev_halo=yd[7], minmax_range=(2, 5))
     rsc_h, rtc_h = spec_scoring.sc_tc(y[8:], 16, prev=y[7])
