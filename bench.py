@@ -138,7 +138,7 @@ def run_reference(args):
             "config": config_dict(args.gpus),
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -266,11 +266,11 @@ def run_ours(args):
               "stretch": {"ms": stage_ms[2], "gbs": ab["stretch"] * T / stage_ms[2] / 1e6},
               "score_kernel_alone": {"ms": sc_ms, "gbs": ab["score"] * T / sc_ms / 1e6}}
     achieved = ab["score"] * T / sc_ms / 1e6
-    roofline = {"bound": "hbm", "kernel": "score_kernel<2,true> (elvis_score_sc_tc)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "score_umma_kernel<2> (elvis_score_sc_tc)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch over the 120-frame clip,
-                # ncu --set full capture profiles/r1c_ncu_full_summary.csv (1.0037e9 + 0.0339e9)
-                "traffic": 1.0375e9 if T == FRAMES else None, "peak_source": peak_src,
+                # ncu --set full capture profiles/r1d_ncu_full_summary.csv (1.0038e9 + 0.0351e9)
+                "traffic": 1.0389e9 if T == FRAMES else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ab["score"] * T,
                 "whole_step": {"achieved": ab["total"] * T / ms_per_step / 1e6, "frac": ab["total"] * T / ms_per_step / 1e6 / peak,
                                "note": "all three stages, pipelined as timed"},
@@ -317,9 +317,18 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "u8 pixels, f32 DCT, f64 scores", "data": "synthetic",
                 "config": config_dict(world, T), "roofline": roofline, "cpu_baseline": cb, "e2e": e2e,
                 "clocks": clocks, "gpu_launches": launches_per_step * args.steps}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -335,6 +344,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its
+    # version banner to stdout when NCCL_DEBUG is set on the box), so everything but our own
+    # line goes to stderr: fd 1 is pointed at fd 2 and the line is written to the saved fd.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
