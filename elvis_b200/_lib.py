@@ -59,6 +59,11 @@ SIGNATURES = {
     "elvis_rowcol_expand": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp],
     "elvis_invert_block_map": [_vp, _i32, _i64, _vp, _i64, _vp],
     "elvis_gather_blocks": [_PP, _PP, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp],
+    "elvis_roi_kvazaar": [_vp, _i64, _i32, _i32, _vp, _vp],
+    "elvis_roi_prepare_f32": [_vp, _i64, _i32, _vp, _vp],
+    "elvis_resize_area_f32": [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
+    "elvis_roi_svtav1_offsets": [_vp, _i64, _i32, _i32, _vp, _vp],
+    "elvis_rgb_to_i420": [_PP, _PP, _PP, _PP, _i32, _vp],
 }
 EXPORTS = ["elvis_abi_version", "elvis_error_string", "elvis_last_cuda_error", *SIGNATURES]
 

@@ -191,3 +191,23 @@ def gaussian_kernels(max_level: int) -> np.ndarray:
         tab[level, 0] = ksize
         tab[level, 1:1 + ksize] = q
     return tab
+
+
+@lru_cache(maxsize=64)
+def area_f32_tables(ssize: int, dsize: int):
+    """cv2's decimation table of a float INTER_AREA resize along one axis, as the three arrays
+    elvis_resize_area_f32 takes (start[dsize + 1] int32, source index int32, weight float32)."""
+    return _area_entries(ssize, dsize)
+
+
+def area_f32_plan(sh: int, sw: int, dh: int, dw: int):
+    """(int_scale_x, int_scale_y, simd_cols) of cv2.resize(float32, INTER_AREA): both 0 unless both
+    ratios are integers, in which case cv2 takes its window-sum path; its 2 x 2 case computes the
+    leading multiple of 4 destination columns with a 4-lane vector kernel that adds in a different
+    order (oracle/spec_cv.py resize_area_f32, pinned against the cv2 of this image)."""
+    sx, sy = sw / dw, sh / dh
+    ix, iy = int(round(sx)), int(round(sy))
+    eps = np.finfo(np.float64).eps
+    if abs(sx - ix) < eps and abs(sy - iy) < eps:
+        return ix, iy, (dw // 4) * 4 if (ix == 2 and iy == 2) else 0
+    return 0, 0, 0

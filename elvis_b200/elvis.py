@@ -180,6 +180,49 @@ def restore_downsample_opencv_lanczos(downsampled_image: np.ndarray, downscale_m
     return ops.restore_lanczos(_packed_clip(downsampled_image), levels, block_size, smalls)[0].cpu().numpy()
 
 
+# ---------------------------------------------------------------- x265 per-block qpfile (8f rank 3)
+def x265_ctu_size(block_size: int, width: int, height: int) -> int:
+    """CTU size choice of encode_with_roi (elvis.py:2032-2053)."""
+    valid = [16, 32, 64]
+    largest = max(width, height)
+    min_ctu = 64 if largest >= 4320 else 32 if largest >= 2160 else 16
+    nearest = min(valid, key=lambda size: abs(size - block_size))
+    if nearest < block_size:
+        larger = [size for size in valid if size >= block_size]
+        ctu = larger[0] if larger else valid[-1]
+    else:
+        ctu = nearest
+    if ctu < min_ctu:
+        ctu = [size for size in valid if size >= min_ctu][0]
+    return ctu
+
+
+def per_block_qp_maps(removability_scores: np.ndarray, block_size: int, width: int, height: int) -> Tuple[np.ndarray, int]:
+    """Part 1 of encode_with_roi up to the aligned maps (elvis.py:2030-2074): scores in [0, 1] ->
+    float32 QP offsets in [-1, 1] on the CTU grid (INTER_AREA).  Returns (maps (T, rows, cols), ctu)."""
+    import math
+    T, by, bx = removability_scores.shape
+    ctu = x265_ctu_size(block_size, width, height)
+    cols, rows = math.ceil(width / ctu), math.ceil(height / ctu)
+    qp = ops.roi_prepare_f32(_to_dev(removability_scores, np.float64), 1)
+    if (rows, cols) != (by, bx):
+        if ctu < block_size or rows > by or cols > bx:
+            raise NotImplementedError("CTU grid finer than the block grid (cv2 bilinear path) is not supported")
+        qp = ops.resize_area_f32(qp, rows, cols)
+    return qp.cpu().numpy(), ctu
+
+
+def write_per_block_qpfile(removability_scores: np.ndarray, block_size: int, width: int, height: int, qpfile_path: str) -> None:
+    """The qpfile text of encode_with_roi (elvis.py:2076-2090): `frame P -1 bx,by,qp ...` per frame."""
+    maps, _ = per_block_qp_maps(removability_scores, block_size, width, height)
+    rows, cols = maps.shape[1:]
+    with open(qpfile_path, "w") as f:
+        for t in range(maps.shape[0]):
+            parts = [f"{t} P -1"]
+            parts.extend(f"{x},{y},{maps[t, y, x]:.4f}" for y in range(rows) for x in range(cols))
+            f.write(" ".join(parts) + "\n")
+
+
 # ---------------------------------------------------------------- side channels
 def encode_strength_maps_to_npz(strength_maps: np.ndarray, output_path: str) -> None:
     """elvis.py:2247-2259 (uint8 maps, np.savez_compressed key `strength_maps`)."""

@@ -496,3 +496,78 @@ def gather_blocks(clip: torch.Tensor, block_map: torch.Tensor, block_px: int, ds
     call("elvis_gather_blocks", C.byref(src), C.byref(dst), T, block_px, dst_by, dst_bx, src_by, src_bx, _ptr(block_map),
          block_map.shape[1], block_map.stride(1), _stream())
     return out
+
+
+# ---------------------------------------------------------------- ROI side files, raw 4:2:0 (8f rank 3)
+def roi_kvazaar(importance: torch.Tensor, base_qp: int, qp_range: int) -> torch.Tensor:
+    """float64 importance (any shape) -> int8 delta QP of utils.py:1046-1052."""
+    _check_cuda(importance, torch.float64, "importance")
+    importance = importance.contiguous()
+    out = torch.empty(importance.shape, dtype=torch.int8, device=importance.device)
+    if out.numel():
+        call("elvis_roi_kvazaar", _ptr(importance), importance.numel(), int(base_qp), int(qp_range), _ptr(out), _stream())
+    return out
+
+
+def roi_prepare_f32(x: torch.Tensor, mode: int) -> torch.Tensor:
+    """mode 0: float32(x); mode 1: float32(clip(2 x - 1, -1, 1)) (float64 arithmetic)."""
+    _check_cuda(x, torch.float64, "x")
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    if out.numel():
+        call("elvis_roi_prepare_f32", _ptr(x), x.numel(), int(mode), _ptr(out), _stream())
+    return out
+
+
+def resize_area_f32(maps: torch.Tensor, dst_h: int, dst_w: int) -> torch.Tensor:
+    """cv2.resize(map, (dst_w, dst_h), INTER_AREA) for every float32 map of (T, h, w); shrinking only."""
+    _check_cuda(maps, torch.float32, "maps")
+    if maps.dim() != 3:
+        raise ValueError("maps must be (T, h, w)")
+    maps = maps.contiguous()
+    T, sh, sw = maps.shape
+    if dst_h > sh or dst_w > sw or dst_h <= 0 or dst_w <= 0:
+        raise NotImplementedError("INTER_AREA enlargement (cv2 switches to a bilinear kernel) is not supported")
+    out = torch.empty((T, dst_h, dst_w), dtype=torch.float32, device=maps.device)
+    if out.numel() == 0:
+        return out
+    ix, iy, simd = _tables.area_f32_plan(sh, sw, dst_h, dst_w)
+    if ix:
+        call("elvis_resize_area_f32", _ptr(maps), T, sh, sw, _ptr(out), dst_h, dst_w, None, None, None, None, None, None, ix, iy, simd,
+             _stream())
+        return out
+    tabs = [torch.from_numpy(a).to(maps.device) for a in (*_tables.area_f32_tables(sw, dst_w), *_tables.area_f32_tables(sh, dst_h))]
+    call("elvis_resize_area_f32", _ptr(maps), T, sh, sw, _ptr(out), dst_h, dst_w, *[_ptr(t) for t in tabs], 0, 0, 0, _stream())
+    return out
+
+
+def roi_svtav1_offsets(resized: torch.Tensor, base_crf: int, qp_range: int) -> torch.Tensor:
+    """float32 importance on the 64-pixel grid -> int32 QP offsets of utils.py:1081-1088."""
+    _check_cuda(resized, torch.float32, "resized")
+    resized = resized.contiguous()
+    out = torch.empty(resized.shape, dtype=torch.int32, device=resized.device)
+    if out.numel():
+        call("elvis_roi_svtav1_offsets", _ptr(resized), resized.numel(), int(base_crf), int(qp_range), _ptr(out), _stream())
+    return out
+
+
+def rgb_to_i420(frames: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(T, H, W, 3) uint8 RGB -> (T, H*W*3/2) uint8 I420 (cv2.COLOR_RGB2YUV_I420, utils.py:460)."""
+    _check_cuda(frames, torch.uint8, "frames")
+    if frames.dim() != 4 or frames.shape[3] != 3:
+        raise ValueError("frames must be (T, H, W, 3)")
+    T, H, W, _ = frames.shape
+    if H % 2 or W % 2:
+        raise ValueError("4:2:0 needs even frame dimensions")
+    if out is None:
+        out = torch.empty((T, H * W * 3 // 2), dtype=torch.uint8, device=frames.device)
+    elif tuple(out.shape) != (T, H * W * 3 // 2) or not out.is_contiguous():
+        raise ValueError("out must be a contiguous (T, H*W*3/2) buffer")
+    if out.numel() == 0:
+        return out
+    y = out[:, :H * W].view(T, H, W)
+    u = out[:, H * W:H * W * 5 // 4].view(T, H // 2, W // 2)
+    v = out[:, H * W * 5 // 4:].view(T, H // 2, W // 2)
+    planes = [plane_of(frames, "frames"), plane_of(y, "y"), plane_of(u, "u"), plane_of(v, "v")]
+    call("elvis_rgb_to_i420", *[C.byref(p) for p in planes], T, _stream())
+    return out

@@ -194,3 +194,51 @@ def restore_with_opencv_unsharp(frames: List[np.ndarray], degradation_maps: np.n
 
 # utils.py:1253-1317: despite its name the reference's "lanczos" restorer runs the same unsharp mask
 restore_with_opencv_lanczos = restore_with_opencv_unsharp
+
+
+# ---------------------------------------------------------------- ROI side files and raw frames (8f rank 3)
+def write_y4m(frames: List[np.ndarray], y4m_path: str, framerate: float) -> None:
+    """utils.py:453-462: YUV4MPEG2 file, 4:2:0, frames converted like cv2.COLOR_RGB2YUV_I420."""
+    height, width = frames[0].shape[:2]
+    fps_num = int(round(framerate * 1000))
+    clip = _to_dev(np.stack([np.asarray(f) for f in frames]), np.uint8)
+    i420 = ops.rgb_to_i420(clip).cpu().numpy()
+    with open(y4m_path, "wb") as f:
+        f.write(f"YUV4MPEG2 W{width} H{height} F{fps_num}:1000 Ip A1:1 C420\n".encode())
+        for t in range(len(frames)):
+            f.write(b"FRAME\n")
+            f.write(i420[t].tobytes())
+
+
+def _same_shape_runs(maps):
+    """Consecutive runs of equally shaped maps (the reference accepts a list of per-frame arrays)."""
+    start = 0
+    for i in range(1, len(maps) + 1):
+        if i == len(maps) or np.shape(maps[i]) != np.shape(maps[start]):
+            yield start, i
+            start = i
+
+
+def create_kvazaar_roi_file(importance_scores: List[np.ndarray], roi_path: str, base_qp: int, qp_range: int = 15) -> None:
+    """utils.py:1026-1053: per frame `int32 w, h` then `int8 dqp[h][w]`."""
+    with open(roi_path, "wb") as f:
+        for a, b in _same_shape_runs(importance_scores):
+            imp = _to_dev(np.stack([np.asarray(m) for m in importance_scores[a:b]]), np.float64)
+            dqp = ops.roi_kvazaar(imp, base_qp, qp_range).cpu().numpy()
+            h, w = dqp.shape[1:]
+            for t in range(b - a):
+                f.write(np.array([w, h], dtype=np.int32).tobytes())
+                f.write(dqp[t].tobytes())
+
+
+def create_svtav1_roi_file(importance_scores: List[np.ndarray], roi_path: str, base_crf: int, qp_range: int, width: int,
+                           height: int) -> None:
+    """utils.py:1056-1092: one text line per frame, QP offsets of the 64x64 superblocks in row order."""
+    blocks_x, blocks_y = (width + 63) // 64, (height + 63) // 64
+    with open(roi_path, "w") as f:
+        for a, b in _same_shape_runs(importance_scores):
+            imp = _to_dev(np.stack([np.asarray(m) for m in importance_scores[a:b]]), np.float64)
+            resized = ops.resize_area_f32(ops.roi_prepare_f32(imp, 0), blocks_y, blocks_x)
+            offsets = ops.roi_svtav1_offsets(resized, base_crf, qp_range).cpu().numpy()
+            for t in range(b - a):
+                f.write(f"{a + t} " + " ".join(map(str, offsets[t].flatten().astype(int))) + "\n")

@@ -255,6 +255,40 @@ ELVIS_API int elvis_gather_blocks(const elvis_plane* src, const elvis_plane* dst
                         int32_t dst_by, int32_t dst_bx, int32_t src_by, int32_t src_bx, const int32_t* map,
                         int32_t map_rows, int32_t map_pitch, elvis_stream_t stream);
 
+/* ---- 8f rank 3: the step after scoring on the server -- delta-QP side files and raw 4:2:0 frames
+ * (utils.py:453-462, 1026-1092; elvis.py:2027-2090).  The host mirrors write the files. */
+
+/* create_kvazaar_roi_file (utils.py:1046-1052): dqp = int8(clip(clip((1 - imp) * 2 * qp_range - qp_range,
+ * -14, 14), 0 - base_qp, 51 - base_qp)), float64 arithmetic, truncating cast. */
+ELVIS_API int elvis_roi_kvazaar(const double* importance, int64_t n, int32_t base_qp, int32_t qp_range, int8_t* dqp,
+                      elvis_stream_t stream);
+
+/* float64 -> float32 input of the two resized ROI maps.  mode 0: float32(x) (utils.py:1078);
+ * mode 1: float32(clip(2 x - 1, -1, 1)) (elvis.py:2030). */
+ELVIS_API int elvis_roi_prepare_f32(const double* x, int64_t n, int32_t mode, float* out, elvis_stream_t stream);
+
+/* cv2.resize(float32 map, INTER_AREA), shrinking only, bit-exact (oracle/spec_cv.py resize_area_f32):
+ * n_maps maps of src_h x src_w -> dst_h x dst_w.  General ratios: per destination column / row the
+ * entries [ofs[d], ofs[d+1]) of (source index, weight) of cv2's decimation table
+ * (elvis_b200/_tables.py:area_f32_tables).  When both ratios are integers pass them as
+ * int_scale_x/y (> 0) and null tables: cv2 then sums the window and multiplies by 1/area;
+ * simd_cols = number of leading destination columns cv2 computes with its 4-lane 2x2 vector path. */
+ELVIS_API int elvis_resize_area_f32(const float* src, int32_t n_maps, int32_t src_h, int32_t src_w, float* dst, int32_t dst_h,
+                          int32_t dst_w, const int32_t* x_ofs, const int32_t* x_src, const float* x_alpha,
+                          const int32_t* y_ofs, const int32_t* y_src, const float* y_alpha, int32_t int_scale_x,
+                          int32_t int_scale_y, int32_t simd_cols, elvis_stream_t stream);
+
+/* create_svtav1_roi_file (utils.py:1081-1088): levels = clip(int32(r * 8), 0, 7);
+ * offset = clip(qp_range - levels * 2 * qp_range // 7, 0 - base_crf, 63 - base_crf). */
+ELVIS_API int elvis_roi_svtav1_offsets(const float* resized, int64_t n, int32_t base_crf, int32_t qp_range, int32_t* offsets,
+                             elvis_stream_t stream);
+
+/* write_y4m's cv2.cvtColor(frame, COLOR_RGB2YUV_I420) (utils.py:453-462): packed RGB clip -> Y, U, V
+ * planes (BT.601 limited range, 20-bit fixed point, chroma from the top-left pixel of each 2x2 quad).
+ * Height and width must be even (ELVIS_ERR_SHAPE otherwise, as cv2 asserts). */
+ELVIS_API int elvis_rgb_to_i420(const elvis_plane* rgb, const elvis_plane* y, const elvis_plane* u, const elvis_plane* v,
+                      int32_t n_frames, elvis_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

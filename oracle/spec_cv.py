@@ -246,3 +246,68 @@ def resize_lanczos4(small: np.ndarray, dsize: int) -> np.ndarray:
     rows = (s[..., :, idx] * coef).sum(axis=-1)                                  # (..., ssize, dsize)
     out = (rows[..., idx, :] * coef[:, :, None]).sum(axis=-2)                    # (..., dsize, dsize)
     return np.clip((out + (1 << 21)) >> 22, 0, 255).astype(np.uint8)
+
+
+# ---------------------------------------------------------------- float32 INTER_AREA, RGB -> I420 (8f rank 3)
+def resize_area_f32(src: np.ndarray, dh: int, dw: int) -> np.ndarray:
+    """cv2.resize(float32 2-D map, (dw, dh), interpolation=cv2.INTER_AREA) when shrinking, operation
+    by operation in float32 (cv2 imgproc resize.cpp: resizeAreaFast_ for integer ratios,
+    ResizeArea_Invoker with the decimation table of `area_table` otherwise).  The 2 x 2 case has a
+    4-lane vector kernel for the leading multiple of 4 columns that adds in a different order than
+    the scalar tail; that width is a property of the cv2 build (128-bit universal intrinsics in the
+    cv2 4.13 of this image, which the tests pin against)."""
+    src = np.asarray(src, np.float32)
+    sh, sw = src.shape
+    if dh > sh or dw > sw:
+        raise NotImplementedError("enlarging INTER_AREA uses cv2's bilinear kernel")
+    sx, sy = sw / dw, sh / dh
+    ix, iy = int(round(sx)), int(round(sy))
+    eps = np.finfo(np.float64).eps
+    out = np.zeros((dh, dw), np.float32)
+    f32 = np.float32
+    if abs(sx - ix) < eps and abs(sy - iy) < eps:
+        scale = f32(1.0 / (ix * iy))
+        simd_cols = (dw // 4) * 4 if (ix == 2 and iy == 2) else 0
+        for y in range(dh):
+            for x in range(dw):
+                win = src[y * iy:(y + 1) * iy, x * ix:(x + 1) * ix]
+                if x < simd_cols:
+                    out[y, x] = f32(f32(f32(win[0, 0] + win[0, 1]) + f32(win[1, 0] + win[1, 1])) * f32(0.25))
+                    continue
+                vals = win.reshape(-1)
+                s, k = f32(0), 0
+                while k + 4 <= len(vals):
+                    s = f32(s + f32(f32(f32(vals[k] + vals[k + 1]) + vals[k + 2]) + vals[k + 3]))
+                    k += 4
+                while k < len(vals):
+                    s = f32(s + vals[k])
+                    k += 1
+                out[y, x] = f32(s * scale)
+        return out
+    xtab = [(d, s, f32(a)) for s, d, a in area_table(sw, dw)]
+    ytab = [(d, s, f32(a)) for s, d, a in area_table(sh, dh)]
+    first = np.ones(dh, bool)
+    for dy, sy_, beta in ytab:
+        buf = np.zeros(dw, np.float32)
+        for dx, sx_, alpha in xtab:
+            buf[dx] = f32(buf[dx] + f32(src[sy_, sx_] * alpha))
+        term = (beta * buf).astype(np.float32)
+        out[dy] = term if first[dy] else (out[dy] + term).astype(np.float32)
+        first[dy] = False
+    return out
+
+
+def rgb_to_i420(frame: np.ndarray) -> np.ndarray:
+    """cv2.cvtColor(frame, cv2.COLOR_RGB2YUV_I420) for an (H, W, 3) uint8 frame with even H, W:
+    BT.601 limited range in 20-bit fixed point, chroma taken from the top-left pixel of each 2 x 2
+    quad.  Returns the (H * 3 / 2, W) uint8 I420 image cv2 returns."""
+    h, w = frame.shape[:2]
+    if h % 2 or w % 2:
+        raise ValueError("4:2:0 needs even frame dimensions")
+    r, g, b = (frame[..., c].astype(np.int64) for c in range(3))
+    half, sh = 1 << 19, 20
+    y = (269484 * r + 528482 * g + 102760 * b + half + (16 << sh)) >> sh
+    rs, gs, bs = r[::2, ::2], g[::2, ::2], b[::2, ::2]
+    u = (-155188 * rs - 305135 * gs + 460324 * bs + half + (128 << sh)) >> sh
+    v = (460324 * rs - 385875 * gs - 74448 * bs + half + (128 << sh)) >> sh
+    return np.concatenate([y.reshape(-1), u.reshape(-1), v.reshape(-1)]).astype(np.uint8).reshape(h * 3 // 2, w)

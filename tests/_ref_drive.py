@@ -60,3 +60,23 @@ def run_reference_removability(sc, tc, fg_masks, alpha, beta, block_size):
             out = E.calculate_removability_scores(raw, frames_dir, width, height, block_size,
                                                   alpha=alpha, working_dir=tmp, smoothing_beta=beta)
     return np.asarray(out)
+
+
+def reference_qpfile(E, scores, block_size, width, height, workdir):
+    """Text of the per-block qpfile the reference's encode_with_roi (elvis.py:2013-2139) writes,
+    read at the point where it is handed to encode_video (which is replaced: no ffmpeg here)."""
+    import os
+    os.makedirs(workdir, exist_ok=True)
+    captured = {}
+
+    def fake_encode_video(**kwargs):
+        with open(kwargs["qpfile"]) as f:
+            captured["text"] = f.read()
+
+    real = E.encode_video
+    E.encode_video = fake_encode_video
+    try:
+        E.encode_with_roi(workdir, os.path.join(workdir, "out.mp4"), scores, block_size, 30.0, width, height)
+    finally:
+        E.encode_video = real
+    return captured["text"]

@@ -109,6 +109,27 @@ def main():
         g[f"f2_passes_{tag}"] = np.concatenate(passes).astype(np.int32)
         g[f"f2_full_ri_{tag}"] = U.stretch_frame_removal_indices(small2, passes, 6, 8, 8)
 
+    # 8f rank 3 -- ROI side files and the Y4M frame conversion, as file bytes
+    import tempfile
+    from _ref_drive import reference_qpfile
+    with tempfile.TemporaryDirectory() as td:
+        imps = [rng.random((17, 30)) for _ in range(2)]
+        imps[0][0, :4] = [0.0, 1.0, 0.5, 0.125]
+        g["f3_imps"] = np.stack(imps)
+        U.create_kvazaar_roi_file(imps, os.path.join(td, "k.bin"), 40, 15)
+        g["f3_kvazaar"] = np.frombuffer(open(os.path.join(td, "k.bin"), "rb").read(), np.uint8)
+        U.create_svtav1_roi_file(imps, os.path.join(td, "s.txt"), 35, 10, 480, 272)
+        g["f3_svtav1"] = np.frombuffer(open(os.path.join(td, "s.txt"), "rb").read(), np.uint8)
+        rgb = [rng.integers(0, 256, (34, 50, 3), dtype=np.uint8) for _ in range(2)]
+        g["f3_rgb"] = np.stack(rgb)
+        U.write_y4m(rgb, os.path.join(td, "v.y4m"), 30.0)
+        g["f3_y4m"] = np.frombuffer(open(os.path.join(td, "v.y4m"), "rb").read(), np.uint8)
+        qs = rng.random((2, 34, 60))
+        g["f3_scores"] = qs
+        g["f3_qpfile"] = np.frombuffer(reference_qpfile(E, qs, 16, 960, 544, os.path.join(td, "q")).encode(), np.uint8)
+        g["f3_qpfile_4k"] = np.frombuffer(reference_qpfile(E, qs[:1, :, :60].repeat(4, 1).repeat(4, 2)[:, :135, :240].copy(), 16, 3840, 2160,
+                                                           os.path.join(td, "q4")).encode(), np.uint8)
+
     out = os.path.join(HERE, "reference_vectors.npz")
     np.savez_compressed(out, **g)
     print(f"wrote {out}: {len(g)} arrays, {os.path.getsize(out) / 1024:.1f} KiB")

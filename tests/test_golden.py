@@ -76,6 +76,22 @@ def _check_all(impl):
         assert all(a.dtype == np.int32 for a in passes) and np.array_equal(np.concatenate(passes), G[f"f2_passes_{tag}"]), tag
         assert np.array_equal(impl.stretch_frame_removal_indices(small2, passes, 6, 8, 8), G[f"f2_full_ri_{tag}"]), tag
 
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "f")
+        imps = list(G["f3_imps"])
+        impl.create_kvazaar_roi_file(imps, path, 40, 15)
+        assert open(path, "rb").read() == G["f3_kvazaar"].tobytes()
+        impl.create_svtav1_roi_file(imps, path, 35, 10, 480, 272)
+        assert open(path, "rb").read() == G["f3_svtav1"].tobytes()
+        impl.write_y4m(list(G["f3_rgb"]), path, 30.0)
+        assert open(path, "rb").read() == G["f3_y4m"].tobytes()
+        impl.write_per_block_qpfile(G["f3_scores"], 16, 960, 544, path)
+        assert open(path, "rb").read() == G["f3_qpfile"].tobytes()
+        s4k = G["f3_scores"][:1, :, :60].repeat(4, 1).repeat(4, 2)[:, :135, :240].copy()
+        impl.write_per_block_qpfile(s4k, 16, 3840, 2160, path)
+        assert open(path, "rb").read() == G["f3_qpfile_4k"].tobytes()
+
     assert np.array_equal(impl.restore_blur_opencv_unsharp_mask(G["f1_img"], G["f1_map"], 16), G["f1_out"])
     for tag, halo, tb in (("h0", 0, 0.0), ("h6b", 6, 0.2)):
         got = impl.restore_with_opencv_unsharp(list(G["f1_frames"]), G["f1_maps"], 16, halo=halo, temporal_blend=tb)

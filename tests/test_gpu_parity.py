@@ -266,6 +266,57 @@ def test_rowcol_plan_batched_matches_per_frame(dev):
             assert np.array_equal(pidx[t, i, :len(a)].cpu().numpy(), a)
 
 
+def test_roi_side_files_and_y4m(dev, tmp_path):
+    """8f rank 3 (utils.py:453-462, 1026-1092; elvis.py:2027-2090): files byte for byte vs the oracle port."""
+    from elvis_b200 import elvis as E, utils as U
+    rng = np.random.default_rng(21)
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    imps = [rng.random((135, 240)) for _ in range(2)] + [rng.random((17, 30))]
+    imps[0][0, :5] = [0.0, 1.0, 0.5, 0.125, 0.9999]
+    for base_qp, rq in ((48, 15), (3, 15), (30, 6)):
+        U.create_kvazaar_roi_file(imps, a, base_qp, rq)
+        P.create_kvazaar_roi_file(imps, b, base_qp, rq)
+        assert open(a, "rb").read() == open(b, "rb").read()
+    for (w, h, crf, rq) in ((3840, 2160, 35, 10), (480, 272, 60, 15), (1920, 1088, 2, 7), (2176, 1152, 30, 12)):
+        maps = [rng.random((h // 16, w // 16)) for _ in range(2)]
+        U.create_svtav1_roi_file(maps, a, crf, rq, w, h)
+        P.create_svtav1_roi_file(maps, b, crf, rq, w, h)
+        assert open(a).read() == open(b).read(), (w, h)
+    for (w, h, bs) in ((480, 272, 16), (3840, 2160, 16), (256, 128, 32), (4352, 2304, 32), (1024, 576, 8)):
+        scores = rng.random((2, h // bs, w // bs))
+        scores[0, 0, :2] = [0.0, 1.0]
+        E.write_per_block_qpfile(scores, bs, w, h, a)
+        P.write_per_block_qpfile(scores, bs, w, h, b)
+        assert open(a).read() == open(b).read(), (w, h, bs)
+    for (h, w) in ((34, 50), (64, 96), (2, 2), (270, 482)):
+        frames = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for _ in range(3)]
+        frames[0][0, :2] = [[255, 255, 255], [0, 0, 0]]
+        U.write_y4m(frames, a, 29.97)
+        P.write_y4m(frames, b, 29.97)
+        assert open(a, "rb").read() == open(b, "rb").read(), (h, w)
+    with pytest.raises(ValueError):
+        U.write_y4m([np.zeros((5, 8, 3), np.uint8)], a, 30.0)
+
+
+def test_rgb_to_i420_strided_and_resize_area_shapes(dev):
+    import torch
+    from elvis_b200 import ops
+    from oracle import spec_cv
+    rng = np.random.default_rng(22)
+    big = rng.integers(0, 256, (2, 40, 70, 3), dtype=np.uint8)
+    view = to_dev(big, dev)[:, 3:35, 5:59]                     # cropped, misaligned view: byte path
+    got = ops.rgb_to_i420(view).cpu().numpy()
+    for t in range(2):
+        assert np.array_equal(got[t], spec_cv.rgb_to_i420(big[t, 3:35, 5:59]).reshape(-1))
+    for (sh, sw, dh, dw) in [(135, 240, 34, 60), (136, 240, 34, 60), (16, 16, 8, 8), (34, 60, 17, 30), (10, 34, 5, 17), (9, 13, 4, 5), (7, 9, 7, 9)]:
+        a = (rng.random((3, sh, sw)) * 2 - 1).astype(np.float32)
+        got = ops.resize_area_f32(to_dev(a, dev), dh, dw).cpu().numpy()
+        for t in range(3):
+            assert np.array_equal(got[t], spec_cv.resize_area_f32(a[t], dh, dw)), (sh, sw, dh, dw)
+    with pytest.raises(NotImplementedError):
+        ops.resize_area_f32(torch.zeros((1, 4, 4), dtype=torch.float32, device=dev), 8, 4)
+
+
 def test_planar_pipeline_matches_per_plane_oracle(dev):
     """Planar YUV 4:2:0: mask from luma scores, applied to chroma at half block size."""
     from elvis_b200.pipeline import ElvisV1, Yuv420

@@ -109,6 +109,49 @@ def test_port_matches_reference_rowcol():
                               P.stretch_frame_removal_indices(m[0], bad, by, bx, bs))
 
 
+def test_spec_cv_float_area_and_i420_vs_cv2():
+    """8f rank 3 arithmetic: float32 INTER_AREA (general, integer-ratio and 2x2 vector paths) and
+    RGB -> I420, bit-exact against the cv2 of this image."""
+    rng = np.random.default_rng(11)
+    for (sh, sw, dh, dw) in [(135, 240, 34, 60), (136, 240, 34, 60), (67, 120, 17, 30), (8, 12, 4, 3), (9, 13, 4, 5),
+                             (135, 240, 68, 120), (16, 16, 8, 8), (34, 60, 17, 30), (10, 34, 5, 17), (24, 36, 8, 12), (7, 9, 7, 9)]:
+        a = (rng.random((sh, sw)) * 2 - 1).astype(np.float32)
+        assert np.array_equal(cv2.resize(a, (dw, dh), interpolation=cv2.INTER_AREA), spec_cv.resize_area_f32(a, dh, dw)), (sh, sw, dh, dw)
+    for (h, w) in [(6, 8), (64, 96), (2, 2), (34, 50)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        img[0, 0], img[0, 1] = (255, 255, 255), (0, 0, 0)
+        assert np.array_equal(cv2.cvtColor(img, cv2.COLOR_RGB2YUV_I420), spec_cv.rgb_to_i420(img))
+
+
+@needs_reference
+def test_port_matches_reference_roi_files(tmp_path):
+    """8f rank 3: the side files byte for byte (utils.py:453-462, 1026-1092; elvis.py:2027-2090)."""
+    E, U = ref_import.load("elvis"), ref_import.load("utils")
+    rng = np.random.default_rng(12)
+    imps = [rng.random((17, 30)) for _ in range(3)]
+    imps[1][0, :4] = [0.0, 1.0, 0.5, 0.125]
+    for base_qp, rng_qp in ((48, 15), (3, 15), (30, 6)):
+        U.create_kvazaar_roi_file(imps, str(tmp_path / "a.bin"), base_qp, rng_qp)
+        P.create_kvazaar_roi_file(imps, str(tmp_path / "b.bin"), base_qp, rng_qp)
+        assert (tmp_path / "a.bin").read_bytes() == (tmp_path / "b.bin").read_bytes()
+    for (w, h, crf, rq) in ((480, 272, 35, 10), (480, 272, 60, 15), (1920, 1088, 2, 7)):
+        maps = [rng.random((h // 16, w // 16)) for _ in range(2)]
+        U.create_svtav1_roi_file(maps, str(tmp_path / "a.txt"), crf, rq, w, h)
+        P.create_svtav1_roi_file(maps, str(tmp_path / "b.txt"), crf, rq, w, h)
+        assert (tmp_path / "a.txt").read_text() == (tmp_path / "b.txt").read_text()
+    frames = [rng.integers(0, 256, (32, 48, 3), dtype=np.uint8) for _ in range(2)]
+    U.write_y4m(frames, str(tmp_path / "a.y4m"), 29.97)
+    P.write_y4m(frames, str(tmp_path / "b.y4m"), 29.97)
+    assert (tmp_path / "a.y4m").read_bytes() == (tmp_path / "b.y4m").read_bytes()
+    # the qpfile of encode_with_roi: capture it where the reference hands it to the encoder
+    from _ref_drive import reference_qpfile
+    for (w, h, bs) in ((480, 272, 16), (3840, 2160, 16), (256, 128, 32), (4352, 2304, 32)):   # same grid, general, same, 2x2
+        scores = rng.random((2, h // bs, w // bs))
+        scores[0, 0, :3] = [0.0, 1.0, 0.5]
+        P.write_per_block_qpfile(scores, bs, w, h, str(tmp_path / "q.txt"))
+        assert reference_qpfile(E, scores, bs, w, h, str(tmp_path / "ref")) == (tmp_path / "q.txt").read_text(), (w, h, bs)
+
+
 @needs_reference
 def test_port_matches_reference_v2_and_scores():
     from _ref_drive import run_reference_removability

@@ -38,3 +38,13 @@ for amount in (0.1, 0.5):
     t_e = timed(lambda: ops.rowcol_expand(pidx[:, :P].contiguous(), pcnt[:, :P].contiguous(), fby, fbx))
     print(json.dumps({"shrink": amount, "frames": T, "passes": P, "final": [fby, fbx], "plan_ms": round(t_plan, 3),
                       "gather_ms": round(t_g, 3), "gather_GBps": round(2 * out.numel() / t_g / 1e6, 1), "expand_ms": round(t_e, 3)}))
+
+# 8f rank 3: RGB -> I420 of 4K frames (37.3 MB of traffic per frame)
+rgb = torch.randint(0, 256, (8, 2160, 3840, 3), dtype=torch.uint8, device=dev)
+i420 = torch.empty((8, 2160 * 3840 * 3 // 2), dtype=torch.uint8, device=dev)
+t_c = timed(lambda: ops.rgb_to_i420(rgb, out=i420), n=10)
+print(json.dumps({"rgb_to_i420_ms_per_8_4k_frames": round(t_c, 4), "GBps": round((rgb.numel() + i420.numel()) / t_c / 1e6, 1)}))
+imp = torch.rand((120, 135, 240), dtype=torch.float64, device=dev)
+t_k = timed(lambda: ops.roi_kvazaar(imp, 40, 15), n=10)
+t_s = timed(lambda: ops.roi_svtav1_offsets(ops.resize_area_f32(ops.roi_prepare_f32(imp, 0), 34, 60), 35, 10), n=10)
+print(json.dumps({"kvazaar_dqp_ms_120_frames": round(t_k, 4), "svtav1_offsets_ms_120_frames": round(t_s, 4)}))
