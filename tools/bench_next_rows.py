@@ -1,4 +1,5 @@
-"""Times the row+column plan / gather kernels at 4K, bs16 (240 x 135 blocks)."""
+"""Times the kernels of the SURVEY 8f rows 2-3 at 4K: row+column plan / gather / expand (bs16, 240 x 135 blocks),
+RGB -> I420 and the ROI maps."""
 import json
 import sys
 
