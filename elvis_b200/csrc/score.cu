@@ -338,8 +338,9 @@ extern "C" int elvis_score_sc_tc(const elvis_plane* y, int32_t n_frames, const u
         resident = (long)kNumSMs * 8;               // warps
     } else if (impl == UMMA) {
         const int R = block_size / 8;
-        tiles = ((long)By * ((Bx * R * R + 31) / 32) + 7) / 8;
-        resident = (long)kNumSMs;                   // CTAs of 8 worker warps
+        const int upc = score_umma_units_per_cta();
+        tiles = ((long)By * ((Bx * R * R + 31) / 32) + upc - 1) / upc;
+        resident = (long)kNumSMs * score_umma_ctas_per_sm();
     } else {
         tiles = (long)((Bx + 7) / 8) * ((By + 2) / 3);
         resident = (long)kNumSMs * 2;               // CTAs

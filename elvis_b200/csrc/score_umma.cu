@@ -10,7 +10,9 @@
 // fp32-accumulation accuracy.  C_t is computed afresh for every frame -- no running sum, so
 // SC / TC do not depend on how the clip is chunked.
 //
-// Roles.  A CTA is two groups of 128 tiles.  Tile m of a group is TMEM lane m; it is served by
+// Roles.  A CTA is one group of 128 tiles (ELVIS_UMMA_GROUPS = 1: two CTAs share an SM and its 512
+// TMEM columns; 5 % faster than one CTA of two groups, 356 vs 374 us).  Tile m of a group is
+// TMEM lane m; it is served by
 // TWO worker threads (lane m % 32 of warps q and q + 4, q = m / 32 -- both reach lanes 32q..),
 // which walk it through a run of frames:
 //   * both read half of the tile's 8 luma rows from a shared-memory ring, expand the 32 bytes
@@ -39,7 +41,11 @@ namespace {
 
 #include "score_umma_tables.inc"
 
-constexpr int kGroups = 2;               // groups of 128 tiles per CTA, each with its own A / D buffers
+#ifndef ELVIS_UMMA_GROUPS
+#define ELVIS_UMMA_GROUPS 1
+#endif
+constexpr int kGroups = ELVIS_UMMA_GROUPS;   // groups of 128 tiles per CTA, each with its own A / D buffers
+constexpr int kCtasPerSm = 2 / kGroups;       // tensor memory holds two groups per SM
 constexpr int kUnitsPerCta = kGroups * 4;     // warp units (32 tiles) per CTA
 constexpr int kWorkerWarps = 2 * kUnitsPerCta;   // an SC warp and a TC warp per unit
 constexpr int kMmaWarp = kWorkerWarps;
@@ -99,6 +105,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) : "r"(taddr) : "memory");
 }
 
+// 64-thread named barrier of the two warps that share a unit.  Immediate ids: with a register id
+// ptxas reserves all 16 barriers of the SM for the CTA and nothing else could share the SM.
+__device__ __forceinline__ void pair_barrier(int unit_local) {
+    if (kUnitsPerCta > 4 && unit_local >= 4) {
+        switch (unit_local) {
+            case 4: asm volatile("bar.sync 5, 64;" ::: "memory"); break;
+            case 5: asm volatile("bar.sync 6, 64;" ::: "memory"); break;
+            case 6: asm volatile("bar.sync 7, 64;" ::: "memory"); break;
+            default: asm volatile("bar.sync 8, 64;" ::: "memory"); break;
+        }
+        return;
+    }
+    switch (unit_local) {
+        case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+        case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    }
+}
+
 // D[tmem] (+)= A[tmem] . B[smem]^T
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
     asm volatile(
@@ -114,7 +140,7 @@ __device__ __forceinline__ uint64_t b_descriptor(uint32_t smem_addr) {
 }
 
 template <int R>
-__global__ void __launch_bounds__(kUmmaThreads, 1)
+__global__ void __launch_bounds__(kUmmaThreads, kCtasPerSm)
 score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_constant__ CUtensorMap tm_halo, const ScoreParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -330,7 +356,7 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
             // the upper half hands its sums to the lower half through one of two slots: the write two
             // frames later comes after the next barrier, which the reader reaches after this read
             if (ROLE == 1) xchg[32 * xslot] = make_float2(s, d);
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + unit_local) : "memory");
+            pair_barrier(unit_local);
             if (ROLE == 0) {
                 const float2 o = xchg[32 * xslot];
                 s += o.x;
@@ -433,6 +459,8 @@ int launch_umma(const ScoreParams& p, const CUtensorMap& tm_clip, const CUtensor
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(score_umma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem);
         if (e != cudaSuccess) return cuda_fail(e);
+        // no carve-out preference: a kernel that forces its own L1 / shared split cannot overlap with the
+        // shrink / stretch kernels of the other stream (measured: pipelined step 1.32 instead of 1.07 ms)
         configured = true;
     }
     const int ctas_per_chunk = (p.By * p.tiles_x + kUnitsPerCta - 1) / kUnitsPerCta;
@@ -442,6 +470,9 @@ int launch_umma(const ScoreParams& p, const CUtensorMap& tm_clip, const CUtensor
 }
 
 }  // namespace
+
+int score_umma_units_per_cta() { return kUnitsPerCta; }
+int score_umma_ctas_per_sm() { return kCtasPerSm; }
 
 // Returns ELVIS_ERR_UNSUPPORTED when the driver cannot encode tensor maps (the caller then uses
 // the CUDA-core kernel).  Plane, strides and halo must be 16-byte aligned.
