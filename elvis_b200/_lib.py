@@ -28,7 +28,7 @@ class ElvisError(RuntimeError):
         super().__init__(f"{fn} failed: {detail} (code {code})")
 
 
-_vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+_vp, _i32, _i64, _f64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_float
 _PP = C.POINTER(Plane)
 
 # name -> argtypes; every entry point returns int.  Kept in the order of the header.
@@ -64,6 +64,10 @@ SIGNATURES = {
     "elvis_resize_area_f32": [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
     "elvis_roi_svtav1_offsets": [_vp, _i64, _i32, _i32, _vp, _vp],
     "elvis_rgb_to_i420": [_PP, _PP, _PP, _PP, _i32, _vp],
+    "elvis_area_downscale": [_PP, _PP, _i32, _i32, _vp],
+    "elvis_merge_blocks": [_PP, _PP, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
+    "elvis_levels_to_gray": [_vp, _i64, _i32, _i32, _vp, _vp],
+    "elvis_gray_to_levels": [_vp, _i64, _f32, _f32, _vp, _vp],
 }
 EXPORTS = ["elvis_abi_version", "elvis_error_string", "elvis_last_cuda_error", *SIGNATURES]
 

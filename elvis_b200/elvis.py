@@ -223,6 +223,56 @@ def write_per_block_qpfile(removability_scores: np.ndarray, block_size: int, wid
             f.write(" ".join(parts) + "\n")
 
 
+# ---------------------------------------------------------------- adaptive pyramid reconstruction (8f rank 4)
+def upscale_realesrgan_adaptive(downsampled_image: np.ndarray, downscale_maps: np.ndarray, block_size: int,
+                                realesrgan_dir: str = None, *, upsample_fn=None) -> np.ndarray:
+    """elvis.py:2522-2600.  The 2x upsampler is external (Real-ESRGAN in the reference): pass it as
+    `upsample_fn` (image -> image of twice the size).  The pyramid around it -- INTER_AREA downscales of
+    the input and the per-block restore of every stage -- runs on the GPU."""
+    if upsample_fn is None:
+        raise NotImplementedError("the Real-ESRGAN 2x upsampler is external to elvis_b200: pass upsample_fn")
+    factors = np.power(2, np.asarray(downscale_maps)).astype(np.int32)
+    max_factor = int(factors.max())
+    height, width, _ = downsampled_image.shape
+    if height % block_size or width % block_size:
+        raise ValueError("Image dimensions must be divisible by block_size.")
+    original = _packed_clip(downsampled_image)
+    fac = _to_dev(factors)[None]
+    current = ops.area_downscale(original, max_factor)[0].cpu().numpy() if max_factor > 1 else downsampled_image
+    current_factor = max_factor // 2
+    while current_factor >= 1:
+        current = np.ascontiguousarray(upsample_fn(current))
+        bs_now = block_size // current_factor
+        if current.shape[0] % bs_now or current.shape[1] % bs_now:
+            raise ValueError("Image dimensions must be divisible by block_size.")
+        cur = _packed_clip(current)
+        down = ops.area_downscale(original, current_factor) if current_factor > 1 else original
+        if down.shape != cur.shape:
+            raise ValueError("upsample_fn must double the image size")
+        # blocks downsampled by <= the stage's factor come back from the (downscaled) input;
+        # the others keep the upsampler's output and count as `current_factor` from now on
+        current = ops.merge_blocks_(cur, down, fac, current_factor, bs_now)[0].cpu().numpy()
+        fac = torch.clamp(fac, max=current_factor)
+        current_factor //= 2
+    return current
+
+
+def strength_maps_to_gray(strength_maps: np.ndarray) -> np.ndarray:
+    """The normalisation of encode_strength_maps (elvis.py:2200-2202): maps -> uint8 frames for the
+    gray map video (PNG writing and the encode are external)."""
+    maps = np.asarray(strength_maps)
+    lo, hi = int(maps.min()), int(maps.max())
+    if hi == lo:
+        raise ValueError("constant strength maps cannot be normalised (the reference divides by zero)")
+    return ops.levels_to_gray(_to_dev(maps, np.int32), lo, hi).cpu().numpy()
+
+
+def gray_to_strength_maps(gray_frames: np.ndarray, min_val: float, max_val: float) -> np.ndarray:
+    """The reconstruction of decode_strength_maps (elvis.py:2238-2243): decoded gray frames -> uint8
+    maps; (min_val, max_val) = (0, 10) for blur rounds, (0, log2(block_size)) for downsample levels."""
+    return ops.gray_to_levels(_to_dev(np.asarray(gray_frames), np.uint8), min_val, max_val).cpu().numpy()
+
+
 # ---------------------------------------------------------------- side channels
 def encode_strength_maps_to_npz(strength_maps: np.ndarray, output_path: str) -> None:
     """elvis.py:2247-2259 (uint8 maps, np.savez_compressed key `strength_maps`)."""

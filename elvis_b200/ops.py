@@ -571,3 +571,56 @@ def rgb_to_i420(frames: torch.Tensor, out: torch.Tensor | None = None) -> torch.
     planes = [plane_of(frames, "frames"), plane_of(y, "y"), plane_of(u, "u"), plane_of(v, "v")]
     call("elvis_rgb_to_i420", *[C.byref(p) for p in planes], T, _stream())
     return out
+
+
+# ---------------------------------------------------------------- pyramid pieces, level-map gray codec (8f rank 4)
+def area_downscale(clip: torch.Tensor, factor: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """cv2.resize(frame, (W // factor, H // factor), INTER_AREA) of every uint8 frame of (T, H, W[, C])
+    for an integer factor that divides H and W."""
+    T, H, W = clip.shape[:3]
+    if factor <= 0 or H % factor or W % factor:
+        raise ValueError("factor must divide the frame dimensions")
+    shape = (T, H // factor, W // factor) + tuple(clip.shape[3:])
+    if out is None:
+        out = torch.empty(shape, dtype=torch.uint8, device=clip.device)
+    elif tuple(out.shape) != shape:
+        raise ValueError(f"out must be {shape}")
+    if out.numel():
+        src, dst = plane_of(clip), plane_of(out, "out")
+        call("elvis_area_downscale", C.byref(src), C.byref(dst), T, int(factor), _stream())
+    return out
+
+
+def merge_blocks_(dst: torch.Tensor, src: torch.Tensor, factors: torch.Tensor, threshold: int, block_px: int) -> torch.Tensor:
+    """In place: dst block <- src block wherever factors (T, By, Bx) int32 <= threshold."""
+    _check_cuda(factors, torch.int32, "factors")
+    factors = factors.contiguous()
+    T, by, bx = factors.shape
+    if dst.shape != src.shape or dst.shape[0] != T:
+        raise ValueError("dst, src and factors disagree")
+    if dst.shape[1] != by * block_px or dst.shape[2] != bx * block_px:
+        raise ValueError("Image dimensions must be divisible by block_size.")
+    if dst.numel():
+        s, d = plane_of(src, "src"), plane_of(dst, "dst")
+        call("elvis_merge_blocks", C.byref(s), C.byref(d), T, int(block_px), by, bx, _ptr(factors), int(threshold), _stream())
+    return dst
+
+
+def levels_to_gray(maps: torch.Tensor, min_value: int, max_value: int) -> torch.Tensor:
+    """int32 level maps -> uint8 gray frames, elvis.py:2200-2202."""
+    _check_cuda(maps, torch.int32, "maps")
+    maps = maps.contiguous()
+    out = torch.empty(maps.shape, dtype=torch.uint8, device=maps.device)
+    if out.numel():
+        call("elvis_levels_to_gray", _ptr(maps), maps.numel(), int(min_value), int(max_value), _ptr(out), _stream())
+    return out
+
+
+def gray_to_levels(gray: torch.Tensor, min_value: float, max_value: float) -> torch.Tensor:
+    """uint8 gray frames -> uint8 level maps, elvis.py:2238-2240."""
+    _check_cuda(gray, torch.uint8, "gray")
+    gray = gray.contiguous()
+    out = torch.empty(gray.shape, dtype=torch.uint8, device=gray.device)
+    if out.numel():
+        call("elvis_gray_to_levels", _ptr(gray), gray.numel(), float(min_value), float(max_value), _ptr(out), _stream())
+    return out

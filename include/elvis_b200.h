@@ -289,6 +289,27 @@ ELVIS_API int elvis_roi_svtav1_offsets(const float* resized, int64_t n, int32_t 
 ELVIS_API int elvis_rgb_to_i420(const elvis_plane* rgb, const elvis_plane* y, const elvis_plane* u, const elvis_plane* v,
                       int32_t n_frames, elvis_stream_t stream);
 
+/* ---- 8f rank 4: the deterministic parts either side of the external neural restorer. */
+
+/* cv2.resize(frame, (w / factor, h / factor), INTER_AREA) for uint8 frames and an integer factor
+ * (the pyramid of upscale_realesrgan_adaptive, elvis.py:2567, 2583): factor 2 -> (a+b+c+d+2)>>2,
+ * larger -> round-half-even(sum * float32(1 / factor^2)).  dst gives the output size. */
+ELVIS_API int elvis_area_downscale(const elvis_plane* src, const elvis_plane* dst, int32_t n_frames, int32_t factor,
+                         elvis_stream_t stream);
+
+/* The per-block restore of one pyramid stage (elvis.py:2586-2591): dst block (j, i) <- src block
+ * (j, i) where factors[t][j][i] <= threshold; other blocks of dst are left as they are. */
+ELVIS_API int elvis_merge_blocks(const elvis_plane* src, const elvis_plane* dst, int32_t n_frames, int32_t block_px, int32_t by,
+                       int32_t bx, const int32_t* factors, int32_t threshold, elvis_stream_t stream);
+
+/* Level maps <-> the 8-bit gray frames of the map video (elvis.py:2200-2202 and 2238-2240; the
+ * video encode / decode is external): gray = uint8((m - min) / (max - min) * 255.0) in float64;
+ * level = uint8(round_half_even(float32(g) / 255 * (max - min) + min)) in float32. */
+ELVIS_API int elvis_levels_to_gray(const int32_t* maps, int64_t n, int32_t min_value, int32_t max_value, uint8_t* gray,
+                         elvis_stream_t stream);
+ELVIS_API int elvis_gray_to_levels(const uint8_t* gray, int64_t n, float min_value, float max_value, uint8_t* levels,
+                         elvis_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

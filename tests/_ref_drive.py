@@ -80,3 +80,24 @@ def reference_qpfile(E, scores, block_size, width, height, workdir):
     finally:
         E.encode_video = real
     return captured["text"]
+
+
+def reference_map_video_arithmetic(E, strength_maps, kind, block_size, workdir):
+    """Runs the reference's encode_strength_maps / decode_strength_maps (elvis.py:2198-2245) with the
+    external video encode / decode replaced by nothing: returns (the uint8 frames it would encode,
+    the maps it reconstructs from exactly those frames)."""
+    import os
+    import cv2
+    video = os.path.join(workdir, f"maps_{kind}.mp4")      # decode keys its range off the file name
+    real_enc, real_dec = E.encode_video, E.decode_video
+    E.encode_video = lambda **kw: None
+    E.decode_video = lambda *a, **kw: None
+    try:
+        E.encode_strength_maps(strength_maps, video, 30.0)
+        frames_dir = os.path.splitext(video)[0]
+        files = sorted(f for f in os.listdir(frames_dir) if f.endswith(".png"))
+        gray = np.stack([cv2.imread(os.path.join(frames_dir, f), cv2.IMREAD_GRAYSCALE) for f in files])
+        decoded = E.decode_strength_maps(video, block_size, frames_dir)
+    finally:
+        E.encode_video, E.decode_video = real_enc, real_dec
+    return gray, decoded

@@ -317,6 +317,42 @@ def test_rgb_to_i420_strided_and_resize_area_shapes(dev):
         ops.resize_area_f32(torch.zeros((1, 4, 4), dtype=torch.float32, device=dev), 8, 4)
 
 
+def test_pyramid_reconstruction_and_map_video(dev):
+    """8f rank 4 (elvis.py:2522-2600, 2198-2245) through the mirrors, against the oracle port."""
+    import cv2
+    from elvis_b200 import elvis as E, ops
+    rng = np.random.default_rng(23)
+
+    def up_cubic(im):
+        return cv2.resize(im, None, fx=2, fy=2, interpolation=cv2.INTER_CUBIC)
+
+    def up_repeat(im):
+        return np.ascontiguousarray(im.repeat(2, 0).repeat(2, 1))
+
+    for (H, W, bs, top) in [(64, 96, 16, 4), (64, 96, 16, 2), (48, 80, 8, 3), (64, 64, 32, 5), (32, 48, 16, 0), (272, 480, 16, 3)]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        maps = rng.integers(0, top + 1, (H // bs, W // bs))
+        maps.flat[0] = top
+        for up in (up_cubic, up_repeat):
+            got = E.upscale_realesrgan_adaptive(img, maps.copy(), bs, upsample_fn=up)
+            assert np.array_equal(got, P.upscale_realesrgan_adaptive(img, maps.copy(), bs, up)), (H, W, bs, top)
+    with pytest.raises(NotImplementedError):
+        E.upscale_realesrgan_adaptive(img, maps, 16)
+    for f in (1, 2, 4, 8, 16):
+        clip = rng.integers(0, 256, (2, 64, 96, 3), dtype=np.uint8)
+        got = ops.area_downscale(to_dev(clip, dev), f).cpu().numpy()
+        for t in range(2):
+            assert np.array_equal(got[t], P.area_downscale(clip[t], f)), f
+    for hi, rng_max in ((10, 10.0), (4, 4), (3, 3)):
+        m = rng.integers(0, hi + 1, (3, 17, 30)).astype(np.int32)
+        m.flat[:2] = [0, hi]
+        gray = E.strength_maps_to_gray(m)
+        assert gray.dtype == np.uint8 and np.array_equal(gray, P.strength_maps_to_gray(m))
+        assert np.array_equal(E.gray_to_strength_maps(gray, 0.0, rng_max), m)
+        noisy = rng.integers(0, 256, gray.shape, dtype=np.uint8)          # what a lossy codec hands back
+        assert np.array_equal(E.gray_to_strength_maps(noisy, 0.0, rng_max), P.gray_to_strength_maps(noisy, 0.0, rng_max))
+
+
 def test_planar_pipeline_matches_per_plane_oracle(dev):
     """Planar YUV 4:2:0: mask from luma scores, applied to chroma at half block size."""
     from elvis_b200.pipeline import ElvisV1, Yuv420

@@ -152,6 +152,37 @@ def test_port_matches_reference_roi_files(tmp_path):
         assert reference_qpfile(E, scores, bs, w, h, str(tmp_path / "ref")) == (tmp_path / "q.txt").read_text(), (w, h, bs)
 
 
+def _up2_cubic(im):
+    return cv2.resize(im, None, fx=2, fy=2, interpolation=cv2.INTER_CUBIC)
+
+
+def _up2_repeat(im):
+    return np.ascontiguousarray(im.repeat(2, 0).repeat(2, 1))
+
+
+@needs_reference
+def test_port_matches_reference_pyramid_and_map_video(tmp_path):
+    """8f rank 4: upscale_realesrgan_adaptive with a deterministic 2x upsampler standing in for the
+    external one (elvis.py:2522-2600), and the arithmetic of the map video (elvis.py:2198-2245)."""
+    from _ref_drive import reference_map_video_arithmetic
+    E = ref_import.load("elvis")
+    rng = np.random.default_rng(13)
+    for (H, W, bs, top) in [(64, 96, 16, 4), (64, 96, 16, 2), (48, 80, 8, 3), (64, 64, 32, 5), (32, 48, 16, 0)]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        maps = rng.integers(0, top + 1, (H // bs, W // bs))
+        maps.flat[0] = top
+        for up in (_up2_cubic, _up2_repeat):
+            ref = E.upscale_realesrgan_adaptive(img, maps.copy(), bs, upsample_fn=up)
+            assert np.array_equal(ref, P.upscale_realesrgan_adaptive(img, maps.copy(), bs, up)), (H, W, bs, top)
+    for kind, bs, hi in (("gaussian", 16, 10), ("downsample", 16, 4), ("downsample", 8, 3)):
+        m = rng.integers(0, hi + 1, (3, 17, 30)).astype(np.int32)
+        m.flat[:2] = [0, hi]
+        gray, decoded = reference_map_video_arithmetic(E, m, kind, bs, str(tmp_path / f"{kind}{bs}"))
+        assert np.array_equal(gray, P.strength_maps_to_gray(m))
+        assert np.array_equal(decoded, P.gray_to_strength_maps(gray, 0.0, 10.0 if kind == "gaussian" else int(np.log2(bs))))
+        assert np.array_equal(decoded, m)          # lossless when the video codec is
+
+
 @needs_reference
 def test_port_matches_reference_v2_and_scores():
     from _ref_drive import run_reference_removability
