@@ -47,6 +47,28 @@ def test_sc_tc_vs_spec(dev, monkeypatch, impl, bs, H, W, T):
     assert mm.tolist() == [sc.min(), sc.max(), tc.min(), tc.max()]
 
 
+@pytest.mark.parametrize("T", [1, 2, 6, 7, 12, 13, 19])
+def test_sc_tc_tcgen05_frame_loop_boundaries(dev, monkeypatch, T):
+    """The tcgen05 kernel unrolls its frame loop by the ring depth (6) and buffers A x2 / D x3: run
+    lengths around the multiples, with and without a halo (which adds a priming frame), one chunk
+    and several."""
+    from elvis_b200 import ops
+    monkeypatch.setenv("ELVIS_SCORE_IMPL", "umma")
+    y = synth_luma(T + 1, 48, 144, seed=T)
+    yd = to_dev(y, dev)
+    for chunk in ("64", "5"):
+        monkeypatch.setenv("ELVIS_SCORE_CHUNK", chunk)
+        sc, tc, _ = ops.score_sc_tc(yd[1:], 16)
+        rsc, rtc = spec_scoring.sc_tc(y[1:], 16)
+        np.testing.assert_allclose(sc.cpu().numpy(), rsc, rtol=RTOL, atol=0)
+        np.testing.assert_allclose(tc.cpu().numpy(), rtc, rtol=RTOL, atol=0)
+        sch, tch, _ = ops.score_sc_tc(yd[1:], 16, prev_halo=yd[0])
+        rsc_h, rtc_h = spec_scoring.sc_tc(y[1:], 16, prev=y[0])
+        np.testing.assert_allclose(sch.cpu().numpy(), rsc_h, rtol=RTOL, atol=0)
+        np.testing.assert_allclose(tch.cpu().numpy(), rtc_h, rtol=RTOL, atol=0)
+        assert np.array_equal(sch.cpu().numpy(), sc.cpu().numpy())      # SC does not depend on the halo
+
+
 @pytest.mark.parametrize("impl", IMPLS)
 def test_sc_tc_random_noise_and_static(dev, monkeypatch, impl):
     from elvis_b200 import ops

@@ -59,3 +59,35 @@ def test_host_dampen_tile_matches_spec(hostlib):
                                  out.ctypes.data_as(ctypes.c_void_p))
         ref = spec_dct_dampen.dampen_plane(blk, np.array([[s]]), 8, return_float=True)
         np.testing.assert_allclose(out, ref, atol=2e-3)
+
+
+def test_rowcol_dims_match_the_oracle_plan():
+    """Host-side pass structure of the row+column shrink (elvis_b200.ops.rowcol_dims) against the
+    oracle's simulation (sizes and counts depend on the grid and the target only)."""
+    import numpy as np
+    from elvis_b200 import ops
+    from oracle import ref_port as P
+    rng = np.random.default_rng(0)
+    for by, bx, amount in [(4, 6, 0.3), (5, 8, 0.55), (9, 7, 0.85), (1, 8, 0.5), (8, 1, 0.5), (6, 6, 1.0), (6, 6, 0.0), (17, 30, 0.4)]:
+        mask, pmap, passes = P.rowcol_plan(rng.random((by, bx)), amount)
+        fby, fbx, counts = ops.rowcol_dims(by, bx, int(by * bx * amount))
+        assert (fby, fbx) == pmap.shape[:2] and counts == [len(a) for a in passes] and sum(counts) == mask.sum()
+
+
+def test_roi_host_logic_matches_the_oracle():
+    """x265 CTU choice and the cv2 float-area tables built on the host."""
+    import numpy as np
+    from elvis_b200 import _tables as T
+    from elvis_b200 import elvis as E
+    from oracle import ref_port as P
+    from oracle import spec_cv
+    for bs in (4, 8, 16, 32, 64, 128):
+        for (w, h) in ((320, 240), (1920, 1080), (3840, 2160), (2160, 3840), (7680, 4320)):
+            assert E.x265_ctu_size(bs, w, h) == P.x265_ctu_size(bs, w, h)
+    for ssize, dsize in ((240, 60), (135, 34), (67, 17), (13, 5), (9, 9)):
+        start, src, alpha = T.area_f32_tables(ssize, dsize)
+        tab = spec_cv.area_table(ssize, dsize)
+        assert [s for s, _, _ in tab] == src.tolist() and np.array_equal(np.array([a for _, _, a in tab], np.float32), alpha)
+        assert np.bincount([d for _, d, _ in tab], minlength=dsize).cumsum().tolist() == start[1:].tolist()
+    assert T.area_f32_plan(136, 240, 34, 60) == (4, 4, 0) and T.area_f32_plan(16, 24, 8, 12) == (2, 2, 12)
+    assert T.area_f32_plan(135, 240, 34, 60) == (0, 0, 0)
