@@ -11,10 +11,9 @@
 // SC / TC do not depend on how the clip is chunked.
 //
 // Roles.  A CTA is one group of 128 tiles (ELVIS_UMMA_GROUPS = 1: two CTAs share an SM and its 512
-// TMEM columns; 5 % faster than one CTA of two groups, 356 vs 374 us).  Tile m of a group is
-// TMEM lane m; it is served by
-// TWO worker threads (lane m % 32 of warps q and q + 4, q = m / 32 -- both reach lanes 32q..),
-// which walk it through a run of frames:
+// TMEM columns; 5 % faster than one CTA of two groups, 356 vs 374 us).  Tile m of the group is
+// TMEM lane m; it is served by TWO worker threads (lane m % 32 of warps q and q + 4, q = m / 32
+// -- both reach lanes 32q..), which walk it through a run of frames:
 //   * both read half of the tile's 8 luma rows from a shared-memory ring, expand the 32 bytes
 //     to fp16 (PRMT + one HADD2 per pair) and write them straight into the A operand in TENSOR
 //     MEMORY (tcgen05.st) -- A never touches shared memory again, whose bandwidth would
@@ -25,8 +24,9 @@
 //     and a 64-thread named barrier, and that one writes SC and TC.  D is triple buffered, so
 //     the previous frame's coefficients are still in tensor memory and no thread carries
 //     coefficients in registers between frames.
-// Warp 16 issues a group's MMAs (one lane) once its 8 worker warps have published A and
-// commits them to an mbarrier.  Warp 17 runs the TMA ring, one lane per 32-tile unit: one 3-D
+// The warp after the workers issues the group's MMAs (one lane) once its 8 worker warps have
+// published A and commits them to an mbarrier.  The last warp runs the TMA ring, one lane per
+// 32-tile unit: one 3-D
 // box (8R rows x 256/R bytes x 1 frame, R = block_size / 8) per frame, kUmmaRing frames deep,
 // full / empty mbarriers per ring slot.  The frame loop is unrolled by the ring depth so that
 // ring slot, A / D buffer and most mbarrier phases are compile-time constants.
@@ -47,7 +47,7 @@ namespace {
 constexpr int kGroups = ELVIS_UMMA_GROUPS;   // groups of 128 tiles per CTA, each with its own A / D buffers
 constexpr int kCtasPerSm = 2 / kGroups;       // tensor memory holds two groups per SM
 constexpr int kUnitsPerCta = kGroups * 4;     // warp units (32 tiles) per CTA
-constexpr int kWorkerWarps = 2 * kUnitsPerCta;   // an SC warp and a TC warp per unit
+constexpr int kWorkerWarps = 2 * kUnitsPerCta;   // a lower-half and an upper-half warp per unit
 constexpr int kMmaWarp = kWorkerWarps;
 constexpr int kTmaWarp = kWorkerWarps + 1;
 constexpr int kUmmaThreads = (kWorkerWarps + 2) * 32;
