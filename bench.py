@@ -50,8 +50,9 @@ def config_dict(n_gpus, frames=FRAMES):
             "frames_per_gpu": frames, "width": WIDTH, "height": HEIGHT, "block_size": BLOCK,
             "shrink_amount": SHRINK, "sharding": f"contiguous frame ranges x{n_gpus}, 1-frame luma halo",
             "l2": "inputs larger than L2 (1.49 GB clip per GPU vs 126 MB L2); no explicit flush",
-            "pipelining": "2 clips in flight on 2 CUDA streams: scoring of clip i+1 overlaps shrink+stretch of clip i "
-                          "(elvis_b200.pipeline.ElvisV1Pipelined); roofline.serial_step is the un-overlapped figure"}
+            "pipelining": "3 clips in flight on 3 CUDA streams: scoring of clip i+2, shrink of clip i+1 and stretch of clip i "
+                          "overlap (elvis_b200.pipeline.ElvisV1Pipelined, split_stretch); every clip takes the full serial path; "
+                          "roofline.serial_step is the un-overlapped figure"}
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -211,7 +212,8 @@ def run_ours(args):
         score_fn = lambda c, slot: sharding.sharded_removability(halo, T * world, BLOCK, ALPHA, BETA, rank, world,  # noqa: E731
                                                                  exchange=False)
     pp = ElvisV1Pipelined(T, HEIGHT, WIDTH, BLOCK, SHRINK, ALPHA, BETA, dev, depth=args.depth, score_fn=score_fn,
-                          move_ctas_per_sm=args.move_ctas, comm_fn=comm_fn)
+                          move_ctas_per_sm=args.move_ctas, comm_fn=comm_fn, split_stretch=args.split_stretch,
+                          stretch_ctas_per_sm=args.stretch_ctas)
     if args.serial:
         def run(n):
             for _ in range(n):
@@ -339,8 +341,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES, help="frames per GPU (default: the 120 of the headline config)")
     ap.add_argument("--serial", action="store_true", help="time one clip at a time instead of the two-stream pipeline")
-    ap.add_argument("--depth", type=int, default=2, help="clips in flight in the two-stream pipeline")
+    ap.add_argument("--depth", type=int, default=3, help="clips in flight in the stream pipeline")
     ap.add_argument("--move-ctas", type=int, default=3, help="shrink/stretch CTAs per SM while pipelined")
+    ap.add_argument("--no-split-stretch", dest="split_stretch", action="store_false",
+                    help="two pipeline stages (score | shrink+stretch) instead of three (score | shrink | stretch)")
+    ap.add_argument("--stretch-ctas", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -568,8 +568,10 @@ def test_score_tightness(dev, monkeypatch):
         assert e_sc < 2e-5 and e_tc < 2e-5
 
 
-def test_pipelined_equals_serial(dev):
-    """Two clips in flight on two streams must give exactly the serial results."""
+@pytest.mark.parametrize("depth,split", [(2, False), (3, True)])
+def test_pipelined_equals_serial(dev, depth, split):
+    """Clips in flight on two (score | move) or three (score | shrink | stretch) streams must give
+    exactly the serial results."""
     import torch
     from elvis_b200.pipeline import ElvisV1, ElvisV1Pipelined, Yuv420
     T, H, W, bs = 5, 96, 160, 16
@@ -579,7 +581,7 @@ def test_pipelined_equals_serial(dev):
         clips.append(Yuv420(to_dev(y, dev), to_dev(u, dev), to_dev(v, dev)))
     serial = ElvisV1(bs, 0.5, 0.5, 0.5)
     ref = [serial.run(c) for c in clips]
-    pp = ElvisV1Pipelined(T, H, W, bs, 0.5, 0.5, 0.5, dev, depth=2)
+    pp = ElvisV1Pipelined(T, H, W, bs, 0.5, 0.5, 0.5, dev, depth=depth, split_stretch=split)
     for i, c in enumerate(clips):
         slot = pp.submit(c)
         slot["done"].synchronize()      # read the slot before it is reused
