@@ -50,9 +50,11 @@ def config_dict(n_gpus, frames=FRAMES):
             "frames_per_gpu": frames, "width": WIDTH, "height": HEIGHT, "block_size": BLOCK,
             "shrink_amount": SHRINK, "sharding": f"contiguous frame ranges x{n_gpus}, 1-frame luma halo",
             "l2": "inputs larger than L2 (1.49 GB clip per GPU vs 126 MB L2); no explicit flush",
-            "pipelining": "3 clips in flight on 3 CUDA streams: scoring of clip i+2, shrink of clip i+1 and stretch of clip i "
-                          "overlap (elvis_b200.pipeline.ElvisV1Pipelined, split_stretch); every clip takes the full serial path; "
-                          "roofline.serial_step is the un-overlapped figure"}
+            "pipelining": ("3 clips in flight on 3 CUDA streams: scoring of clip i+2, shrink of clip i+1 and stretch of clip i overlap"
+                           if n_gpus == 1 else
+                           "2 clips in flight on 2 CUDA streams (+1 for NCCL): scoring of clip i+1 overlaps shrink+stretch of clip i")
+                          + " (elvis_b200.pipeline.ElvisV1Pipelined); every clip takes the full serial path; "
+                            "roofline.serial_step is the un-overlapped figure"}
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -211,8 +213,12 @@ def run_ours(args):
         comm_fn = lambda c: sharding.exchange_halo(halo, rank, world)  # noqa: E731
         score_fn = lambda c, slot: sharding.sharded_removability(halo, T * world, BLOCK, ALPHA, BETA, rank, world,  # noqa: E731
                                                                  exchange=False)
-    pp = ElvisV1Pipelined(T, HEIGHT, WIDTH, BLOCK, SHRINK, ALPHA, BETA, dev, depth=args.depth, score_fn=score_fn,
-                          move_ctas_per_sm=args.move_ctas, comm_fn=comm_fn, split_stretch=args.split_stretch,
+    # one GPU: three stages, three clips in flight (1.01 ms per clip; two stages: 1.07).  Sharded: two stages,
+    # two clips (measured at N=2: 1.09 ms; three stages 1.11-1.35 ms -- the NCCL kernels wait for SM slots)
+    split = (world == 1) if args.split_stretch is None else args.split_stretch
+    depth = (3 if split else 2) if args.depth is None else args.depth
+    pp = ElvisV1Pipelined(T, HEIGHT, WIDTH, BLOCK, SHRINK, ALPHA, BETA, dev, depth=depth, score_fn=score_fn,
+                          move_ctas_per_sm=args.move_ctas, comm_fn=comm_fn, split_stretch=split,
                           stretch_ctas_per_sm=args.stretch_ctas)
     if args.serial:
         def run(n):
@@ -341,10 +347,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES, help="frames per GPU (default: the 120 of the headline config)")
     ap.add_argument("--serial", action="store_true", help="time one clip at a time instead of the two-stream pipeline")
-    ap.add_argument("--depth", type=int, default=3, help="clips in flight in the stream pipeline")
+    ap.add_argument("--depth", type=int, default=None, help="clips in flight in the stream pipeline (default: 3 on one GPU, 2 when sharded)")
     ap.add_argument("--move-ctas", type=int, default=3, help="shrink/stretch CTAs per SM while pipelined")
+    ap.add_argument("--split-stretch", dest="split_stretch", action="store_true", default=None,
+                    help="three pipeline stages (score | shrink | stretch); default on one GPU")
     ap.add_argument("--no-split-stretch", dest="split_stretch", action="store_false",
-                    help="two pipeline stages (score | shrink+stretch) instead of three (score | shrink | stretch)")
+                    help="two pipeline stages (score | shrink+stretch); default when sharded: the NCCL kernels of the "
+                         "halo exchange and the all-reduces need SM slots that three resident kernels do not leave")
     ap.add_argument("--stretch-ctas", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
