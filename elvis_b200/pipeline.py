@@ -7,6 +7,8 @@ removal mask / level map computed from luma is applied to the co-located chroma 
 half the block size (SURVEY.md appendix "Layout")."""
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -131,11 +133,12 @@ class ElvisV1Pipelined:
         sw = (bx - self.k) * block_size
         # the move stage gets the higher stream priority: its short, register-light CTAs are placed
         # into the resources the long-running scoring CTAs leave free instead of queueing behind them
-        self.s_score = torch.cuda.Stream(self.dev, priority=0)
-        self.s_move = torch.cuda.Stream(self.dev, priority=-1)
+        prio = [int(x) for x in os.environ.get("ELVIS_PIPE_PRIO", "0,-1,-1").split(",")]
+        self.s_score = torch.cuda.Stream(self.dev, priority=prio[0])
+        self.s_move = torch.cuda.Stream(self.dev, priority=prio[1])
         # optional third stage: stretch on its own stream, so that the stretch of clip i overlaps
         # the shrink of clip i+1 as well (neither saturates DRAM alone)
-        self.s_stretch = torch.cuda.Stream(self.dev, priority=-1) if split_stretch else None
+        self.s_stretch = torch.cuda.Stream(self.dev, priority=prio[2]) if split_stretch else None
         self.stretch_ctas = move_ctas_per_sm if stretch_ctas_per_sm is None else stretch_ctas_per_sm
         self.score_fn = score_fn      # optional: clip, slot -> scores (e.g. the sharded scorer)
         # optional: clip -> None, communication the scorer depends on (the halo exchange of the
