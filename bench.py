@@ -158,6 +158,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL's internal streams at high priority: its small kernels (halo send/recv, 16-byte all-reduces) then
+        # take the first SM slot that frees up instead of queueing behind the move kernels (N=2: 1.088 -> 1.080 ms)
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=dev)
     T = args.frames
     pipe = ElvisV1(BLOCK, SHRINK, ALPHA, BETA)
