@@ -13,7 +13,7 @@ OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_SHAPE = 0, -1, -2, -3, -4
 F32, F64 = 0, 1
 REMOVE_HIGH, REMOVE_LOW = 0, 1
 LEVELS_ROUND, LEVELS_INVERTED_ROUND, LEVELS_INVERTED_BINS = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Plane(C.Structure):

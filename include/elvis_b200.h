@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ELVIS_B200_ABI_VERSION 2
+#define ELVIS_B200_ABI_VERSION 3
 
 #define ELVIS_OK               0
 #define ELVIS_ERR_INVALID_ARG (-1)   /* NULL pointer, non-positive size, out-of-range parameter   */
