@@ -80,7 +80,10 @@ ELVIS_API int         elvis_last_cuda_error(void);
  * By = height / bs, Bx = width / bs.  prev_halo: one luma frame (same row_stride) that
  * precedes frame 0, or NULL (then TC[0] = 0).  block_size in {8, 16, 32}; dct_size must be
  * 8.  sc, tc: float32 (T, By, Bx).  minmax: NULL or 4 floats {sc_min, sc_max, tc_min,
- * tc_max} over frames [mm_begin, mm_end) -- overwritten, not accumulated. */
+ * tc_max} over frames [mm_begin, mm_end) -- overwritten, not accumulated.
+ * Two kernels sit behind this entry point: the tcgen05 / TMA kernel (plane, strides and halo
+ * 16-byte aligned, clip large enough to fill the GPU) and a CUDA-core kernel (anything else);
+ * both meet the same tolerance against the spec.  ELVIS_SCORE_IMPL=umma|simt forces one. */
 ELVIS_API int elvis_score_sc_tc(const elvis_plane* y, int32_t n_frames, const uint8_t* prev_halo,
                       int32_t block_size, int32_t dct_size, float* sc, float* tc,
                       float* minmax, int32_t mm_begin, int32_t mm_end, elvis_stream_t stream);
