@@ -130,6 +130,20 @@ def main():
         g["f3_qpfile_4k"] = np.frombuffer(reference_qpfile(E, qs[:1, :, :60].repeat(4, 1).repeat(4, 2)[:, :135, :240].copy(), 16, 3840, 2160,
                                                            os.path.join(td, "q4")).encode(), np.uint8)
 
+    # 8f rank 4 -- pyramid reconstruction with a deterministic 2x upsampler (pixel repetition) standing in for
+    # the external one, and the arithmetic of the level-map video
+    from _ref_drive import reference_map_video_arithmetic
+    pimg = rng.integers(0, 256, (64, 96, 3), dtype=np.uint8)
+    pmaps = rng.integers(0, 5, (4, 6))
+    pmaps.flat[0] = 4
+    g.update(f4_img=pimg, f4_maps=pmaps)
+    g["f4_out"] = E.upscale_realesrgan_adaptive(pimg, pmaps.copy(), 16, upsample_fn=lambda im: np.ascontiguousarray(im.repeat(2, 0).repeat(2, 1)))
+    with tempfile.TemporaryDirectory() as td:
+        lv = rng.integers(0, 11, (2, 17, 30)).astype(np.int32)
+        lv.flat[:2] = [0, 10]
+        g["f4_levels"] = lv
+        g["f4_gray"], g["f4_decoded"] = reference_map_video_arithmetic(E, lv, "gaussian", 16, td)
+
     out = os.path.join(HERE, "reference_vectors.npz")
     np.savez_compressed(out, **g)
     print(f"wrote {out}: {len(g)} arrays, {os.path.getsize(out) / 1024:.1f} KiB")

@@ -92,6 +92,16 @@ def _check_all(impl):
         impl.write_per_block_qpfile(s4k, 16, 3840, 2160, path)
         assert open(path, "rb").read() == G["f3_qpfile_4k"].tobytes()
 
+    up2 = lambda im: np.ascontiguousarray(im.repeat(2, 0).repeat(2, 1))      # noqa: E731
+    if impl.kind == "gpu":
+        got = impl.upscale_realesrgan_adaptive(G["f4_img"], G["f4_maps"].copy(), 16, upsample_fn=up2)
+    else:
+        got = impl.upscale_realesrgan_adaptive(G["f4_img"], G["f4_maps"].copy(), 16, up2)
+    assert np.array_equal(got, G["f4_out"])
+    gray = impl.strength_maps_to_gray(G["f4_levels"])
+    assert gray.dtype == np.uint8 and np.array_equal(gray, G["f4_gray"])
+    assert np.array_equal(impl.gray_to_strength_maps(G["f4_gray"], 0.0, 10.0), G["f4_decoded"])
+
     assert np.array_equal(impl.restore_blur_opencv_unsharp_mask(G["f1_img"], G["f1_map"], 16), G["f1_out"])
     for tag, halo, tb in (("h0", 0, 0.0), ("h6b", 6, 0.2)):
         got = impl.restore_with_opencv_unsharp(list(G["f1_frames"]), G["f1_maps"], 16, halo=halo, temporal_blend=tb)
