@@ -68,6 +68,7 @@ SIGNATURES = {
     "elvis_merge_blocks": [_PP, _PP, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
     "elvis_levels_to_gray": [_vp, _i64, _i32, _i32, _vp, _vp],
     "elvis_gray_to_levels": [_vp, _i64, _f32, _f32, _vp, _vp],
+    "elvis_resize_nearest": [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp],
 }
 EXPORTS = ["elvis_abi_version", "elvis_error_string", "elvis_last_cuda_error", *SIGNATURES]
 

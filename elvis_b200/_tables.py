@@ -211,3 +211,11 @@ def area_f32_plan(sh: int, sw: int, dh: int, dw: int):
     if abs(sx - ix) < eps and abs(sy - iy) < eps:
         return ix, iy, (dw // 4) * 4 if (ix == 2 and iy == 2) else 0
     return 0, 0, 0
+
+
+@lru_cache(maxsize=64)
+def nearest_index(ssize: int, dsize: int) -> np.ndarray:
+    """Source index per destination index of cv2.resize(INTER_NEAREST): cv2 multiplies by
+    1 / (dsize / ssize), not by ssize / dsize -- the two differ in the last bit for some ratios."""
+    ifx = 1.0 / (dsize / ssize)
+    return np.minimum(np.floor(np.arange(dsize) * ifx).astype(np.int64), ssize - 1).astype(np.int32)

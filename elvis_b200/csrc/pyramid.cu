@@ -79,6 +79,20 @@ __global__ void __launch_bounds__(256) gray_to_levels_kernel(const uint8_t* __re
     }
 }
 
+// cv2.resize(map, INTER_NEAREST) of block-level maps: element (dy, dx) <- src(y_idx[dy], x_idx[dx]);
+// the index tables hold cv2's min(floor(d * (1 / (dsize / ssize))), ssize - 1)
+template <typename E>
+__global__ void __launch_bounds__(256) nearest_kernel(const E* __restrict__ src, int T, int sh, int sw, E* __restrict__ dst, int dh,
+                                                      int dw, const int32_t* __restrict__ y_idx, const int32_t* __restrict__ x_idx) {
+    const int64_t total = (int64_t)T * dh * dw;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int dx = (int)(i % dw);
+        const int dy = (int)((i / dw) % dh);
+        const int64_t t = i / ((int64_t)dw * dh);
+        dst[i] = src[(t * sh + y_idx[dy]) * sw + x_idx[dx]];
+    }
+}
+
 unsigned grid_of(int64_t n) {
     int64_t g = (n + 255) / 256;
     const int64_t cap = (int64_t)kNumSMs * 16;
@@ -151,6 +165,23 @@ extern "C" int elvis_gray_to_levels(const uint8_t* gray, int64_t n, float min_va
                                     elvis_stream_t stream) {
     if (!gray || !levels || n <= 0) return ELVIS_ERR_INVALID_ARG;
     gray_to_levels_kernel<<<grid_of(n), 256, 0, as_stream(stream)>>>(gray, n, min_value, max_value - min_value, levels);
+    ELVIS_CHECK_LAUNCH();
+    return ELVIS_OK;
+}
+
+extern "C" int elvis_resize_nearest(const void* src, int32_t elem_bytes, int32_t n_maps, int32_t src_h, int32_t src_w, void* dst,
+                                    int32_t dst_h, int32_t dst_w, const int32_t* y_idx, const int32_t* x_idx, elvis_stream_t stream) {
+    if (!src || !dst || !y_idx || !x_idx || n_maps <= 0 || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0) return ELVIS_ERR_INVALID_ARG;
+    const unsigned grid = grid_of((int64_t)n_maps * dst_h * dst_w);
+    cudaStream_t st = as_stream(stream);
+    if (elem_bytes == 1)
+        nearest_kernel<uint8_t><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(src), n_maps, src_h, src_w, static_cast<uint8_t*>(dst), dst_h, dst_w, y_idx, x_idx);
+    else if (elem_bytes == 4)
+        nearest_kernel<uint32_t><<<grid, 256, 0, st>>>(static_cast<const uint32_t*>(src), n_maps, src_h, src_w, static_cast<uint32_t*>(dst), dst_h, dst_w, y_idx, x_idx);
+    else if (elem_bytes == 8)
+        nearest_kernel<uint64_t><<<grid, 256, 0, st>>>(static_cast<const uint64_t*>(src), n_maps, src_h, src_w, static_cast<uint64_t*>(dst), dst_h, dst_w, y_idx, x_idx);
+    else
+        return ELVIS_ERR_UNSUPPORTED;
     ELVIS_CHECK_LAUNCH();
     return ELVIS_OK;
 }

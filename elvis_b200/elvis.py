@@ -83,8 +83,9 @@ def calculate_removability_scores(raw_video_file: str, reference_frames_folder: 
         for i in range(frame_count):
             path = os.path.join(masks_dir, f"{i + 1:05d}.png")
             if os.path.exists(path):
-                m = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
-                bg[i] = cv2.resize(m, (bx, by), interpolation=cv2.INTER_NEAREST) == 0   # elvis.py:1189-1193
+                m = cv2.imread(path, cv2.IMREAD_GRAYSCALE)      # file IO; the resize runs on the GPU
+                small = ops.resize_nearest(_to_dev(m, np.uint8)[None], by, bx)           # elvis.py:1189-1193
+                bg[i] = (small[0] == 0).cpu().numpy()
         background = _to_dev(bg)
     return removability_from_luma(y, block_size, alpha, smoothing_beta, background).cpu().numpy()
 

@@ -624,3 +624,21 @@ def gray_to_levels(gray: torch.Tensor, min_value: float, max_value: float) -> to
     if out.numel():
         call("elvis_gray_to_levels", _ptr(gray), gray.numel(), float(min_value), float(max_value), _ptr(out), _stream())
     return out
+
+
+def resize_nearest(maps: torch.Tensor, dst_h: int, dst_w: int) -> torch.Tensor:
+    """cv2.resize(map, (dst_w, dst_h), INTER_NEAREST) for every map of a dense (T, h, w) tensor with
+    1-, 4- or 8-byte elements."""
+    if not maps.is_cuda:
+        raise TypeError("maps must be a CUDA tensor (elvis_b200 has no CPU path)")
+    if maps.dim() != 3:
+        raise ValueError("maps must be (T, h, w)")
+    maps = maps.contiguous()
+    T, sh, sw = maps.shape
+    out = torch.empty((T, dst_h, dst_w), dtype=maps.dtype, device=maps.device)
+    if out.numel() == 0:
+        return out
+    yi = torch.from_numpy(_tables.nearest_index(sh, dst_h)).to(maps.device)
+    xi = torch.from_numpy(_tables.nearest_index(sw, dst_w)).to(maps.device)
+    call("elvis_resize_nearest", _ptr(maps), maps.element_size(), T, sh, sw, _ptr(out), dst_h, dst_w, _ptr(yi), _ptr(xi), _stream())
+    return out

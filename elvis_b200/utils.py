@@ -181,9 +181,8 @@ def restore_with_opencv_unsharp(frames: List[np.ndarray], degradation_maps: np.n
     maps = np.zeros((len(frames), by, bx), np.int32)
     for i in range(min(len(frames), len(degradation_maps))):
         m = np.asarray(degradation_maps[i])
-        if m.shape != (by, bx):      # utils.py:1343-1345 (host-side nearest resize of the map)
-            import cv2
-            m = cv2.resize(m.astype(np.float32), (bx, by), interpolation=cv2.INTER_NEAREST).astype(np.int32)
+        if m.shape != (by, bx):      # utils.py:1343-1345: nearest resize of the map, via float32 as the reference does
+            m = ops.resize_nearest(_to_dev(m.astype(np.float32))[None], by, bx)[0].cpu().numpy().astype(np.int32)
         maps[i] = m
     out = ops.restore_unsharp(clip, _to_dev(maps), block_size, halo=halo, max_level=max(1, int(maps.max())))
     if temporal_blend > 0:

@@ -313,6 +313,13 @@ ELVIS_API int elvis_levels_to_gray(const int32_t* maps, int64_t n, int32_t min_v
 ELVIS_API int elvis_gray_to_levels(const uint8_t* gray, int64_t n, float min_value, float max_value, uint8_t* levels,
                          elvis_stream_t stream);
 
+/* cv2.resize(map, (dst_w, dst_h), INTER_NEAREST) of n_maps dense block-level maps with 1-, 4- or 8-byte
+ * elements (masks, level maps, scores whose grid differs from the frame's: elvis.py:1189-1193,
+ * utils.py:1291-1296).  y_idx / x_idx: cv2's source index per destination row / column,
+ * min(floor(d * (1.0 / (dsize / ssize))), ssize - 1) in double (elvis_b200/_tables.py:nearest_index). */
+ELVIS_API int elvis_resize_nearest(const void* src, int32_t elem_bytes, int32_t n_maps, int32_t src_h, int32_t src_w, void* dst,
+                         int32_t dst_h, int32_t dst_w, const int32_t* y_idx, const int32_t* x_idx, elvis_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -375,6 +375,21 @@ def test_pyramid_reconstruction_and_map_video(dev):
         assert np.array_equal(E.gray_to_strength_maps(noisy, 0.0, rng_max), P.gray_to_strength_maps(noisy, 0.0, rng_max))
 
 
+def test_resize_nearest_matches_cv2(dev):
+    """Map resize of the mirrors (elvis.py:1189-1193, utils.py:1343-1345): cv2's INTER_NEAREST index rule."""
+    import cv2
+    from elvis_b200 import ops
+    rng = np.random.default_rng(31)
+    for (sh, sw, dh, dw) in [(1080, 1920, 67, 120), (17, 30, 34, 60), (33, 58, 34, 60), (5, 7, 11, 13), (100, 37, 9, 80), (64, 64, 64, 64)]:
+        a = rng.integers(0, 256, (2, sh, sw), dtype=np.uint8)
+        f = rng.random((2, sh, sw)).astype(np.float32)
+        d = rng.random((2, sh, sw))
+        for arr in (a, f, d):
+            got = ops.resize_nearest(to_dev(arr, dev), dh, dw).cpu().numpy()
+            for t in range(2):
+                assert np.array_equal(got[t], cv2.resize(arr[t], (dw, dh), interpolation=cv2.INTER_NEAREST)), (sh, sw, dh, dw, arr.dtype)
+
+
 def test_planar_pipeline_matches_per_plane_oracle(dev):
     """Planar YUV 4:2:0: mask from luma scores, applied to chroma at half block size."""
     from elvis_b200.pipeline import ElvisV1, Yuv420
@@ -713,6 +728,37 @@ def test_unsharp_restorer_utils(dev, halo, tb):
     # fewer maps than frames: the rest is returned untouched (utils.py:1341)
     got = U.restore_with_opencv_unsharp(frames, maps[:2], 16)
     assert np.array_equal(got[3], frames[3]) and np.array_equal(got[2], frames[2])
+
+
+def test_mirrors_resize_mismatched_maps_like_the_reference(dev, tmp_path):
+    """Maps that arrive at another resolution than the frame's block grid are brought to it with
+    INTER_NEAREST on the GPU (utils.py:1343-1345; UFO masks elvis.py:1186-1193)."""
+    import cv2
+    from elvis_b200 import elvis as E, utils as U
+    rng = np.random.default_rng(41)
+    frames = [rng.integers(0, 256, (48, 80, 3), dtype=np.uint8) for _ in range(2)]
+    odd = rng.integers(0, 5, (2, 7, 9))                     # the block grid is 3 x 5
+    fixed = np.stack([cv2.resize(m.astype(np.float32), (5, 3), interpolation=cv2.INTER_NEAREST).astype(np.int32) for m in odd])
+    got = U.restore_with_opencv_unsharp(frames, odd, 16)
+    ref = P.restore_with_opencv_unsharp(frames, fixed, 16, 0, 0.0)
+    assert all(np.array_equal(a, b) for a, b in zip(got, ref))
+    # calculate_removability_scores with UFO masks on disk
+    T, H, W, bs = 4, 64, 96, 16
+    y, u, v = synth_yuv420(T, H, W, seed=5)
+    raw = tmp_path / "reference_raw.yuv"
+    with open(raw, "wb") as f:
+        for t in range(T):
+            f.write(y[t].tobytes() + u[t].tobytes() + v[t].tobytes())
+    mdir = tmp_path / "maps" / "ufo_masks"
+    mdir.mkdir(parents=True)
+    bgs = []
+    for t in range(T):
+        m = (rng.random((H, W)) > 0.5).astype(np.uint8) * 255
+        cv2.imwrite(str(mdir / f"{t + 1:05d}.png"), m)
+        bgs.append(cv2.resize(m, (W // bs, H // bs), interpolation=cv2.INTER_NEAREST) == 0)
+    got = E.calculate_removability_scores(str(raw), "", W, H, bs, alpha=0.4, working_dir=str(tmp_path), smoothing_beta=0.5)
+    rsc, rtc = spec_scoring.sc_tc(y, bs)
+    np.testing.assert_allclose(got, P.combine_removability(rsc, rtc, 0.4, 0.5, np.stack(bgs)), rtol=RTOL, atol=1e-9)
 
 
 def test_unsharp_restorer_planar(dev):

@@ -91,3 +91,15 @@ def test_roi_host_logic_matches_the_oracle():
         assert np.bincount([d for _, d, _ in tab], minlength=dsize).cumsum().tolist() == start[1:].tolist()
     assert T.area_f32_plan(136, 240, 34, 60) == (4, 4, 0) and T.area_f32_plan(16, 24, 8, 12) == (2, 2, 12)
     assert T.area_f32_plan(135, 240, 34, 60) == (0, 0, 0)
+
+
+def test_nearest_index_matches_cv2():
+    import numpy as np
+    cv2 = __import__("pytest").importorskip("cv2")
+    from elvis_b200 import _tables as T
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        ssize, dsize = (int(v) for v in rng.integers(1, 300, 2))
+        row = np.arange(ssize, dtype=np.float32)[None]
+        ref = cv2.resize(row, (dsize, 1), interpolation=cv2.INTER_NEAREST)[0].astype(np.int64)
+        assert np.array_equal(T.nearest_index(ssize, dsize), ref), (ssize, dsize)
