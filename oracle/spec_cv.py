@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY -- integer restatement of the three OpenCV primitives the
 reference's v2 degradations delegate to (parity pinned: checked bit-exact against the
-real `cv2` of this image, 4.13.0, in tests/test_oracle_cv.py; the reference pins
+real `cv2` of this image, 4.13.0, in tests/test_oracle.py; the reference pins
 opencv-python 4.8.0.76 -- requirements.txt:42).
 
   * cv2.GaussianBlur(block, (5, 5), sigmaX=1.0)        elvis.py:2190, utils.py:1209, presley.py:989
