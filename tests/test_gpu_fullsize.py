@@ -114,3 +114,32 @@ def test_v2_properties_full_size(torch_dev):
     assert bool((y1.amax(dim=(2, 4)) == y1.amin(dim=(2, 4))).all())
     twice = v2.downsample_pow2(once, lv4, 4)
     assert torch.equal(once.y, twice.y) and torch.equal(v2.blur(once, rounds).y, once.y)
+
+
+def test_rowcol_properties_full_size(torch_dev):
+    """SURVEY 8f rank 2 at 4K (240 x 135 blocks of 16): a target met by whole passes removes exactly the
+    blocks missing from the position map; stretching by position map restores every survivor and
+    zeroes the rest; the recorded passes expand back to the original grid size."""
+    torch, dev = torch_dev
+    from elvis_b200 import ops
+    bs, by, bx = 16, 135, 240
+    gen = torch.Generator(device=dev).manual_seed(7)
+    frame = torch.randint(1, 256, (1, by * bs, bx * bs, 3), dtype=torch.uint8, device=dev, generator=gen)
+    imp = torch.rand((1, by, bx), dtype=torch.float64, device=dev, generator=gen)
+    target = 20 * by + 20 * bx - 20 * 21 // 2 - 20 * 19 // 2       # 20 row passes and 20 column passes, all complete
+    fby, fbx, counts = ops.rowcol_dims(by, bx, target)
+    assert sum(counts) == target and (fby, fbx) == (by - 20, bx - 20) and len(counts) == 40
+    mask, pos, pidx, pcnt, meta = ops.rowcol_plan(imp, target)
+    assert meta[0].tolist() == [40, fby, fbx, target] and int(mask.sum()) == target
+    kept = pos[0, :fby, :fbx].reshape(-1).long()
+    assert kept.unique().numel() == kept.numel() == by * bx - target
+    assert not bool(mask.reshape(-1)[kept].any())
+    shrunk = ops.gather_blocks(frame, pos, bs, fby, fbx)
+    inv = ops.invert_block_map(pos[:, :fby, :fbx].reshape(1, -1).contiguous(), by * bx).view(1, by, bx)
+    assert bool(((inv >= 0) == (mask == 0)).all())
+    full = ops.gather_blocks(shrunk, inv, bs, by, bx)
+    keep_px = _block_mask_to_pixels(torch, mask == 0, bs)[..., None]
+    assert torch.equal(full * keep_px, frame * keep_px) and not bool((full * (~keep_px)).any())
+    grid = ops.rowcol_expand(pidx[:, :40].contiguous(), pcnt[:, :40].contiguous(), fby, fbx)
+    assert grid.shape == (1, by, bx) and int((grid >= 0).sum()) == fby * fbx
+    assert torch.equal(grid[grid >= 0].sort().values, torch.arange(fby * fbx, device=dev, dtype=torch.int32))

@@ -316,3 +316,36 @@ def test_scoring_spec_properties():
     assert np.allclose(t3, tc[1:]) and np.allclose(s3, sc[1:])
     p = y[0]
     assert np.array_equal(spec_dct_dampen.dampen_plane(p, np.zeros((2, 3)), 16), p)
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(2, 6), st.integers(2, 7), st.integers(0, 2), st.integers(0, 2 ** 31 - 1))
+def test_rowcol_properties(by, bx, whole_passes, seed):
+    """Row+column shrink (utils.py:763-1018) when the target is met by whole passes (a partial last
+    pass leaves stale blocks in the grid -- a quirk of the reference that the port reproduces and
+    test_port_matches_reference_rowcol pins): the removed blocks are exactly the ones missing from
+    the position map, and stretching by position map puts every survivor back and zeros the rest."""
+    rng = np.random.default_rng(seed)
+    bs = 4
+    img = rng.integers(1, 256, (by * bs, bx * bs, 3), dtype=np.uint8)         # no zeros: zeros mark removed blocks
+    imp = np.round(rng.random((by, bx)) * 4) / 4
+    target = [0, by, by + (bx - 1)][whole_passes]
+    amount = (target + 1e-6) / (by * bx)
+    assert int(by * bx * amount) == target
+    small, mask, pmap = P.shrink_frame_position_map(img, imp, bs, amount)
+    assert mask.sum() == target
+    assert pmap.shape[:2] == (by - (whole_passes == 2), bx - (whole_passes >= 1))
+    kept = {(int(y), int(x)) for y, x in pmap.reshape(-1, 2)}
+    assert len(kept) == pmap.shape[0] * pmap.shape[1] == by * bx - target
+    assert all(not mask[y, x] for y, x in kept)
+    full = P.stretch_frame_position_map(small, mask, pmap, bs)
+    for y in range(by):
+        for x in range(bx):
+            blk = full[y * bs:(y + 1) * bs, x * bs:(x + 1) * bs]
+            if mask[y, x]:
+                assert not blk.any()
+            else:
+                assert np.array_equal(blk, img[y * bs:(y + 1) * bs, x * bs:(x + 1) * bs])
+    small2, mask2, passes = P.shrink_frame_removal_indices(img, imp, bs, amount)
+    assert np.array_equal(small2, small) and np.array_equal(mask2, mask) and sum(len(p) for p in passes) == target
+    assert P.stretch_frame_removal_indices(small2, passes, by, bx, bs).shape == img.shape
