@@ -280,8 +280,8 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": "score_umma_kernel<2> (elvis_score_sc_tc)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch over the 120-frame clip,
-                # ncu --set full capture profiles/r1d_ncu_full_summary.csv (1.0038e9 + 0.0351e9)
-                "traffic": 1.0389e9 if T == FRAMES else None, "peak_source": peak_src,
+                # ncu --set full capture profiles/r1d_ncu_full_summary.csv (1.0038e9 + 0.0327e9)
+                "traffic": 1.0364e9 if T == FRAMES else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ab["score"] * T,
                 "whole_step": {"achieved": ab["total"] * T / ms_per_step / 1e6, "frac": ab["total"] * T / ms_per_step / 1e6 / peak,
                                "note": "all three stages, pipelined as timed"},
