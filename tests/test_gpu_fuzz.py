@@ -96,3 +96,63 @@ def test_fuzz_degradations(dev):
         assert np.array_equal(E.restore_blur_opencv_unsharp_mask(img, lv, bs), P.restore_blur_opencv_unsharp_mask(img, lv, bs)), (case, "unsharp")
         dl = rng.integers(0, int(np.log2(bs)) + 1, (by, bx))
         assert np.array_equal(E.restore_downsample_opencv_lanczos(img, dl, bs), P.restore_downsample_opencv_lanczos(img, dl, bs)), (case, "lanczos")
+
+
+def test_fuzz_planar_pipeline_and_side_channels(dev):
+    """Planar YUV 4:2:0 clips of random geometry through ElvisV1 (fused Y+U+V move kernel for
+    16-multiples, per-plane kernels otherwise), the pipelined variants, and the bit packers."""
+    import torch
+    from _util import synth_yuv420
+    from elvis_b200 import ops
+    from elvis_b200.pipeline import ElvisV1, ElvisV1Pipelined, Yuv420
+    rng = np.random.default_rng(2027)
+    for case in range(10):
+        bs = int(rng.choice([8, 16, 32]))
+        by, bx = int(rng.integers(1, 6)), int(rng.integers(2, 14))
+        T, H, W = int(rng.integers(1, 7)), by * bs, bx * bs
+        amount = float(rng.choice([0.0, 0.25, 0.5, 0.9]))
+        y, u, v = synth_yuv420(T, H, W, seed=100 + case)
+        clip = Yuv420(_to(y, dev), _to(u, dev), _to(v, dev))
+        scores, mask, shrunk, full = ElvisV1(bs, amount, 0.4, 0.6).run(clip)
+        s_np, m_np = scores.cpu().numpy(), mask.cpu().numpy()
+        k = P.blocks_to_remove_elvis(amount, bx)
+        assert np.array_equal(m_np, P.select_rows(s_np, k, P.REMOVE_HIGH)), (case, bs, by, bx, T, amount)
+        for name, plane, pb in (("y", y, bs), ("u", u, bs // 2), ("v", v, bs // 2)):
+            for t in range(T):
+                rs = P.shrink_plane(plane[t], m_np[t], pb)
+                assert np.array_equal(getattr(shrunk, name)[t].cpu().numpy(), rs), (case, name, t)
+                assert np.array_equal(getattr(full, name)[t].cpu().numpy(), P.stretch_plane(rs, m_np[t], pb)), (case, name, t)
+        for depth, split in ((2, False), (3, True)):
+            slot = ElvisV1Pipelined(T, H, W, bs, amount, 0.4, 0.6, dev, depth=depth, split_stretch=split).submit(clip)
+            slot["done"].synchronize()
+            assert torch.equal(slot["mask"], mask) and torch.equal(slot["scores"], scores)
+            assert all(torch.equal(a, b) for a, b in zip(slot["full"].planes, full.planes))
+        packed, shape = P.pack_masks(m_np)
+        assert np.array_equal(ops.pack_mask_bits(mask).cpu().numpy(), packed)
+        assert np.array_equal(ops.unpack_mask_bits(_to(packed, dev), shape).cpu().numpy(), m_np)
+        lv = rng.integers(0, 4, (T, by, bx)).astype(np.int32)
+        p2 = ops.pack_levels_2bit(_to(lv, dev))
+        assert np.array_equal(p2.cpu().numpy(), P.pack_levels_2bit(lv))
+        assert np.array_equal(ops.unpack_levels_2bit(p2, bx).cpu().numpy(), lv)
+
+
+def test_fuzz_roi_and_i420(dev, tmp_path):
+    from elvis_b200 import utils as U
+    rng = np.random.default_rng(2028)
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    for case in range(8):
+        h, w = 16 * int(rng.integers(3, 40)), 16 * int(rng.integers(5, 70))
+        maps = [rng.random((h // 16, w // 16)) for _ in range(2)]
+        crf, rq = int(rng.integers(0, 64)), int(rng.integers(0, 20))
+        U.create_svtav1_roi_file(maps, a, crf, rq, w, h)
+        P.create_svtav1_roi_file(maps, b, crf, rq, w, h)
+        assert open(a).read() == open(b).read(), (case, h, w, crf, rq)
+        qp, rr = int(rng.integers(0, 52)), int(rng.integers(0, 26))
+        U.create_kvazaar_roi_file(maps, a, qp, rr)
+        P.create_kvazaar_roi_file(maps, b, qp, rr)
+        assert open(a, "rb").read() == open(b, "rb").read(), (case, qp, rr)
+        fh, fw = 2 * int(rng.integers(1, 40)), 2 * int(rng.integers(1, 60))
+        frames = [rng.integers(0, 256, (fh, fw, 3), dtype=np.uint8) for _ in range(2)]
+        U.write_y4m(frames, a, 25.0)
+        P.write_y4m(frames, b, 25.0)
+        assert open(a, "rb").read() == open(b, "rb").read(), (case, fh, fw)
