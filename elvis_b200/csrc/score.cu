@@ -1,6 +1,9 @@
 // a1: per-block spatial (SC) and temporal (TC) DCT-energy features -- the arithmetic the
 // reference delegates to the external EVCA package (elvis.py:1014-1031, presley.py:202).
-// Spec: oracle/spec_scoring.py.
+// Spec: oracle/spec_scoring.py.  This file holds the entry point elvis_score_sc_tc, which picks
+// the kernel, and the CUDA-core kernel: the path for small clips, planes that are not 16-byte
+// aligned and drivers without tensor maps.  Large aligned clips go to the tcgen05 kernel in
+// score_umma.cu; score_mma.cu is the earlier mma.sync attempt, kept selectable.
 //
 // Mapping.  One thread owns one 8x8 luma tile and walks it through a run of consecutive
 // frames; the tile never leaves registers, so there is no shared-memory staging and no

@@ -1,4 +1,6 @@
-// a1 on tensor cores: the scoring kernel for 16x16 blocks.
+// a1 on the LEGACY tensor-core path (mma.sync): the first tensor-core scoring kernel, for 16x16
+// blocks.  Correct, but slower than both other kernels on B200 (744 us vs 508 us CUDA cores vs
+// 353 us tcgen05, score_umma.cu) -- kept behind ELVIS_SCORE_IMPL=mma|tma as a measured data point.
 //
 // Why: ncu on the CUDA-core kernel (score.cu; profiles/r1a_*) shows it issue-bound, not
 // HBM-bound -- 16 instructions per pixel, DRAM at 20 % -- which is the condition under which
