@@ -11,6 +11,7 @@ from oracle import spec_scoring
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-4
+SCALE = int(os.environ.get("ELVIS_FUZZ_SCALE", "1"))     # multiply the number of random cases (soak runs)
 
 
 @pytest.fixture(scope="module")
@@ -30,7 +31,7 @@ def test_fuzz_scoring(dev, monkeypatch, impl):
     from elvis_b200 import ops
     monkeypatch.setenv("ELVIS_SCORE_IMPL", impl)
     rng = np.random.default_rng(2024)
-    for case in range(24):
+    for case in range(24 * SCALE):
         bs = int(rng.choice([8, 16, 32]))
         by, bx = int(rng.integers(1, 6)), int(rng.integers(1, 40))
         # widths that are / are not multiples of 16 bytes, with spare columns and rows beyond the block grid
@@ -55,7 +56,7 @@ def test_fuzz_scoring(dev, monkeypatch, impl):
 def test_fuzz_shrink_stretch_and_rowcol(dev):
     from elvis_b200 import elvis as E, utils as U
     rng = np.random.default_rng(2025)
-    for case in range(24):
+    for case in range(24 * SCALE):
         bs = int(rng.choice([4, 8, 16]))
         by, bx = int(rng.integers(1, 7)), int(rng.integers(2, 12))
         img = rng.integers(0, 256, (by * bs, bx * bs, 3), dtype=np.uint8)
@@ -80,7 +81,7 @@ def test_fuzz_shrink_stretch_and_rowcol(dev):
 def test_fuzz_degradations(dev):
     from elvis_b200 import elvis as E, utils as U
     rng = np.random.default_rng(2026)
-    for case in range(16):
+    for case in range(16 * SCALE):
         bs = int(rng.choice([8, 16, 32]))
         by, bx = int(rng.integers(1, 5)), int(rng.integers(1, 7))
         img = rng.integers(0, 256, (by * bs, bx * bs, 3), dtype=np.uint8)
@@ -106,7 +107,7 @@ def test_fuzz_planar_pipeline_and_side_channels(dev):
     from elvis_b200 import ops
     from elvis_b200.pipeline import ElvisV1, ElvisV1Pipelined, Yuv420
     rng = np.random.default_rng(2027)
-    for case in range(10):
+    for case in range(10 * SCALE):
         bs = int(rng.choice([8, 16, 32]))
         by, bx = int(rng.integers(1, 6)), int(rng.integers(2, 14))
         T, H, W = int(rng.integers(1, 7)), by * bs, bx * bs
@@ -140,7 +141,7 @@ def test_fuzz_roi_and_i420(dev, tmp_path):
     from elvis_b200 import utils as U
     rng = np.random.default_rng(2028)
     a, b = str(tmp_path / "a"), str(tmp_path / "b")
-    for case in range(8):
+    for case in range(8 * SCALE):
         h, w = 16 * int(rng.integers(3, 40)), 16 * int(rng.integers(5, 70))
         maps = [rng.random((h // 16, w // 16)) for _ in range(2)]
         crf, rq = int(rng.integers(0, 64)), int(rng.integers(0, 20))
