@@ -13,7 +13,7 @@ OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_SHAPE = 0, -1, -2, -3, -4
 F32, F64 = 0, 1
 REMOVE_HIGH, REMOVE_LOW = 0, 1
 LEVELS_ROUND, LEVELS_INVERTED_ROUND, LEVELS_INVERTED_BINS = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class Plane(C.Structure):
@@ -69,6 +69,9 @@ SIGNATURES = {
     "elvis_levels_to_gray": [_vp, _i64, _i32, _i32, _vp, _vp],
     "elvis_gray_to_levels": [_vp, _i64, _f32, _f32, _vp, _vp],
     "elvis_resize_nearest": [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp],
+    "elvis_resize_linear_float": [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "elvis_rgb_to_gray": [_PP, _PP, _i32, _vp],
+    "elvis_refill_map": [_vp, _i32, _i64, _i64, _vp, _vp],
 }
 EXPORTS = ["elvis_abi_version", "elvis_error_string", "elvis_last_cuda_error", *SIGNATURES]
 

@@ -219,3 +219,26 @@ def nearest_index(ssize: int, dsize: int) -> np.ndarray:
     1 / (dsize / ssize), not by ssize / dsize -- the two differ in the last bit for some ratios."""
     ifx = 1.0 / (dsize / ssize)
     return np.minimum(np.floor(np.arange(dsize) * ifx).astype(np.int64), ssize - 1).astype(np.int32)
+
+
+@lru_cache(maxsize=64)
+def linear_float_index(ssize: int, dsize: int, fused: bool):
+    """Source index (int32) and fraction (float64) per destination index of cv2.resize(float map,
+    INTER_LINEAR): coordinate = (d + 0.5) * (ssize / dsize) - 0.5 in double -- one fused multiply-add on
+    cv2's float64 path (`fused`; evaluated exactly with rationals here), a rounded product and a rounded
+    difference on its float32 path -- index = floor, fraction = coordinate - index; left of the first /
+    right of the last sample the fraction is 0."""
+    from fractions import Fraction
+    scale = ssize / dsize
+    idx = np.empty(dsize, np.int32)
+    frac = np.empty(dsize, np.float64)
+    for d in range(dsize):
+        fx = float(Fraction(2 * d + 1, 2) * Fraction(scale) - Fraction(1, 2)) if fused else (d + 0.5) * scale - 0.5
+        s = int(np.floor(fx))
+        f = fx - s
+        if s < 0:
+            s, f = 0, 0.0
+        if s >= ssize - 1:
+            s, f = ssize - 1, 0.0
+        idx[d], frac[d] = s, f
+    return idx, frac

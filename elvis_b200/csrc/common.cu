@@ -2,6 +2,20 @@
 
 namespace elvis {
 thread_local int g_last_cuda_error = 0;
+
+int num_sms() {
+    static std::atomic<int> cache[128];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 128) {
+        const int v = cache[dev].load(std::memory_order_relaxed);
+        if (v > 0) return v;
+    }
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (dev >= 0 && dev < 128) cache[dev].store(n, std::memory_order_relaxed);
+    return n;
+}
 }
 
 extern "C" int elvis_abi_version(void) { return ELVIS_B200_ABI_VERSION; }

@@ -1,6 +1,7 @@
 // Shared host/device helpers for the elvis_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdlib>
 #include <stdint.h>
 #include "../../include/elvis_b200.h"
@@ -41,7 +42,29 @@ inline int plane_ok(const elvis_plane* p) {
     return p && p->data && p->height > 0 && p->width > 0 && p->channels >= 1 && p->row_stride >= (int64_t)p->width * p->channels;
 }
 
-constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+// SM count of the CURRENT device (148 on B200: 2 dies x 74 SMs), queried once per device.
+int num_sms();
+#define kNumSMs (::elvis::num_sms())
+
+// Per-device "this kernel's opt-in attribute has been set" flag.  Function attributes such as
+// cudaFuncAttributeMaxDynamicSharedMemorySize belong to the (function, device) pair, so a
+// process-wide once-flag would leave the second GPU of a process unconfigured.  The flag is a
+// cache of an idempotent call (benign if two threads race to set it), not library state.
+struct PerDeviceOnce {
+    std::atomic<uint64_t> lo{0}, hi{0};   // devices 0..127
+    template <typename F> cudaError_t run(F&& configure) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= 128) return configure();
+        std::atomic<uint64_t>& word = dev < 64 ? lo : hi;
+        const uint64_t bit = 1ull << (dev & 63);
+        if (word.load(std::memory_order_acquire) & bit) return cudaSuccess;
+        e = configure();
+        if (e == cudaSuccess) word.fetch_or(bit, std::memory_order_release);
+        return e;
+    }
+};
 
 // streaming 128/64/32-bit accesses: no L1 allocation (every byte is touched once)
 template <typename V> __device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }

@@ -213,6 +213,71 @@ __global__ void __launch_bounds__(256) rgb_to_i420_x16_kernel(const I420Params p
     }
 }
 
+// cv2.COLOR_RGB2GRAY on uint8 (pinned against cv2 4.13 in tests/test_oracle.py: 15-bit fixed point,
+// (9798 R + 19235 G + 3735 B + 2^14) >> 15).  One thread = 4 pixels of a row (12 bytes in, one word out).
+struct GrayParams {
+    const uint8_t* rgb;
+    uint8_t* y;
+    int64_t rgb_frame, rgb_row, y_frame, y_row;
+    int32_t T, H, W, words;
+};
+
+__device__ __forceinline__ uint32_t gray_of(uint32_t r, uint32_t g, uint32_t b) {
+    return (9798u * r + 19235u * g + 3735u * b + (1u << 14)) >> 15;
+}
+
+__global__ void __launch_bounds__(256) rgb_to_gray_kernel(const GrayParams p) {
+    const int qw = (p.W + 3) / 4;
+    const int64_t total = (int64_t)p.T * p.H * qw;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int qx = (int)(i % qw);
+        const int yy = (int)((i / qw) % p.H);
+        const int t = (int)(i / ((int64_t)qw * p.H));
+        const int x0 = qx * 4, n = min(4, p.W - x0);
+        const uint8_t* src = p.rgb + (int64_t)t * p.rgb_frame + (int64_t)yy * p.rgb_row + (int64_t)x0 * 3;
+        uint8_t* dst = p.y + (int64_t)t * p.y_frame + (int64_t)yy * p.y_row + x0;
+        if (p.words && n == 4) {
+            const uint32_t w0 = __ldcs(reinterpret_cast<const uint32_t*>(src)), w1 = __ldcs(reinterpret_cast<const uint32_t*>(src) + 1),
+                           w2 = __ldcs(reinterpret_cast<const uint32_t*>(src) + 2);
+            const uint32_t g0 = gray_of(w0 & 0xff, (w0 >> 8) & 0xff, (w0 >> 16) & 0xff);
+            const uint32_t g1 = gray_of(w0 >> 24, w1 & 0xff, (w1 >> 8) & 0xff);
+            const uint32_t g2 = gray_of((w1 >> 16) & 0xff, w1 >> 24, w2 & 0xff);
+            const uint32_t g3 = gray_of((w2 >> 8) & 0xff, (w2 >> 16) & 0xff, w2 >> 24);
+            __stcs(reinterpret_cast<uint32_t*>(dst), g0 | (g1 << 8) | (g2 << 16) | (g3 << 24));
+        } else {
+            for (int k = 0; k < n; ++k) dst[k] = (uint8_t)gray_of(src[3 * k], src[3 * k + 1], src[3 * k + 2]);
+        }
+    }
+}
+
+// cv2.resize(map, INTER_LINEAR) for float32 / float64 maps (pinned against cv2 4.13 in
+// tests/test_oracle.py: oracle/spec_cv.py resize_linear_float).  cv2 interpolates as a fused
+// lerp, horizontally then vertically: h = fma(S[x1] - S[x0], fx, S[x0]); out = fma(h1 - h0, fy, h0),
+// each subtraction rounded on its own.  The source index / fraction tables come from the host
+// (elvis_b200/_tables.py linear_float_index: coordinate = fma(d + 0.5, src/dst, -0.5) in double; the
+// fraction is rounded to float for float32 maps).
+template <typename F> __device__ __forceinline__ F lerp_rn(F a, F b, F f);
+template <> __device__ __forceinline__ float lerp_rn<float>(float a, float b, float f) { return __fmaf_rn(__fsub_rn(b, a), f, a); }
+template <> __device__ __forceinline__ double lerp_rn<double>(double a, double b, double f) { return __fma_rn(__dsub_rn(b, a), f, a); }
+
+template <typename F>
+__global__ void __launch_bounds__(256) resize_linear_float_kernel(const F* __restrict__ src, int T, int sh, int sw, F* __restrict__ dst,
+                                                                  int dh, int dw, const int32_t* __restrict__ yi, const double* __restrict__ yf,
+                                                                  const int32_t* __restrict__ xi, const double* __restrict__ xf) {
+    const int64_t total = (int64_t)T * dh * dw;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int x = (int)(i % dw);
+        const int y = (int)((i / dw) % dh);
+        const int t = (int)(i / ((int64_t)dw * dh));
+        const int x0 = xi[x], x1 = min(x0 + 1, sw - 1), y0 = yi[y], y1 = min(y0 + 1, sh - 1);
+        const F fx = (F)xf[x], fy = (F)yf[y];
+        const F* m = src + (int64_t)t * sh * sw;
+        const F h0 = lerp_rn<F>(m[(int64_t)y0 * sw + x0], m[(int64_t)y0 * sw + x1], fx);
+        const F h1 = lerp_rn<F>(m[(int64_t)y1 * sw + x0], m[(int64_t)y1 * sw + x1], fx);
+        dst[i] = lerp_rn<F>(h0, h1, fy);
+    }
+}
+
 unsigned grid_for(int64_t n) {
     int64_t g = (n + 255) / 256;
     const int64_t cap = (int64_t)kNumSMs * 16;
@@ -314,6 +379,45 @@ extern "C" int elvis_rgb_to_i420(const elvis_plane* rgb, const elvis_plane* y, c
         rgb_to_i420_x16_kernel<<<grid_for((int64_t)n_frames * (H / 2) * (W / 16)), 256, 0, as_stream(stream)>>>(p);
     else
         rgb_to_i420_kernel<<<grid_for((int64_t)n_frames * (H / 2) * ((W + 3) / 4)), 256, 0, as_stream(stream)>>>(p);
+    ELVIS_CHECK_LAUNCH();
+    return ELVIS_OK;
+}
+
+extern "C" int elvis_rgb_to_gray(const elvis_plane* rgb, const elvis_plane* y, int32_t n_frames, elvis_stream_t stream) {
+    if (!plane_ok(rgb) || !plane_ok(y) || n_frames <= 0) return ELVIS_ERR_INVALID_ARG;
+    if (rgb->channels != 3 || y->channels != 1) return ELVIS_ERR_INVALID_ARG;
+    if (y->height < rgb->height || y->width < rgb->width) return ELVIS_ERR_SHAPE;
+    GrayParams p;
+    p.rgb = static_cast<const uint8_t*>(rgb->data);
+    p.y = static_cast<uint8_t*>(y->data);
+    p.rgb_frame = rgb->frame_stride;
+    p.rgb_row = rgb->row_stride;
+    p.y_frame = y->frame_stride;
+    p.y_row = y->row_stride;
+    p.T = n_frames;
+    p.H = rgb->height;
+    p.W = rgb->width;
+    p.words = aligned_to(p.rgb, 4) && rgb->frame_stride % 4 == 0 && rgb->row_stride % 4 == 0 && aligned_to(p.y, 4) &&
+              y->frame_stride % 4 == 0 && y->row_stride % 4 == 0;
+    rgb_to_gray_kernel<<<grid_for((int64_t)n_frames * p.H * ((p.W + 3) / 4)), 256, 0, as_stream(stream)>>>(p);
+    ELVIS_CHECK_LAUNCH();
+    return ELVIS_OK;
+}
+
+extern "C" int elvis_resize_linear_float(const void* src, int32_t dtype, int32_t n_maps, int32_t src_h, int32_t src_w, void* dst,
+                                         int32_t dst_h, int32_t dst_w, const int32_t* y_index, const double* y_frac,
+                                         const int32_t* x_index, const double* x_frac, elvis_stream_t stream) {
+    if (!src || !dst || !y_index || !y_frac || !x_index || !x_frac) return ELVIS_ERR_INVALID_ARG;
+    if (n_maps <= 0 || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0) return ELVIS_ERR_INVALID_ARG;
+    const unsigned grid = grid_for((int64_t)n_maps * dst_h * dst_w);
+    if (dtype == ELVIS_F32)
+        resize_linear_float_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const float*>(src), n_maps, src_h, src_w,
+                                                                              static_cast<float*>(dst), dst_h, dst_w, y_index, y_frac, x_index, x_frac);
+    else if (dtype == ELVIS_F64)
+        resize_linear_float_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const double*>(src), n_maps, src_h, src_w,
+                                                                               static_cast<double*>(dst), dst_h, dst_w, y_index, y_frac, x_index, x_frac);
+    else
+        return ELVIS_ERR_INVALID_ARG;
     ELVIS_CHECK_LAUNCH();
     return ELVIS_OK;
 }

@@ -241,6 +241,36 @@ __global__ void __launch_bounds__(256) gather_blocks_kernel(const GatherParams p
     }
 }
 
+
+// Row-major refill map of presley.py:787-827 (stretch_video_frames): the i-th kept block of a frame
+// (mask == 0, row-major order) takes shrunk block i -- wherever its row and column fall -- as long
+// as i < capacity = shrunk_by * shrunk_bx; removed blocks and kept blocks beyond the capacity stay
+// black (-1).  One CTA per frame: ballot prefix counts inside a warp, warp totals through smem.
+constexpr int kRefillThreads = 256;
+__global__ void __launch_bounds__(kRefillThreads) refill_map_kernel(const uint8_t* __restrict__ mask, int n, int capacity,
+                                                                    int32_t* __restrict__ map) {
+    __shared__ int warp_total[kRefillThreads / 32];
+    __shared__ int carry;
+    const uint8_t* m = mask + (int64_t)blockIdx.x * n;
+    int32_t* out = map + (int64_t)blockIdx.x * n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += kRefillThreads) {
+        const int i = base + threadIdx.x;
+        const bool kept = i < n && m[i] == 0;
+        const unsigned b = __ballot_sync(0xffffffffu, kept);
+        if (lane == 0) warp_total[warp] = __popc(b);
+        __syncthreads();
+        int before = carry + __popc(b & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) before += warp_total[w];
+        if (i < n) out[i] = (kept && before < capacity) ? before : -1;
+        __syncthreads();
+        if (threadIdx.x == kRefillThreads - 1) carry = before + (kept ? 1 : 0);
+        __syncthreads();
+    }
+}
+
 }  // namespace
 }  // namespace elvis
 
@@ -339,6 +369,15 @@ extern "C" int elvis_gather_blocks(const elvis_plane* src, const elvis_plane* ds
         case 2: gather_blocks_kernel<uint16_t><<<grid, 256, 0, st>>>(p); break;
         default: gather_blocks_kernel<uint8_t><<<grid, 256, 0, st>>>(p); break;
     }
+    ELVIS_CHECK_LAUNCH();
+    return ELVIS_OK;
+}
+
+extern "C" int elvis_refill_map(const uint8_t* mask, int32_t n_frames, int64_t blocks_per_frame, int64_t capacity, int32_t* map,
+                                elvis_stream_t stream) {
+    if (!mask || !map || n_frames <= 0 || blocks_per_frame <= 0 || blocks_per_frame > INT32_MAX || capacity < 0) return ELVIS_ERR_INVALID_ARG;
+    const int cap = capacity > blocks_per_frame ? (int)blocks_per_frame : (int)capacity;
+    refill_map_kernel<<<n_frames, kRefillThreads, 0, as_stream(stream)>>>(mask, (int)blocks_per_frame, cap, map);
     ELVIS_CHECK_LAUNCH();
     return ELVIS_OK;
 }

@@ -342,10 +342,11 @@ int launch_score_mma(ScoreParams p, int plane_h, int plane_w, bool use_tma, cuda
         if (!ok) use_tma = false;   // driver without tensor-map support: same arithmetic, direct loads
     }
     if (use_tma) {
-        static bool attr_set = [] {
-            return cudaFuncSetAttribute(score_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) == cudaSuccess;
-        }();
-        (void)attr_set;
+        static PerDeviceOnce configured;   // the attribute is per (kernel, device)
+        const cudaError_t e = configured.run([] {
+            return cudaFuncSetAttribute(score_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        });
+        if (e != cudaSuccess) return cuda_fail(e);
         score_mma_kernel<true><<<grid, (kConsumerWarps + 1) * 32, kSmemBytes, st>>>(tm_clip, tm_halo, p);
     } else {
         score_mma_kernel<false><<<grid, kConsumerWarps * 32, 0, st>>>(tm_clip, tm_halo, p);

@@ -455,14 +455,13 @@ bool make_unit_map(CUtensorMap* m, const uint8_t* ptr, int W, int H, int T, int6
 
 template <int R>
 int launch_umma(const ScoreParams& p, const CUtensorMap& tm_clip, const CUtensorMap& tm_halo, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(score_umma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem);
-        if (e != cudaSuccess) return cuda_fail(e);
-        // no carve-out preference: a kernel that forces its own L1 / shared split cannot overlap with the
-        // shrink / stretch kernels of the other stream (measured: pipelined step 1.32 instead of 1.07 ms)
-        configured = true;
-    }
+    // no carve-out preference: a kernel that forces its own L1 / shared split cannot overlap with the
+    // shrink / stretch kernels of the other stream (measured: pipelined step 1.32 instead of 1.07 ms)
+    static PerDeviceOnce configured;   // the attribute is per (kernel, device)
+    const cudaError_t e = configured.run([] {
+        return cudaFuncSetAttribute(score_umma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem);
+    });
+    if (e != cudaSuccess) return cuda_fail(e);
     const int ctas_per_chunk = (p.By * p.tiles_x + kUnitsPerCta - 1) / kUnitsPerCta;
     score_umma_kernel<R><<<ctas_per_chunk * p.n_chunks, kUmmaThreads, kUmmaSmem, st>>>(tm_clip, tm_halo, p);
     ELVIS_CHECK_LAUNCH();

@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(256) pack2_kernel(const int32_t* __restrict__ 
         unsigned b = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            if (c + q < bx) b |= ((unsigned)lv[r * bx + c + q] & 3u) << (2 * q);
+            if (c + q < bx) b |= (unsigned)min(max(lv[r * bx + c + q], 0), 3) << (2 * q);   // saturating: level 4 (16x at bs 16) is kept as 8x
         out[j] = (uint8_t)b;
     }
 }

@@ -200,16 +200,18 @@ def x265_ctu_size(block_size: int, width: int, height: int) -> int:
 
 def per_block_qp_maps(removability_scores: np.ndarray, block_size: int, width: int, height: int) -> Tuple[np.ndarray, int]:
     """Part 1 of encode_with_roi up to the aligned maps (elvis.py:2030-2074): scores in [0, 1] ->
-    float32 QP offsets in [-1, 1] on the CTU grid (INTER_AREA).  Returns (maps (T, rows, cols), ctu)."""
+    float32 QP offsets in [-1, 1] on the CTU grid (INTER_AREA when the CTU is at least a block, else
+    INTER_LINEAR -- elvis.py:2068).  Returns (maps (T, rows, cols), ctu)."""
     import math
     T, by, bx = removability_scores.shape
     ctu = x265_ctu_size(block_size, width, height)
     cols, rows = math.ceil(width / ctu), math.ceil(height / ctu)
     qp = ops.roi_prepare_f32(_to_dev(removability_scores, np.float64), 1)
     if (rows, cols) != (by, bx):
-        if ctu < block_size or rows > by or cols > bx:
-            raise NotImplementedError("CTU grid finer than the block grid (cv2 bilinear path) is not supported")
-        qp = ops.resize_area_f32(qp, rows, cols)
+        if ctu < block_size:            # CTU grid finer than the block grid: cv2's float32 bilinear resize
+            qp = ops.resize_linear_float(qp, rows, cols)
+        else:
+            qp = ops.resize_area_f32(qp, rows, cols)
     return qp.cpu().numpy(), ctu
 
 

@@ -9,6 +9,7 @@ Clip layouts
 from __future__ import annotations
 
 import ctypes as C
+import functools
 
 import numpy as np
 import torch
@@ -25,6 +26,22 @@ __all__ = ["score_sc_tc", "minmax", "combine_removability", "normalize_", "impor
 
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _on_device(fn):
+    """Run an operator with the device of its first tensor argument current: the library launches
+    on the CURRENT device and on the stream handed to it, so both must belong to the tensors' GPU
+    (one process may drive several GPUs)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        t = args[0] if args else None
+        if isinstance(t, (tuple, list)) and t:
+            t = t[0]
+        if isinstance(t, torch.Tensor) and t.is_cuda and t.device.index != torch.cuda.current_device():
+            with torch.cuda.device(t.device):
+                return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapper
 
 
 def _ptr(t: torch.Tensor | None) -> C.c_void_p:
@@ -364,10 +381,14 @@ def temporal_blend_(clip: torch.Tensor, temporal_blend: float) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------ a13
-def pack_mask_bits(mask: torch.Tensor) -> torch.Tensor:
+def pack_mask_bits(mask: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """np.packbits(mask) of a uint8 {0, 1} mask (MSB first, flat over all axes; elvis.py:4412-4418)."""
     _check_cuda(mask, torch.uint8, "mask")
     m = mask.contiguous()
-    out = torch.empty((m.numel() + 7) // 8, dtype=torch.uint8, device=m.device)
+    if out is None:
+        out = torch.empty((m.numel() + 7) // 8, dtype=torch.uint8, device=m.device)
+    elif out.numel() != (m.numel() + 7) // 8 or out.dtype != torch.uint8 or not out.is_contiguous():
+        raise ValueError("out must hold ceil(n / 8) contiguous bytes")
     call("elvis_pack_mask_bits", _ptr(m), m.numel(), _ptr(out), _stream())
     return out
 
@@ -642,3 +663,66 @@ def resize_nearest(maps: torch.Tensor, dst_h: int, dst_w: int) -> torch.Tensor:
     xi = torch.from_numpy(_tables.nearest_index(sw, dst_w)).to(maps.device)
     call("elvis_resize_nearest", _ptr(maps), maps.element_size(), T, sh, sw, _ptr(out), dst_h, dst_w, _ptr(yi), _ptr(xi), _stream())
     return out
+
+
+def resize_linear_float(maps: torch.Tensor, dst_h: int, dst_w: int) -> torch.Tensor:
+    """cv2.resize(map, (dst_w, dst_h), INTER_LINEAR) for every float32 / float64 map of a dense (T, h, w)
+    tensor (utils.py:1127-1128; elvis.py:2068-2073).  Sources with a single row or column take another
+    cv2 path and are not supported."""
+    if not maps.is_cuda:
+        raise TypeError("maps must be a CUDA tensor (elvis_b200 has no CPU path)")
+    if maps.dim() != 3:
+        raise ValueError("maps must be (T, h, w)")
+    dt = _float_dtype(maps, "maps")
+    maps = maps.contiguous()
+    T, sh, sw = maps.shape
+    if sh < 2 or sw < 2:
+        raise NotImplementedError("INTER_LINEAR of a single-row / single-column map (cv2 takes another path) is not supported")
+    out = torch.empty((T, dst_h, dst_w), dtype=maps.dtype, device=maps.device)
+    if out.numel() == 0:
+        return out
+    fused = dt == F64
+    tabs = [torch.from_numpy(a).to(maps.device) for a in (*_tables.linear_float_index(sh, dst_h, fused),
+                                                           *_tables.linear_float_index(sw, dst_w, fused))]
+    call("elvis_resize_linear_float", _ptr(maps), dt, T, sh, sw, _ptr(out), dst_h, dst_w, *[_ptr(t) for t in tabs], _stream())
+    return out
+
+
+def rgb_to_gray(frames: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(T, H, W, 3) uint8 RGB -> (T, H, W) uint8 luma, cv2.COLOR_RGB2GRAY's fixed point."""
+    _check_cuda(frames, torch.uint8, "frames")
+    if frames.dim() != 4 or frames.shape[3] != 3:
+        raise ValueError("frames must be (T, H, W, 3)")
+    T, H, W, _ = frames.shape
+    if out is None:
+        out = torch.empty((T, H, W), dtype=torch.uint8, device=frames.device)
+    elif tuple(out.shape) != (T, H, W):
+        raise ValueError("out must be (T, H, W)")
+    if out.numel():
+        src, dst = plane_of(frames, "frames"), plane_of(out, "out")
+        call("elvis_rgb_to_gray", C.byref(src), C.byref(dst), T, _stream())
+    return out
+
+
+def refill_map(mask: torch.Tensor, capacity: int) -> torch.Tensor:
+    """(T, By, Bx) uint8 removal mask -> int32 (T, By, Bx): the row-major rank of every kept block among
+    the kept blocks of its frame (the shrunk block it takes back, presley.py:806-819), -1 for removed
+    blocks and for ranks >= capacity."""
+    mask = _mask_arg(mask)
+    T, by, bx = mask.shape
+    out = torch.empty((T, by, bx), dtype=torch.int32, device=mask.device)
+    if out.numel():
+        call("elvis_refill_map", _ptr(mask), T, by * bx, int(capacity), _ptr(out), _stream())
+    return out
+
+
+# every public operator runs on the device of its first tensor argument
+for _name in ("score_sc_tc", "minmax", "combine_removability", "normalize_", "importance_scores", "select_rows", "shrink",
+              "stretch", "move_yuv420", "levels_from_scores", "degrade_blur", "degrade_downsample", "dct_dampen",
+              "restore_unsharp", "restore_lanczos", "temporal_blend_", "pack_mask_bits", "unpack_mask_bits",
+              "pack_levels_2bit", "unpack_levels_2bit", "rowcol_plan", "rowcol_expand", "invert_block_map", "gather_blocks",
+              "roi_kvazaar", "roi_prepare_f32", "resize_area_f32", "roi_svtav1_offsets", "rgb_to_i420", "area_downscale",
+              "merge_blocks_", "levels_to_gray", "gray_to_levels", "resize_nearest", "resize_linear_float", "rgb_to_gray",
+              "refill_map"):
+    globals()[_name] = _on_device(globals()[_name])
+del _name

@@ -9,42 +9,13 @@ from __future__ import annotations
 
 import os
 
-from dataclasses import dataclass
 from typing import Optional, Tuple
 
 import torch
 
 from . import ops
 from .elvis import blocks_to_remove
-
-
-@dataclass
-class Yuv420:
-    """Three CUDA uint8 planes: y (T, H, W), u and v (T, H/2, W/2)."""
-    y: torch.Tensor
-    u: torch.Tensor
-    v: torch.Tensor
-
-    @staticmethod
-    def from_i420(buf: torch.Tensor, height: int, width: int) -> "Yuv420":
-        """Views into a (T, H*W*3/2) I420 buffer (no copy)."""
-        n, cw, ch = height * width, width // 2, height // 2
-        return Yuv420(buf[:, :n].unflatten(1, (height, width)),
-                      buf[:, n:n + cw * ch].unflatten(1, (ch, cw)),
-                      buf[:, n + cw * ch:n + 2 * cw * ch].unflatten(1, (ch, cw)))
-
-    @staticmethod
-    def empty(n_frames: int, height: int, width: int, device="cuda") -> "Yuv420":
-        buf = torch.empty((n_frames, height * width * 3 // 2), dtype=torch.uint8, device=device)
-        return Yuv420.from_i420(buf, height, width)
-
-    @property
-    def planes(self):
-        return (self.y, self.u, self.v)
-
-    @property
-    def nbytes(self) -> int:
-        return sum(p.numel() for p in self.planes)
+from .yuv import Yuv420
 
 
 def move_planes(src: Yuv420, dst: Yuv420, mask: torch.Tensor, bs: int, small_bx: int, stretch_: bool,
@@ -246,60 +217,146 @@ class PresleyV2:
 
 
 class HostElvisV1:
-    """The headline path for callers whose frames live in HOST memory (the end-to-end API):
-    an I420 clip in, removal masks + shrunk I420 clip + stretched I420 clip out, all host
-    tensors.  Work is enqueued on one of `depth` private streams with its own device
-    buffers, so consecutive calls overlap one clip's device->host copies with the next
-    clip's host->device copy (full-duplex PCIe).  Pass pinned tensors to get async copies.
+    """The headline path for callers whose frames live in HOST memory (the end-to-end API): an
+    I420 clip in; removal masks, shrunk I420 clip and stretched I420 clip out, all host tensors.
+    Work is enqueued on one of `depth` private streams with its own device buffers, so consecutive
+    calls overlap one clip's device->host copies with the next clip's host->device copy
+    (full-duplex PCIe).  Pass pinned tensors to get async copies.
+
+    outputs selects what is produced and copied back: the reference's SERVER keeps
+    ("mask", "shrunk") -- it encodes the shrunk frames and ships the masks as a side channel
+    (elvis.py:4389-4418) -- while the stretched clip is the CLIENT's product (HostElvisClient;
+    elvis.py:4537-4557).  The default returns all three (the composite the benchmark's `e2e` times).
+    pack_masks=True returns np.packbits-compatible bit-packed masks (the side-channel format,
+    elvis.py:4412-4418), packed on the device.  score_fn(luma_with_halo_slots, slot_index) -> scores
+    replaces the local scorer (the frame-sharded scorer of elvis_b200.sharding); the clip's luma then
+    sits in slot["halo"], a HaloClip over the input buffer.
     """
 
     def __init__(self, n_frames: int, height: int, width: int, block_size: int = 16, shrink_amount: float = 0.5,
-                 alpha: float = 0.5, beta: float = 0.5, device="cuda", depth: int = 2):
+                 alpha: float = 0.5, beta: float = 0.5, device="cuda", depth: int = 2,
+                 outputs: Tuple[str, ...] = ("mask", "shrunk", "stretched"), pack_masks: bool = False, score_fn=None):
+        bad = set(outputs) - {"mask", "shrunk", "stretched"}
+        if bad or not outputs:
+            raise ValueError(f"outputs must be a non-empty subset of mask / shrunk / stretched, got {outputs}")
         self.pipe = ElvisV1(block_size, shrink_amount, alpha, beta)
         self.T, self.H, self.W = n_frames, height, width
         self.dev = torch.device(device)
+        self.outputs, self.pack_masks, self.score_fn = tuple(outputs), pack_masks, score_fn
         by, bx = height // block_size, width // block_size
+        self.by, self.bx = by, bx
         self.k = blocks_to_remove(shrink_amount, bx)
         self.sw = (bx - self.k) * block_size
+        self.frame_bytes = height * width * 3 // 2
         self.slots = []
+        from .sharding import HaloClip
         for _ in range(depth):
-            self.slots.append({
-                "stream": torch.cuda.Stream(self.dev),
-                "in": torch.empty((n_frames, height * width * 3 // 2), dtype=torch.uint8, device=self.dev),
-                "shrunk": torch.empty((n_frames, height * self.sw * 3 // 2), dtype=torch.uint8, device=self.dev),
-                "full": torch.empty((n_frames, height * width * 3 // 2), dtype=torch.uint8, device=self.dev),
-            })
+            # two spare frames around the clip: halo slots of the frame-sharded scorer (unused otherwise)
+            buf = torch.empty((n_frames + 2, self.frame_bytes), dtype=torch.uint8, device=self.dev)
+            slot = {"stream": torch.cuda.Stream(self.dev), "buf": buf, "in": buf[1:n_frames + 1],
+                    "halo": HaloClip(n_frames, height, width, self.dev, buf=buf[:, :height * width].unflatten(1, (height, width))),
+                    "shrunk": torch.empty((n_frames, height * self.sw * 3 // 2), dtype=torch.uint8, device=self.dev),
+                    "mask": torch.empty((n_frames, by, bx), dtype=torch.uint8, device=self.dev)}
+            if "stretched" in outputs:
+                slot["full"] = torch.empty((n_frames, self.frame_bytes), dtype=torch.uint8, device=self.dev)
+            if pack_masks:
+                slot["bits"] = torch.empty(((n_frames * by * bx + 7) // 8,), dtype=torch.uint8, device=self.dev)
+            self.slots.append(slot)
         self._next = 0
 
+    @property
+    def mask_bytes(self) -> int:
+        n = self.T * self.by * self.bx
+        return (n + 7) // 8 if self.pack_masks else n
+
     def host_buffers(self, pinned: bool = True):
-        """Convenience: (shrunk_i420, stretched_i420, masks) host tensors of the right shapes."""
-        by, bx = self.H // self.pipe.bs, self.W // self.pipe.bs
+        """Convenience: (shrunk_i420, stretched_i420, masks) host tensors of the right shapes (None for
+        outputs that were not requested)."""
         mk = lambda *s: torch.empty(s, dtype=torch.uint8, pin_memory=pinned)   # noqa: E731
-        return mk(self.T, self.H * self.sw * 3 // 2), mk(self.T, self.H * self.W * 3 // 2), mk(self.T, by, bx)
+        return (mk(self.T, self.H * self.sw * 3 // 2) if "shrunk" in self.outputs else None,
+                mk(self.T, self.frame_bytes) if "stretched" in self.outputs else None,
+                (mk(self.mask_bytes) if self.pack_masks else mk(self.T, self.by, self.bx)) if "mask" in self.outputs else None)
 
     @property
     def h2d_bytes(self) -> int:
-        return self.T * self.H * self.W * 3 // 2
+        return self.T * self.frame_bytes
 
     @property
     def d2h_bytes(self) -> int:
-        by, bx = self.H // self.pipe.bs, self.W // self.pipe.bs
-        return self.T * (self.H * self.sw * 3 // 2 + self.H * self.W * 3 // 2 + by * bx)
+        n = 0
+        if "shrunk" in self.outputs:
+            n += self.T * self.H * self.sw * 3 // 2
+        if "stretched" in self.outputs:
+            n += self.T * self.frame_bytes
+        if "mask" in self.outputs:
+            n += self.mask_bytes
+        return n
 
-    def process(self, i420_host: torch.Tensor, shrunk_host: torch.Tensor, stretched_host: torch.Tensor,
-                mask_host: torch.Tensor) -> torch.cuda.Event:
-        """Enqueue one clip; returns an event that fires when the three outputs are in host
+    def process(self, i420_host: torch.Tensor, shrunk_host: Optional[torch.Tensor] = None,
+                stretched_host: Optional[torch.Tensor] = None, mask_host: Optional[torch.Tensor] = None) -> torch.cuda.Event:
+        """Enqueue one clip; returns an event that fires when the requested outputs are in host
         memory.  Call .synchronize() on it (or on the device) before reading them."""
         slot = self.slots[self._next]
+        index = self._next
         self._next = (self._next + 1) % len(self.slots)
         with torch.cuda.stream(slot["stream"]):
             slot["in"].copy_(i420_host, non_blocking=True)
             clip = Yuv420.from_i420(slot["in"], self.H, self.W)
             shrunk = Yuv420.from_i420(slot["shrunk"], self.H, self.sw)
-            full = Yuv420.from_i420(slot["full"], self.H, self.W)
-            _, mask, _, _ = self.pipe.run(clip, shrunk_out=shrunk, stretched_out=full)
-            mask_host.copy_(mask, non_blocking=True)
-            shrunk_host.copy_(slot["shrunk"], non_blocking=True)
+            scores = self.score_fn(slot["halo"], index) if self.score_fn is not None else self.pipe.score(clip)
+            mask = ops.select_rows(scores, self.k, ops.REMOVE_HIGH, out=slot["mask"])
+            move_planes(clip, shrunk, mask, self.pipe.bs, self.bx - self.k, stretch_=False)
+            if "stretched" in self.outputs:
+                self.pipe.stretch(shrunk, mask, Yuv420.from_i420(slot["full"], self.H, self.W))
+                stretched_host.copy_(slot["full"], non_blocking=True)
+            if "mask" in self.outputs:
+                mask_host.copy_(ops.pack_mask_bits(mask, out=slot["bits"]) if self.pack_masks else mask, non_blocking=True)
+            if "shrunk" in self.outputs:
+                shrunk_host.copy_(slot["shrunk"], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        return done
+
+
+class HostElvisClient:
+    """The client side of the same flow for host buffers (elvis.py:4537-4557): shrunk I420 clip and the
+    bit-packed mask side channel in, stretched I420 clip (black placeholders for the inpainter) out."""
+
+    def __init__(self, n_frames: int, height: int, width: int, block_size: int = 16, shrink_amount: float = 0.5,
+                 device="cuda", depth: int = 2, packed_masks: bool = True):
+        self.bs, self.T, self.H, self.W = block_size, n_frames, height, width
+        self.dev = torch.device(device)
+        self.by, self.bx = height // block_size, width // block_size
+        self.k = blocks_to_remove(shrink_amount, self.bx)
+        self.sw = (self.bx - self.k) * block_size
+        self.packed_masks = packed_masks
+        n = n_frames * self.by * self.bx
+        self.mask_bytes = (n + 7) // 8 if packed_masks else n
+        self.slots = [{"stream": torch.cuda.Stream(self.dev),
+                       "shrunk": torch.empty((n_frames, height * self.sw * 3 // 2), dtype=torch.uint8, device=self.dev),
+                       "mask_in": torch.empty((self.mask_bytes,), dtype=torch.uint8, device=self.dev),
+                       "full": torch.empty((n_frames, height * width * 3 // 2), dtype=torch.uint8, device=self.dev)}
+                      for _ in range(depth)]
+        self._next = 0
+
+    @property
+    def h2d_bytes(self) -> int:
+        return self.T * self.H * self.sw * 3 // 2 + self.mask_bytes
+
+    @property
+    def d2h_bytes(self) -> int:
+        return self.T * self.H * self.W * 3 // 2
+
+    def process(self, shrunk_host: torch.Tensor, mask_host: torch.Tensor, stretched_host: torch.Tensor) -> torch.cuda.Event:
+        slot = self.slots[self._next]
+        self._next = (self._next + 1) % len(self.slots)
+        with torch.cuda.stream(slot["stream"]):
+            slot["shrunk"].copy_(shrunk_host, non_blocking=True)
+            slot["mask_in"].copy_(mask_host.reshape(-1), non_blocking=True)
+            shape = (self.T, self.by, self.bx)
+            mask = ops.unpack_mask_bits(slot["mask_in"], shape) if self.packed_masks else slot["mask_in"].view(shape)
+            move_planes(Yuv420.from_i420(slot["shrunk"], self.H, self.sw), Yuv420.from_i420(slot["full"], self.H, self.W), mask,
+                        self.bs, self.bx - self.k, stretch_=True)
             stretched_host.copy_(slot["full"], non_blocking=True)
             done = torch.cuda.Event()
             done.record()

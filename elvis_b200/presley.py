@@ -29,16 +29,15 @@ class Complexities:
 
 
 def rgb_to_luma(frames: torch.Tensor) -> torch.Tensor:
-    """(T, H, W, 3) uint8 RGB -> (T, H, W) uint8 BT.601 luma, cv2.COLOR_RGB2GRAY's fixed-point
-    rule (R*4899 + G*9617 + B*1868 + 8192) >> 14."""
-    f = frames.to(torch.int32)
-    y = (f[..., 0] * 4899 + f[..., 1] * 9617 + f[..., 2] * 1868 + 8192) >> 14
-    return y.to(torch.uint8)
+    """(T, H, W, 3) uint8 RGB -> (T, H, W) uint8 luma on the GPU: cv2.COLOR_RGB2GRAY's 15-bit fixed
+    point, (9798 R + 19235 G + 3735 B + 2^14) >> 15 (pinned against cv2 in tests/test_oracle.py)."""
+    return ops.rgb_to_gray(frames)
 
 
 def analyze_frames(frames: np.ndarray, config: EVCAConfig) -> Complexities:
     """Stand-in for `evca.analyze_frames(np.array(frames), EVCAConfig(block_size=bs))`
-    (presley.py:202): per-block SC/TC of the clip's luma, float64 (T, By, Bx)."""
+    (presley.py:202): per-block SC/TC of the clip's luma, float64 (T, By, Bx).  frames: (T, H, W)
+    luma or (T, H, W, 3) RGB uint8."""
     f = _to_dev(np.asarray(frames), np.uint8)
     y = f if f.dim() == 3 else rgb_to_luma(f)
     sc, tc, _ = ops.score_sc_tc(y.contiguous(), config.block_size, dct_size=config.dct_size)
@@ -69,18 +68,22 @@ def shrink_video_frames(frames: List[np.ndarray], importance_scores: List[np.nda
 
 
 def stretch_video_frames(shrunken_frames: List[np.ndarray], removal_masks: List[np.ndarray], block_size: int) -> List[np.ndarray]:
-    """presley.py:787-827 (row-major refill == per-row refill because every row of a
-    row-only shrink keeps the same number of blocks)."""
+    """presley.py:787-827: the kept positions of a frame take the shrunk blocks back in ROW-MAJOR
+    order over the whole frame (kept block i <- shrunk block (i // sbx, i % sbx), bounds-guarded).
+    That equals the per-row refill of utils.stretch_frame_row_only only when every row kept the same
+    number of blocks; after a partial last shrink pass (int(By*Bx*shrink) % By != 0) the rows differ
+    and blocks wrap across rows, exactly as in the reference."""
     if len(shrunken_frames) == 0:
         return []
     masks = _to_dev(np.stack([np.asarray(m) != 0 for m in removal_masks]), np.uint8)
     clip = _to_dev(np.stack(shrunken_frames), np.uint8)
+    by, bx = masks.shape[1:]
     sby, sbx = clip.shape[1] // block_size, clip.shape[2] // block_size
-    if sbx == 0:
-        by, bx = masks.shape[1:]
+    if sbx == 0 or sby == 0:
         z = np.zeros((by * block_size, bx * block_size) + tuple(clip.shape[3:]), np.uint8)
         return [z.copy() for _ in shrunken_frames]
-    out = ops.stretch(clip[:, :sby * block_size, :sbx * block_size], masks, block_size).cpu().numpy()
+    refill = ops.refill_map(masks, sby * sbx)
+    out = ops.gather_blocks(clip[:, :sby * block_size, :sbx * block_size], refill, block_size, by, bx).cpu().numpy()
     return [out[i] for i in range(len(shrunken_frames))]
 
 

@@ -26,6 +26,12 @@ def frame_range(n_frames: int, rank: int, world: int) -> Tuple[int, int]:
     return a, a + base + (1 if rank < extra else 0)
 
 
+def check_shardable(n_frames: int, world: int) -> None:
+    """Every rank must own at least one frame (the same verdict on every rank, so nobody hangs)."""
+    if n_frames < world:
+        raise ValueError(f"{n_frames} frames cannot be sharded over {world} ranks: every rank needs at least one frame")
+
+
 class HaloClip:
     """A rank's luma frames with one halo slot on each side, so that received halos land in
     place and the scoring kernel sees one contiguous extended clip (no concatenation copy).
@@ -35,9 +41,13 @@ class HaloClip:
         buf[n+1]          Y[b]     (valid iff rank < world-1)
     """
 
-    def __init__(self, n_local: int, height: int, width: int, device, pin: bool = False):
+    def __init__(self, n_local: int, height: int, width: int, device, pin: bool = False, buf: Optional[torch.Tensor] = None):
+        """buf: optional caller-owned (n_local + 2, H, W) uint8 view (frames may be strided, e.g. the luma
+        of an I420 buffer; each frame must be contiguous so that it can be sent as one message)."""
         self.n = n_local
-        self.buf = torch.empty((n_local + 2, height, width), dtype=torch.uint8, device=device)
+        if buf is not None and (tuple(buf.shape) != (n_local + 2, height, width) or not buf[0].is_contiguous()):
+            raise ValueError("buf must be (n_local + 2, H, W) with contiguous frames")
+        self.buf = buf if buf is not None else torch.empty((n_local + 2, height, width), dtype=torch.uint8, device=device)
 
     @property
     def owned(self) -> torch.Tensor:
@@ -53,8 +63,12 @@ class HaloClip:
 def exchange_halo(clip: HaloClip, rank: int, world: int, group=None) -> None:
     """Send my first/last owned frame to the previous/next rank and receive theirs into the
     halo slots.  One batched isend/irecv group => a single NCCL group call."""
-    if world == 1 or clip.n == 0:
+    if world == 1:
         return
+    if clip.n == 0:
+        # frame_range gives a rank no frames when n_frames < world; its neighbours would still post
+        # sends / receives to it and wait for ever
+        raise ValueError("a rank without frames cannot take part in the halo exchange: shard over at most n_frames ranks")
     ops = []
     if rank > 0:
         ops.append(dist.P2POp(dist.isend, clip.buf[1], rank - 1, group))
@@ -95,6 +109,7 @@ def sharded_removability(clip: HaloClip, n_frames_total: int, block_size: int, a
     caller has already run exchange_halo (e.g. ahead of time on a communication stream)."""
     if kernels is None:
         from . import ops as kernels
+    check_shardable(n_frames_total, world)
     if exchange:
         exchange_halo(clip, rank, world, group)
     ext, first = clip.extended(rank, world)

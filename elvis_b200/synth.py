@@ -9,7 +9,7 @@ import math
 
 import torch
 
-from .pipeline import Yuv420
+from .yuv import Yuv420
 
 
 def synth_yuv420(n_frames: int, height: int, width: int, seed: int = 1234, device="cuda",

@@ -143,9 +143,10 @@ def stretch_frame_removal_indices(shrunk_frame: np.ndarray, removal_indices: lis
 
 def _block_importance(importance: np.ndarray, by: int, bx: int) -> np.ndarray:
     importance = np.asarray(importance)
-    if importance.shape != (by, bx):   # utils.py:1127-1128 (host-side map resize, rarely taken)
-        import cv2
-        importance = cv2.resize(importance, (bx, by), interpolation=cv2.INTER_LINEAR)
+    if importance.shape != (by, bx):   # utils.py:1127-1128: cv2.resize(map, (bx, by), INTER_LINEAR), on the GPU
+        if importance.ndim != 2 or importance.dtype not in (np.float32, np.float64):
+            raise TypeError("importance map must be a 2-D float32 / float64 array")
+        importance = ops.resize_linear_float(_to_dev(importance)[None], by, bx)[0].cpu().numpy()
     return importance
 
 

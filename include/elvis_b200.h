@@ -12,7 +12,9 @@
  *   - every pointer is a DEVICE pointer unless the parameter name starts with `host_`;
  *   - nothing here allocates, frees or synchronises; all work is enqueued on `stream`
  *     (a cudaStream_t passed as void*; NULL = the legacy default stream);
- *   - all entry points are re-entrant (no global mutable state);
+ *   - all entry points are re-entrant and may be used on several devices of one process: the
+ *     only process-wide state is a per-device cache of idempotent facts (SM count, opt-in
+ *     kernel attributes already set), kernels are launched on the CURRENT device;
  *   - the return value is ELVIS_OK (0) or a negative ELVIS_ERR_* code; for ELVIS_ERR_CUDA
  *     the failing cudaError_t is returned by elvis_last_cuda_error() (thread local);
  *   - clips are batched: leading dimension T (frames); the reference's per-frame calls are
@@ -28,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ELVIS_B200_ABI_VERSION 3
+#define ELVIS_B200_ABI_VERSION 4
 
 #define ELVIS_OK               0
 #define ELVIS_ERR_INVALID_ARG (-1)   /* NULL pointer, non-positive size, out-of-range parameter   */
@@ -215,7 +217,8 @@ ELVIS_API int elvis_temporal_blend(const elvis_plane* clip, int32_t n_frames, do
 /* ---- a13: side-channel packers.  Bit packing is np.packbits-compatible (elvis.py:4414):
  * flat over n values, MSB first, last byte zero padded.  The 2-bit level packer is new
  * (README.md:50 TODO): per row of bx levels, ceil(bx/4) bytes, level i in bits
- * 2*(i%4).. of byte i/4. */
+ * 2*(i%4).. of byte i/4; levels saturate to 0..3 (the reference's level 4 = 16x at block
+ * size 16, elvis.py:2146, is kept as 8x). */
 ELVIS_API int elvis_pack_mask_bits(const uint8_t* mask, int64_t n, uint8_t* packed, elvis_stream_t stream);
 ELVIS_API int elvis_unpack_mask_bits(const uint8_t* packed, int64_t n, uint8_t* mask, elvis_stream_t stream);
 ELVIS_API int elvis_pack_levels_2bit(const int32_t* levels, int64_t rows, int32_t bx, uint8_t* packed,
@@ -319,6 +322,27 @@ ELVIS_API int elvis_gray_to_levels(const uint8_t* gray, int64_t n, float min_val
  * min(floor(d * (1.0 / (dsize / ssize))), ssize - 1) in double (elvis_b200/_tables.py:nearest_index). */
 ELVIS_API int elvis_resize_nearest(const void* src, int32_t elem_bytes, int32_t n_maps, int32_t src_h, int32_t src_w, void* dst,
                          int32_t dst_h, int32_t dst_w, const int32_t* y_idx, const int32_t* x_idx, elvis_stream_t stream);
+
+/* cv2.resize(map, (dst_w, dst_h), INTER_LINEAR) of n_maps dense float32 / float64 block-level maps
+ * (dtype = ELVIS_F32 / ELVIS_F64): the importance map whose grid differs from the frame's
+ * (utils.py:1127-1128, 1197-1198) and the x265 QP map when the CTU grid is finer than the block
+ * grid (elvis.py:2068-2073).  cv2's fused lerp, horizontal then vertical; y_/x_index and
+ * y_/x_frac are the source index and fraction per destination row / column
+ * (elvis_b200/_tables.py:linear_float_index). */
+ELVIS_API int elvis_resize_linear_float(const void* src, int32_t dtype, int32_t n_maps, int32_t src_h, int32_t src_w, void* dst,
+                              int32_t dst_h, int32_t dst_w, const int32_t* y_index, const double* y_frac,
+                              const int32_t* x_index, const double* x_frac, elvis_stream_t stream);
+
+/* Luma of packed RGB frames for the scoring stage when the caller holds RGB frames
+ * (presley.py:184-202: `analyze_frames(np.array(frames), ...)`): cv2.COLOR_RGB2GRAY's 15-bit
+ * fixed point, (9798 R + 19235 G + 3735 B + 2^14) >> 15.  rgb: channels = 3; y: channels = 1. */
+ELVIS_API int elvis_rgb_to_gray(const elvis_plane* rgb, const elvis_plane* y, int32_t n_frames, elvis_stream_t stream);
+
+/* Row-major refill map of stretch_video_frames (presley.py:806-819): map[t][i] = rank of block i
+ * among the kept blocks (mask == 0) of frame t in row-major order, or -1 for removed blocks and for
+ * kept blocks whose rank is >= capacity (= shrunk_by * shrunk_bx).  Feed it to elvis_gather_blocks. */
+ELVIS_API int elvis_refill_map(const uint8_t* mask, int32_t n_frames, int64_t blocks_per_frame, int64_t capacity, int32_t* map,
+                     elvis_stream_t stream);
 
 #ifdef __cplusplus
 }

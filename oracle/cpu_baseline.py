@@ -75,12 +75,64 @@ class CpuElvisV1:
         parts = mapper(_score_chunk, _chunks(self.T, self.workers))
         sc = np.concatenate([p[0] for p in parts])
         tc = np.concatenate([p[1] for p in parts])
+        self.sc, self.tc = sc, tc
         _G["scores"][:] = P.combine_removability(sc, tc, self.alpha, self.beta)
         mapper(_move_chunk, _chunks(self.T, self.workers))
         return time.perf_counter() - t0
 
     def outputs(self):
-        return {k: _G[k] for k in ("scores", "mask", "sy", "su", "sv", "fy", "fu", "fv")}
+        out = {k: _G[k] for k in ("scores", "mask", "sy", "su", "sv", "fy", "fu", "fv")}
+        out.update(in_y=_G["y"], in_u=_G["u"], in_v=_G["v"], sc=self.sc, tc=self.tc)
+        return out
+
+    def close(self):
+        if self.pool:
+            self.pool.close()
+            self.pool.join()
+            self.pool = None
+
+
+# ------------------------------------------------------------------ v2 degradations (configs[2], configs[3])
+def _v2_chunk(ab):
+    a, b = ab
+    bs, kind = _G["bs"], _G["kind"]
+    for t in range(a, b):
+        m = _G["map"][t]
+        for name, pb in (("y", bs), ("u", bs // 2), ("v", bs // 2)):
+            src = _G[name][t]
+            if kind == "blur":
+                out = P.blur_plane(src, m, pb)
+            elif kind == "downsample":
+                out = P.downsample_plane(src, np.where(m > 0, np.maximum(1, pb >> m), pb), pb)
+            else:
+                from . import spec_dct_dampen
+                out = spec_dct_dampen.dampen_plane(src, m, pb)
+            _G["o" + name][t] = out
+    return b - a
+
+
+class CpuV2:
+    """One v2 degradation of a planar clip with every host core: kind = "blur" (rounds map int32,
+    elvis.py:2171-2196), "downsample" (pow2 level map int32, elvis.py:2141-2169) or "dampen" (strength
+    map float, oracle/spec_dct_dampen.py); chroma blocks at half the block size."""
+
+    def __init__(self, y, u, v, block_map, block_size=16, kind="blur", workers=None):
+        self.workers = workers or os.cpu_count() or 1
+        self.T = y.shape[0]
+        _G.clear()
+        _G.update(y=y, u=u, v=v, bs=block_size, kind=kind, map=block_map)
+        for name, pl in (("y", y), ("u", u), ("v", v)):
+            _G["o" + name] = _shared(pl.shape)
+        self.pool = mp.get_context("fork").Pool(self.workers) if self.workers > 1 else None
+
+    def step(self) -> float:
+        t0 = time.perf_counter()
+        mapper = self.pool.map if self.pool else lambda f, xs: list(map(f, xs))
+        mapper(_v2_chunk, _chunks(self.T, self.workers))
+        return time.perf_counter() - t0
+
+    def outputs(self):
+        return {k: _G["o" + k] for k in ("y", "u", "v")}
 
     def close(self):
         if self.pool:

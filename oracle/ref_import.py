@@ -48,3 +48,30 @@ def load(name: str):
     spec.loader.exec_module(mod)
     _cache[name] = mod
     return mod
+
+
+def load_presley_functions(*names: str) -> dict:
+    """presley.py cannot be imported (it runs its experiment at import time), but its hot-path
+    functions are self-contained: compile the UNMODIFIED definitions of `names` out of the file's AST
+    into a fresh namespace holding numpy / cv2 / typing.  Nothing is copied into this repository."""
+    import ast
+    import typing
+    import numpy as np
+    key = ("presley",) + names
+    if key in _cache:
+        return _cache[key]
+    path = os.path.join(REFERENCE_ROOT, "presley.py")
+    tree = ast.parse(open(path).read(), path)
+    wanted = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    if {n.name for n in wanted} != set(names):
+        raise KeyError(f"presley.py lacks {set(names) - {n.name for n in wanted}}")
+    ns: dict = {"np": np, "List": typing.List, "Tuple": typing.Tuple, "Any": typing.Any, "Callable": typing.Callable,
+                "Optional": typing.Optional, "Dict": typing.Dict}
+    try:
+        import cv2
+        ns["cv2"] = cv2
+    except ImportError:
+        pass
+    exec(compile(ast.Module(body=wanted, type_ignores=[]), path, "exec"), ns)
+    _cache[key] = {n: ns[n] for n in names}
+    return _cache[key]

@@ -311,3 +311,75 @@ def rgb_to_i420(frame: np.ndarray) -> np.ndarray:
     u = (-155188 * rs - 305135 * gs + 460324 * bs + half + (128 << sh)) >> sh
     v = (460324 * rs - 385875 * gs - 74448 * bs + half + (128 << sh)) >> sh
     return np.concatenate([y.reshape(-1), u.reshape(-1), v.reshape(-1)]).astype(np.uint8).reshape(h * 3 // 2, w)
+
+
+# ----------------------------------------------------------------------------- float INTER_LINEAR, RGB2GRAY
+def _fma(a: np.ndarray, b: float, c: np.ndarray, dtype) -> np.ndarray:
+    """Elementwise fused a * b + c with ONE rounding to `dtype` (exact rational arithmetic)."""
+    from fractions import Fraction
+    out = np.empty(a.shape, dtype)
+    fo, fa, fc, fb = out.reshape(-1), a.reshape(-1), c.reshape(-1), Fraction(float(b))
+    for i in range(fa.size):
+        v = Fraction(float(fa[i])) * fb + Fraction(float(fc[i]))
+        if dtype == np.float64:
+            fo[i] = float(v)
+        else:                                  # round the exact value to float32 once (no double rounding)
+            d = float(v)
+            f = np.float32(d)
+            if Fraction(float(f)) != v:        # d -> f may have rounded a half-way case the wrong way
+                lo, hi = (np.nextafter(f, np.float32(-np.inf)), f) if Fraction(float(f)) > v else (f, np.nextafter(f, np.float32(np.inf)))
+                dl, dh = v - Fraction(float(lo)), Fraction(float(hi)) - v
+                if dl != dh:
+                    f = lo if dl < dh else hi
+                else:                          # tie: even mantissa
+                    f = lo if (lo.view(np.uint32) & 1) == 0 else hi
+            fo[i] = f
+    return out
+
+
+def linear_float_coords(ssize: int, dsize: int, fused: bool):
+    """[(source index, fraction)] per destination index of cv2.resize(float map, INTER_LINEAR).
+    Coordinate (d + 0.5) * (ssize / dsize) - 0.5 in double -- evaluated as ONE fused multiply-add on
+    cv2's float64 path (`fused`), as a rounded product and a rounded difference on its float32 path
+    (both pinned against cv2 4.13: the two differ where the product lands within an ulp of x.5) --
+    then index = floor, fraction = coordinate - index, clamped with a zero fraction at the borders."""
+    from fractions import Fraction
+    scale = ssize / dsize
+    out = []
+    for d in range(dsize):
+        fx = float(Fraction(2 * d + 1, 2) * Fraction(scale) - Fraction(1, 2)) if fused else (d + 0.5) * scale - 0.5
+        s = int(np.floor(fx))
+        f = fx - s
+        if s < 0:
+            s, f = 0, 0.0
+        if s >= ssize - 1:
+            s, f = ssize - 1, 0.0
+        out.append((s, f))
+    return out
+
+
+def resize_linear_float(src: np.ndarray, dh: int, dw: int) -> np.ndarray:
+    """cv2.resize(src, (dw, dh), interpolation=INTER_LINEAR) for a 2-D float32 / float64 map with at
+    least two rows and two columns (utils.py:1127-1128, 1197-1198; elvis.py:2068-2073): fused lerp
+    x0 + (x1 - x0) * f with the difference rounded first, horizontal pass then vertical pass; float32
+    maps use float32 fractions.  (Single-row / single-column sources take another cv2 path: not restated.)"""
+    dtype = src.dtype.type
+    sh, sw = src.shape
+    if sh < 2 or sw < 2:
+        raise NotImplementedError("single-row / single-column source maps")
+    fused = dtype == np.float64
+    rows = np.empty((sh, dw), dtype)
+    for x, (s, f) in enumerate(linear_float_coords(sw, dw, fused)):
+        x0, x1 = src[:, s], src[:, min(s + 1, sw - 1)]
+        rows[:, x] = _fma((x1 - x0).astype(dtype), float(dtype(f)), x0, dtype)
+    out = np.empty((dh, dw), dtype)
+    for y, (s, f) in enumerate(linear_float_coords(sh, dh, fused)):
+        r0, r1 = rows[s], rows[min(s + 1, sh - 1)]
+        out[y] = _fma((r1 - r0).astype(dtype), float(dtype(f)), r0, dtype)
+    return out
+
+
+def rgb_to_gray(frame: np.ndarray) -> np.ndarray:
+    """cv2.cvtColor(frame, COLOR_RGB2GRAY) for uint8 (..., 3): 15-bit fixed point."""
+    x = frame.astype(np.int64)
+    return ((x[..., 0] * 9798 + x[..., 1] * 19235 + x[..., 2] * 3735 + (1 << 14)) >> 15).astype(np.uint8)

@@ -144,6 +144,43 @@ def main():
         g["f4_levels"] = lv
         g["f4_gray"], g["f4_decoded"] = reference_map_video_arithmetic(E, lv, "gaussian", 16, td)
 
+    # ---- round 2 additions (appended so that the random stream of everything above is unchanged)
+    # a7 -- presley batch shrink / stretch incl. partial last passes (row-major refill, presley.py:787-827)
+    PF = ref_import.load_presley_functions("shrink_frame_row_only", "shrink_video_frames", "stretch_video_frames")
+    pframes = [rng.integers(0, 256, (43, 59, 3), dtype=np.uint8) for _ in range(2)]
+    g["p7_frames"] = np.stack(pframes)
+    for tag, amount in (("q25", 0.25), ("q33", 0.33), ("q50", 0.5), ("q60", 0.6)):
+        imps = [np.round(rng.random((5, 7)) * 16) / 16 for _ in range(2)]
+        g[f"p7_imp_{tag}"] = np.stack(imps)
+        small, masks = PF["shrink_video_frames"](pframes, imps, 8, amount, PF["shrink_frame_row_only"])
+        g[f"p7_small_{tag}"], g[f"p7_mask_{tag}"] = np.stack(small), np.stack(masks)
+        g[f"p7_full_{tag}"] = np.stack(PF["stretch_video_frames"](small, masks, 8))
+
+    # utils degradations with an importance map whose grid differs from the frame's (cv2 float64 INTER_LINEAR)
+    im3 = rng.integers(0, 256, (16 * 3 + 3, 16 * 4 + 5, 3), dtype=np.uint8)
+    g["a10m_img"] = im3
+    for tag, shape in (("up", (2, 3)), ("down", (7, 9))):
+        imp = rng.random(shape)
+        g[f"a10m_imp_{tag}"] = imp
+        g[f"a10m_out_{tag}"], g[f"a10m_map_{tag}"] = U.degrade_adaptive_downsample(im3, imp, 16)
+        g[f"a11m_out_{tag}"], g[f"a11m_map_{tag}"] = U.degrade_adaptive_blur(im3, imp, 16)
+
+    # x265 qpfile with a CTU grid finer than the block grid (block 128 > CTU 64: cv2 float32 INTER_LINEAR)
+    with tempfile.TemporaryDirectory() as td:
+        ql = rng.random((2, 3, 5))
+        g["f3_scores_lin"] = ql
+        g["f3_qpfile_lin"] = np.frombuffer(reference_qpfile(E, ql, 128, 640, 384, os.path.join(td, "ql")).encode(), np.uint8)
+
+    # cv2 primitives the round-2 kernels restate, frozen from the cv2 of this image
+    for tag, dt in (("f32", np.float32), ("f64", np.float64)):
+        m = (rng.random((9, 16)) * 2 - 0.5).astype(dt)
+        g[f"lin_src_{tag}"] = m
+        g[f"lin_up_{tag}"] = cv2.resize(m, (33, 27), interpolation=cv2.INTER_LINEAR)
+        g[f"lin_down_{tag}"] = cv2.resize(m, (7, 4), interpolation=cv2.INTER_LINEAR)
+    rgbg = rng.integers(0, 256, (2, 21, 37, 3), dtype=np.uint8)
+    g["gray_rgb"] = rgbg
+    g["gray_out"] = np.stack([cv2.cvtColor(f, cv2.COLOR_RGB2GRAY) for f in rgbg])
+
     out = os.path.join(HERE, "reference_vectors.npz")
     np.savez_compressed(out, **g)
     print(f"wrote {out}: {len(g)} arrays, {os.path.getsize(out) / 1024:.1f} KiB")

@@ -20,8 +20,8 @@ class _Impl:
         if kind == "gpu":
             import torch
             assert torch.cuda.is_available()
-            from elvis_b200 import elvis, utils
-            self.E, self.U = elvis, utils
+            from elvis_b200 import elvis, presley, utils
+            self.E, self.U, self.Pr = elvis, utils, presley
 
     def removability(self, sc, tc, alpha, beta, bg):
         if self.kind == "gpu":
@@ -39,8 +39,10 @@ class _Impl:
 
     def __getattr__(self, name):
         if self.kind == "gpu":
-            mod = self.E if hasattr(self.E, name) else self.U
-            return getattr(mod, name)
+            for mod in (self.E, self.U, self.Pr):
+                if hasattr(mod, name):
+                    return getattr(mod, name)
+            raise AttributeError(name)
         return getattr(P, name)
 
 
@@ -119,8 +121,37 @@ def _check_all(impl):
             assert np.array_equal(out, G[f"{key}_out_{bs}"]), (fn, bs)
 
 
+def _check_round2(impl):
+    """Vectors added in round 2: presley batch stretch (row-major refill, partial passes), utils
+    degradations with a mismatched importance grid, the qpfile's INTER_LINEAR branch."""
+    frames = list(G["p7_frames"])
+    for tag, amount in (("q25", 0.25), ("q33", 0.33), ("q50", 0.5), ("q60", 0.6)):
+        small, masks = list(G[f"p7_small_{tag}"]), list(G[f"p7_mask_{tag}"])
+        if impl.kind == "gpu":
+            got_small, got_masks = impl.shrink_video_frames(frames, list(G[f"p7_imp_{tag}"]), 8, amount, impl.Pr.shrink_frame_row_only)
+            assert np.array_equal(np.stack(got_small), G[f"p7_small_{tag}"]), tag
+            assert got_masks[0].dtype == bool and np.array_equal(np.stack(got_masks), G[f"p7_mask_{tag}"]), tag
+        assert np.array_equal(np.stack(impl.stretch_video_frames(small, masks, 8)), G[f"p7_full_{tag}"]), tag
+    for tag in ("up", "down"):
+        for fn, key in (("degrade_adaptive_downsample", "a10m"), ("degrade_adaptive_blur", "a11m")):
+            out, lv = getattr(impl, fn)(G["a10m_img"], G[f"a10m_imp_{tag}"], 16)
+            assert np.array_equal(lv, G[f"{key}_map_{tag}"]), (fn, tag)
+            assert np.array_equal(out, G[f"{key}_out_{tag}"]), (fn, tag)
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "f")
+        impl.write_per_block_qpfile(G["f3_scores_lin"], 128, 640, 384, path)
+        assert open(path, "rb").read() == G["f3_qpfile_lin"].tobytes()
+
+
 def test_oracle_reproduces_golden_vectors():
     _check_all(_Impl("oracle"))
+    _check_round2(_Impl("oracle"))
+    from oracle import spec_cv
+    for tag in ("f32", "f64"):
+        assert np.array_equal(spec_cv.resize_linear_float(G[f"lin_src_{tag}"], 27, 33), G[f"lin_up_{tag}"])
+        assert np.array_equal(spec_cv.resize_linear_float(G[f"lin_src_{tag}"], 4, 7), G[f"lin_down_{tag}"])
+    assert np.array_equal(spec_cv.rgb_to_gray(G["gray_rgb"]), G["gray_out"])
     packed, shape = P.pack_masks(G["a13_masks"])
     assert np.array_equal(packed, G["a13_packed"])
     assert np.array_equal(P.unpack_masks(packed, shape), G["a13_masks"])
@@ -130,6 +161,14 @@ def test_oracle_reproduces_golden_vectors():
 def test_cuda_reproduces_golden_vectors():
     impl = _Impl("gpu")
     _check_all(impl)
+    _check_round2(impl)
+    import torch
+    from elvis_b200 import ops
+    for tag in ("f32", "f64"):
+        src = torch.from_numpy(G[f"lin_src_{tag}"]).cuda()[None]
+        assert np.array_equal(ops.resize_linear_float(src, 27, 33)[0].cpu().numpy(), G[f"lin_up_{tag}"])
+        assert np.array_equal(ops.resize_linear_float(src, 4, 7)[0].cpu().numpy(), G[f"lin_down_{tag}"])
+    assert np.array_equal(ops.rgb_to_gray(torch.from_numpy(G["gray_rgb"]).cuda()).cpu().numpy(), G["gray_out"])
     packed, shape = impl.E.pack_removal_masks(G["a13_masks"])
     assert np.array_equal(packed, G["a13_packed"])
     assert np.array_equal(impl.E.unpack_removal_masks(packed, shape), G["a13_masks"])

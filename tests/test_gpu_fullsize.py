@@ -143,3 +143,38 @@ def test_rowcol_properties_full_size(torch_dev):
     grid = ops.rowcol_expand(pidx[:, :40].contiguous(), pcnt[:, :40].contiguous(), fby, fbx)
     assert grid.shape == (1, by, bx) and int((grid >= 0).sum()) == fby * fbx
     assert torch.equal(grid[grid >= 0].sort().values, torch.arange(fby * fbx, device=dev, dtype=torch.int32))
+
+
+def test_v1_benchmark_config_vs_oracle_value_for_value(torch_dev):
+    """BASELINE.json configs[1] -- 4K x 120 frames, 16x16 blocks, 50 % removal -- through the default
+    path (tcgen05 scoring kernel, multi-chunk schedule) against the oracle on ALL 120 frames: SC/TC
+    within rtol 1e-4 (+ 1e-6 of the SC range for flat blocks), scores within 2e-6 absolute, masks equal
+    wherever the oracle's own decision margin exceeds 1e-5, shrunk and stretched planes bit for bit.
+    The oracle runs on every host core through the fork pool of oracle/cpu_baseline.py (seconds)."""
+    import numpy as np
+    torch, dev = torch_dev
+    from elvis_b200 import ops
+    from elvis_b200.pipeline import ElvisV1
+    from elvis_b200.synth import synth_yuv420
+    from oracle import verify
+    from oracle.cpu_baseline import CpuElvisV1
+    T, H, W, bs, amount = 120, 2160, 3840, 16, 0.5
+    clip = synth_yuv420(T, H, W, seed=1234, device=dev)
+    sc, tc, _ = ops.score_sc_tc(clip.y, bs)
+    scores, mask, shrunk, full = ElvisV1(bs, amount, 0.5, 0.5).run(clip)
+    torch.cuda.synchronize()
+    y, u, v = (p.cpu().numpy() for p in clip.planes)
+    cpu = CpuElvisV1(y, u, v, bs, amount, 0.5, 0.5)
+    try:
+        cpu.step()
+        ref = cpu.outputs()
+        np.testing.assert_allclose(tc.cpu().numpy(), ref["tc"], rtol=1e-4, atol=1e-6 * float(ref["tc"].max()))
+        np.testing.assert_allclose(sc.cpu().numpy(), ref["sc"], rtol=1e-4, atol=1e-6 * float(ref["sc"].max()))
+        got = {"scores": scores.cpu().numpy(), "mask": mask.cpu().numpy()}
+        for tag, s_, f_ in (("y", shrunk.y, full.y), ("u", shrunk.u, full.u), ("v", shrunk.v, full.v)):
+            got["s" + tag], got["f" + tag] = s_.cpu().numpy(), f_.cpu().numpy()
+        verdict = verify.compare_v1(got, ref, bs, int(amount * (W // bs)))
+    finally:
+        cpu.close()
+    assert verdict["ok"], verdict
+    assert verdict["frames_with_identical_mask"] >= T - 2, verdict      # near-ties are rare on this content

@@ -782,3 +782,110 @@ def test_lanczos_restorer_elvis(dev, bs):
     assert np.array_equal(E.restore_downsample_opencv_lanczos(img, maps, bs), P.restore_downsample_opencv_lanczos(img, maps, bs))
     zero = np.zeros((3, 5), int)
     assert E.restore_downsample_opencv_lanczos(img, zero, bs) is img
+
+
+# ---------------------------------------------------------------------------------- round 2
+def test_analyze_frames_rgb_and_luma(dev):
+    """presley.analyze_frames (the stand-in for evca.analyze_frames, presley.py:202): RGB input goes
+    through the cv2-exact luma kernel, luma input is used as is; SC/TC against the spec."""
+    from elvis_b200 import presley
+    from oracle import spec_cv
+    rng = np.random.default_rng(21)
+    rgb = np.clip(rng.normal(128, 50, (5, 64, 96, 3)), 0, 255).astype(np.uint8)
+    rgb[1:] = np.roll(rgb[:-1], 3, axis=2) // 2 + rgb[1:] // 2
+    luma = spec_cv.rgb_to_gray(rgb)
+    got_luma = presley.rgb_to_luma(to_dev(rgb, dev)).cpu().numpy()
+    assert np.array_equal(got_luma, luma)
+    for bs in (8, 16):
+        cx = presley.analyze_frames(list(rgb), presley.EVCAConfig(block_size=bs))
+        rsc, rtc = spec_scoring.sc_tc(luma, bs)
+        assert cx.SC.dtype == np.float64 and cx.SC.shape == rsc.shape
+        np.testing.assert_allclose(cx.SC, rsc, rtol=RTOL, atol=0)
+        np.testing.assert_allclose(cx.TC, rtc, rtol=RTOL, atol=0)
+        cy = presley.analyze_frames(luma, presley.EVCAConfig(block_size=bs))
+        assert np.array_equal(cx.SC, cy.SC) and np.array_equal(cx.TC, cy.TC)
+    # odd widths take the byte path of the luma kernel; strided frames
+    odd = rng.integers(0, 256, (2, 9, 13, 3), dtype=np.uint8)
+    assert np.array_equal(presley.rgb_to_luma(to_dev(odd, dev)).cpu().numpy(), spec_cv.rgb_to_gray(odd))
+    wide = to_dev(rng.integers(0, 256, (2, 10, 40, 3), dtype=np.uint8), dev)
+    view = wide[:, 1:9, 4:36]
+    from elvis_b200 import ops
+    assert np.array_equal(ops.rgb_to_gray(view).cpu().numpy(), spec_cv.rgb_to_gray(view.cpu().numpy()))
+
+
+@pytest.mark.parametrize("by,bx,bs,amount", [(5, 7, 8, 0.25), (5, 7, 8, 0.33), (5, 7, 8, 0.5), (4, 6, 4, 0.5), (3, 9, 8, 0.9),
+                                             (6, 5, 8, 0.0), (2, 2, 8, 0.99), (9, 20, 16, 0.37)])
+def test_presley_batch_shrink_stretch(dev, by, bx, bs, amount):
+    """presley.shrink_video_frames / stretch_video_frames (presley.py:761-827): the stretch refills the
+    kept positions in row-major order over the frame, which differs from the per-row refill after a
+    partial last pass."""
+    from elvis_b200 import presley
+    rng = np.random.default_rng(by * 100 + bx)
+    frames = [rng.integers(0, 256, (by * bs + 3, bx * bs + 2, 3), dtype=np.uint8) for _ in range(3)]
+    imps = [np.round(rng.random((by, bx)) * 8) / 8 for _ in range(3)]
+    small, masks = presley.shrink_video_frames(frames, imps, bs, amount, presley.shrink_frame_row_only)
+    for f, i, s, m in zip(frames, imps, small, masks):
+        rs, rm = P.shrink_frame_row_only(f, i, bs, amount)
+        assert np.array_equal(s, rs) and np.array_equal(m, rm)
+    full = presley.stretch_video_frames(small, masks, bs)
+    ref = P.stretch_video_frames(small, masks, bs)
+    assert all(np.array_equal(a, b) for a, b in zip(full, ref))
+    # a shrunk frame smaller than the mask implies (the reference's bounds guard), and masks that keep more
+    # blocks than the shrunk frame holds
+    cut = [s[:, :max(bs, s.shape[1] - bs)] for s in small]
+    assert all(np.array_equal(a, b) for a, b in zip(presley.stretch_video_frames(cut, masks, bs), P.stretch_video_frames(cut, masks, bs)))
+
+
+def test_resize_linear_float_vs_spec(dev):
+    from elvis_b200 import ops
+    from oracle import spec_cv
+    rng = np.random.default_rng(5)
+    for dt in (np.float32, np.float64):
+        for sh, sw, dh, dw in ((9, 16, 27, 33), (5, 7, 8, 9), (34, 60, 40, 70), (135, 240, 68, 120), (12, 16, 3, 4), (2, 2, 5, 1)):
+            a = (rng.random((3, sh, sw)) * 2 - 0.5).astype(dt)
+            got = ops.resize_linear_float(to_dev(a, dev), dh, dw).cpu().numpy()
+            assert got.dtype == dt
+            for t in range(3):
+                assert np.array_equal(got[t], spec_cv.resize_linear_float(a[t], dh, dw)), (dt.__name__, sh, sw, dh, dw)
+    with pytest.raises(NotImplementedError):
+        ops.resize_linear_float(to_dev(np.zeros((1, 1, 5)), dev), 3, 3)
+
+
+def test_two_devices_in_one_process():
+    """Opt-in kernel attributes (the tcgen05 kernel's dynamic shared memory) are per device, and every
+    operator must launch on the device and stream of its tensors, not of the current device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import os
+    from elvis_b200 import ops
+    from elvis_b200.pipeline import ElvisV1, Yuv420
+    y, u, v = synth_yuv420(6, 128, 512, seed=9)
+    rsc, rtc = spec_scoring.sc_tc(y, 16)
+    os.environ["ELVIS_SCORE_IMPL"] = "umma"
+    try:
+        for d in (0, 1, 0):
+            dev = torch.device("cuda", d)
+            assert torch.cuda.current_device() == 0
+            sc, tc, _ = ops.score_sc_tc(torch.from_numpy(y).to(dev), 16)
+            assert sc.device == dev
+            np.testing.assert_allclose(sc.cpu().numpy(), rsc, rtol=RTOL, atol=0)
+            np.testing.assert_allclose(tc.cpu().numpy(), rtc, rtol=RTOL, atol=0)
+    finally:
+        del os.environ["ELVIS_SCORE_IMPL"]
+    outs = []
+    for d in (0, 1):
+        dev = torch.device("cuda", d)
+        clip = Yuv420(*(torch.from_numpy(p).to(dev) for p in (y, u, v)))
+        scores, mask, shrunk, full = ElvisV1(16, 0.5, 0.5, 0.5).run(clip)
+        torch.cuda.synchronize(dev)
+        outs.append([t.cpu().numpy() for t in (scores, mask, shrunk.y, shrunk.u, full.y, full.v)])
+    assert all(np.array_equal(a, b) for a, b in zip(*outs))
+
+
+def test_pack_levels_2bit_saturates(dev):
+    from elvis_b200 import ops
+    lv = np.array([[[4, -1, 3, 7, 2, 0, 1]]], np.int32)
+    packed = ops.pack_levels_2bit(to_dev(lv, dev))
+    assert np.array_equal(packed.cpu().numpy(), P.pack_levels_2bit(lv))
+    assert ops.unpack_levels_2bit(packed, 7).cpu().numpy().tolist() == [[[3, 0, 3, 3, 2, 0, 1]]]

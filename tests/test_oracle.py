@@ -123,6 +123,57 @@ def test_spec_cv_float_area_and_i420_vs_cv2():
         assert np.array_equal(cv2.cvtColor(img, cv2.COLOR_RGB2YUV_I420), spec_cv.rgb_to_i420(img))
 
 
+def test_spec_cv_float_linear_and_gray_vs_cv2():
+    """cv2.resize(float map, INTER_LINEAR) -- fused lerp, fma-contracted coordinate on the float64 path
+    only -- and COLOR_RGB2GRAY's 15-bit fixed point, restated bit for bit."""
+    from elvis_b200 import _tables as T
+    rng = np.random.default_rng(13)
+    for dt in (np.float32, np.float64):
+        shapes = [tuple(int(v) for v in rng.integers(2, 40, 4)) for _ in range(40)]
+        shapes += [(9, 16, 27, 33), (10, 16, 5, 8), (12, 16, 3, 4), (135, 240, 68, 120), (17, 30, 34, 60), (3, 5, 6, 10)]
+        for sh, sw, dh, dw in shapes:
+            a = (rng.random((sh, sw)) * 2 - 0.5).astype(dt)
+            ref = cv2.resize(a, (dw, dh), interpolation=cv2.INTER_LINEAR)
+            assert np.array_equal(ref, spec_cv.resize_linear_float(a, dh, dw)), (dt.__name__, sh, sw, dh, dw)
+            fused = dt == np.float64
+            idx, frac = T.linear_float_index(sw, dw, fused)
+            cs = spec_cv.linear_float_coords(sw, dw, fused)
+            assert idx.tolist() == [c[0] for c in cs] and frac.tolist() == [c[1] for c in cs]
+    for w in (1, 3, 7, 16, 33, 257):
+        a = rng.integers(0, 256, (5, w, 3), dtype=np.uint8)
+        assert np.array_equal(cv2.cvtColor(a, cv2.COLOR_RGB2GRAY), spec_cv.rgb_to_gray(a))
+
+
+@needs_reference
+def test_port_matches_reference_presley_stretch_and_mismatched_maps(tmp_path):
+    """presley.py's batch wrappers (compiled from the unmodified file) incl. partial last passes, where
+    its row-major refill differs from utils.stretch_frame_row_only; utils degradations with an
+    importance grid that differs from the frame's; the qpfile's INTER_LINEAR branch."""
+    from _ref_drive import reference_qpfile
+    E, U = ref_import.load("elvis"), ref_import.load("utils")
+    PF = ref_import.load_presley_functions("shrink_frame_row_only", "shrink_video_frames", "stretch_video_frames")
+    rng = np.random.default_rng(3)
+    differs = 0
+    for (by, bx, bs, sh) in ((5, 7, 8, 0.25), (5, 7, 8, 0.33), (5, 7, 8, 0.5), (4, 6, 4, 0.5), (3, 9, 8, 0.9), (6, 5, 8, 0.0), (2, 2, 8, 0.99)):
+        frames = [rng.integers(0, 256, (by * bs + 3, bx * bs + 2, 3), dtype=np.uint8) for _ in range(2)]
+        imps = [np.round(rng.random((by, bx)) * 8) / 8 for _ in range(2)]
+        small, masks = PF["shrink_video_frames"](frames, imps, bs, sh, PF["shrink_frame_row_only"])
+        ref = PF["stretch_video_frames"](small, masks, bs)
+        mine = P.stretch_video_frames(small, masks, bs)
+        assert all(np.array_equal(a, b) for a, b in zip(ref, mine)), (by, bx, bs, sh)
+        differs += any(not np.array_equal(a, P.stretch_frame_row_only(s, m, bs)) for a, s, m in zip(ref, small, masks))
+    assert differs >= 3       # the partial-pass cases are really exercised
+    frame = rng.integers(0, 256, (16 * 3 + 3, 16 * 4 + 5, 3), dtype=np.uint8)
+    for shape in ((2, 3), (7, 9), (3, 9), (5, 4)):
+        imp = rng.random(shape)
+        for name in ("degrade_adaptive_downsample", "degrade_adaptive_blur"):
+            r, m = getattr(U, name)(frame, imp, 16), getattr(P, name)(frame, imp, 16)
+            assert np.array_equal(r[0], m[0]) and np.array_equal(r[1], m[1]), (name, shape)
+    qs = rng.random((2, 3, 5))
+    P.write_per_block_qpfile(qs, 128, 640, 384, str(tmp_path / "q.txt"))
+    assert open(tmp_path / "q.txt").read() == reference_qpfile(E, qs, 128, 640, 384, str(tmp_path / "ref"))
+
+
 @needs_reference
 def test_port_matches_reference_roi_files(tmp_path):
     """8f rank 3: the side files byte for byte (utils.py:453-462, 1026-1092; elvis.py:2027-2090)."""
@@ -299,8 +350,8 @@ def test_level_rules_and_2bit_packing():
     lv = rng.integers(0, 4, (2, 3, 13))
     packed = P.pack_levels_2bit(lv)
     assert packed.shape == (2, 3, 4) and np.array_equal(P.unpack_levels_2bit(packed, 13), lv)
-    with pytest.raises(ValueError):
-        P.pack_levels_2bit(np.array([[4]]))
+    # saturating: the reference's level 4 (16x at bs 16) is kept as 8x in the 2-bit map; negatives as 0
+    assert P.unpack_levels_2bit(P.pack_levels_2bit(np.array([[4, -1, 3, 7, 2]])), 5).tolist() == [[3, 0, 3, 3, 2]]
 
 
 def test_scoring_spec_properties():
