@@ -47,6 +47,7 @@ SIGNATURES = {
     "elvis_levels_from_scores": [_vp, _i64, _i32, _i32, _vp, _vp],
     "elvis_degrade_blur": [_PP, _PP, _i32, _i32, _i32, _i32, _vp, _vp],
     "elvis_degrade_downsample": [_PP, _PP, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp],
+    "elvis_degrade_downsample_pow2_yuv420": [_PP, _PP, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
     "elvis_dct_dampen": [_PP, _PP, _i32, _i32, _i32, _i32, _vp, _vp],
     "elvis_restore_unsharp": [_PP, _PP, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _vp],
     "elvis_restore_lanczos": [_PP, _PP, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp],

@@ -8,6 +8,8 @@
 // is an explicitly rounded fp32 op in cv2's accumulation order.
 #include "common.cuh"
 #include "dct8.cuh"
+#include "down_pow2.cuh"
+#include <cstring>
 
 namespace elvis {
 namespace {
@@ -231,6 +233,130 @@ __global__ void __launch_bounds__(256) blur_fast_kernel(const BlockGeom g, const
                 for (int j = 0; j < 4; ++j) {
                     dp[j] = (uint8_t)(px.x >> (8 * j));
                     dp[4 + j] = (uint8_t)(px.y >> (8 * j));
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- blur on the tensor cores
+// One blur round of an isolated block is Z = round((G X G^T) / 2^16) with G the 5-tap operator along an
+// axis (taps 14 62 104 62 14, reflect-101 folded into the edge rows) -- two 16 x 16 x 16 integer matrix
+// products.  A warp owns one 16 x 16 tile (one luma block, or 2 x 2 blocks of 8 x 8 with a block-diagonal
+// G) and keeps it in the operand layout of mma.sync.m16n8k16 (u8 x u8 -> s32) for all rounds:
+//   * the tile is held "transposed for free": a matrix M in the accumulator (C) layout is, read as a
+//     B operand, M^T with the K index permuted; the permutation is absorbed into which pixel columns a
+//     thread owns, so thread (g, q) = (lane / 4, lane % 4) simply owns pixels 4q..4q+3 of two tile rows
+//     (one 32-bit word each), loads them as the B operand and stores the result words as they come;
+//   * step 1: M1 = G X^T (2 IMMA, one per n-tile); step 2: Z = G M1^T = G X G^T with the 16-bit M1
+//     split into high and low bytes (2 + 2 IMMA, the high product shifted left by 8; the rounding
+//     constant 2^15 enters as the initial accumulator 128 of the high product); byte 2 of every
+//     accumulator is the blurred pixel.  A = G never changes: two registers per thread.
+// 6 IMMA + ~30 integer instructions per thread and round for 8 pixels (the dp4a kernel above: ~90),
+// all exact: bit-identical to cv2's fixed-point GaussianBlur (oracle/spec_cv.py, tools/emu/check_blur_imma.py).
+__device__ __forceinline__ void imma_16816(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0, const int (&c)[4]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.u8.u8.s32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%7, %8, %9, %10};"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+                 : "r"(a0), "r"(a1), "r"(b0), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
+}
+
+// entry (m, c) of the per-axis operator of a 16-wide tile made of PB-wide blocks
+__device__ __forceinline__ uint32_t blur_operator_entry(int PB, int m, int c) {
+    const int blk = (m / PB) * PB, ml = m - blk;
+    uint32_t s = 0;
+#pragma unroll
+    for (int d = -2; d <= 2; ++d) {
+        const uint32_t tap = d == 0 ? 104u : ((d == 1 || d == -1) ? 62u : 14u);
+        if (blk + reflect101(ml + d, PB) == c) s += tap;
+    }
+    return s;
+}
+
+// tile-row owned by accumulator-layout row i (the same map orders the columns: 4 q + j <-> layout 2 q + j, 8 + 2 q + j - 2)
+__device__ __forceinline__ int imma_tile_row(int i) { return 4 * ((i & 7) >> 1) + (i & 1) + (i >= 8 ? 2 : 0); }
+
+template <int PB, bool ALIGNED>
+__global__ void __launch_bounds__(256) blur_imma_kernel(const BlockGeom g, const int32_t* __restrict__ rounds) {
+    constexpr int kWarps = 8;
+    constexpr int kPerTile = 16 / PB;                       // blocks per tile side: 1 (luma) or 2 (chroma)
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int r0 = imma_tile_row(gq), r1 = imma_tile_row(gq + 8), c0 = 4 * tq;
+    uint32_t a0 = 0u, a1 = 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        a0 |= blur_operator_entry(PB, r0, c0 + i) << (8 * i);
+        a1 |= blur_operator_entry(PB, r1, c0 + i) << (8 * i);
+    }
+    const int tiles_x = (g.Bx + kPerTile - 1) / kPerTile, tiles_y = (g.By + kPerTile - 1) / kPerTile;
+    const int64_t n_tiles = (int64_t)g.T * tiles_y * tiles_x;
+    const int64_t stride = (int64_t)gridDim.x * kWarps;
+    const int zero4[4] = {0, 0, 0, 0}, half4[4] = {128, 128, 128, 128};
+    for (int64_t tile = (int64_t)blockIdx.x * kWarps + w; tile < n_tiles; tile += stride) {
+        const int tx = (int)(tile % tiles_x);
+        const int64_t q = tile / tiles_x;
+        const int ty = (int)(q % tiles_y), t = (int)(q / tiles_y);
+        // the thread's 8 pixels lie in ONE block of the tile: rows r0, r1 share a half, columns 4q..4q+3 too
+        const int byq = ty * kPerTile + (PB == 8 ? (gq >= 4) : 0), bxq = tx * kPerTile + (PB == 8 ? (tq >= 2) : 0);
+        const bool live = byq < g.By && bxq < g.Bx;
+        int nr = 0;
+        const uint8_t* sp = g.src;
+        uint8_t* dp = g.dst;
+        if (live) {
+            nr = rounds[((int64_t)t * g.By + byq) * g.Bx + bxq];
+            sp += (int64_t)t * g.src_frame + (int64_t)ty * 16 * g.src_row + (int64_t)tx * 16 + c0;
+            dp += (int64_t)t * g.dst_frame + (int64_t)ty * 16 * g.dst_row + (int64_t)tx * 16 + c0;
+        }
+        uint32_t w0 = 0u, w1 = 0u;
+        if (live) {
+            const uint8_t *p0 = sp + (int64_t)r0 * g.src_row, *p1 = sp + (int64_t)r1 * g.src_row;
+            if (ALIGNED) {
+                w0 = __ldcs(reinterpret_cast<const uint32_t*>(p0));
+                w1 = __ldcs(reinterpret_cast<const uint32_t*>(p1));
+            } else {
+                w0 = p0[0] | (p0[1] << 8) | (p0[2] << 16) | ((uint32_t)p0[3] << 24);
+                w1 = p1[0] | (p1[1] << 8) | (p1[2] << 16) | ((uint32_t)p1[3] << 24);
+            }
+        }
+        int max_r = nr;
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) max_r = max(max_r, __shfl_xor_sync(0xffffffffu, max_r, m));
+        for (int k = 0; k < max_r; ++k) {
+            int m1a[4], m1b[4];                               // M1 = G X^T: n-tile 0 (from my first row) and 1 (second row)
+            imma_16816(m1a, a0, a1, w0, zero4);
+            imma_16816(m1b, a0, a1, w1, zero4);
+            uint32_t z[2];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {            // layout rows g / g + 8 of M1 feed n-tile `half` of step 2
+                const uint32_t q0 = (uint32_t)m1a[2 * half], q1 = (uint32_t)m1a[2 * half + 1];
+                const uint32_t q2 = (uint32_t)m1b[2 * half], q3 = (uint32_t)m1b[2 * half + 1];
+                const uint32_t hi = __byte_perm(__byte_perm(q0, q1, 0x0051), __byte_perm(q2, q3, 0x0051), 0x5410);
+                const uint32_t lo = __byte_perm(__byte_perm(q0, q1, 0x0040), __byte_perm(q2, q3, 0x0040), 0x5410);
+                int acc[4];
+                imma_16816(acc, a0, a1, hi, half4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] <<= 8;
+                imma_16816(acc, a0, a1, lo, acc);
+                // my first row's word comes from acc[0..1] of both halves, my second row's from acc[2..3]: keep all four
+                z[half] = __byte_perm(__byte_perm((uint32_t)acc[0], (uint32_t)acc[1], 0x0062), __byte_perm((uint32_t)acc[2], (uint32_t)acc[3], 0x0062), 0x5410);
+            }
+            // z[half] = (row g: cols 2q,2q+1 of n-tile half | row g+8: the same) -> words of my two rows
+            const uint32_t n0 = __byte_perm(z[0], z[1], 0x5410), n1 = __byte_perm(z[0], z[1], 0x7632);
+            if (k < nr) {
+                w0 = n0;
+                w1 = n1;
+            }
+        }
+        if (live) {
+            uint8_t *p0 = dp + (int64_t)r0 * g.dst_row, *p1 = dp + (int64_t)r1 * g.dst_row;
+            if (ALIGNED) {
+                __stcs(reinterpret_cast<uint32_t*>(p0), w0);
+                __stcs(reinterpret_cast<uint32_t*>(p1), w1);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    p0[j] = (uint8_t)(w0 >> (8 * j));
+                    p1[j] = (uint8_t)(w1 >> (8 * j));
                 }
             }
         }
@@ -504,6 +630,130 @@ __global__ void __launch_bounds__(256) downsample_fast_kernel(const BlockGeom g,
     }
 }
 
+// ------------------------------------------------- downsample, power-of-two closed form
+// The default for planar planes with 16- / 8-pixel blocks and power-of-two reductions (down_pow2.cuh):
+// one warp = one 16 x 16 block or two 8 x 8 blocks, the level is uniform per lane group, so the
+// per-level code is straight-line packed 16-bit integer arithmetic with a handful of shuffles
+// (about 11 instructions per pixel against 30 of the table-driven kernel above).
+template <int PB, bool ALIGNED>
+__global__ void __launch_bounds__(256) downsample_pow2_kernel(const BlockGeom g, const int32_t* __restrict__ levels,
+                                                              const int32_t* __restrict__ tables, int n_levels) {
+    constexpr int kWarps = 8;
+    constexpr int kGroup = 2 * PB;
+    constexpr int kBlocks = 32 / kGroup;
+    constexpr int kLevelStride = 8 + (PB + 1) + 4 * PB + 8 * PB;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int gl = lane % kGroup, base = lane - gl, blk = lane / kGroup;
+    const int r = gl >> 1, h = gl & 1;
+    constexpr int kBytes = PB / 2;                          // bytes of a row this lane owns
+    const int64_t n_blocks = (int64_t)g.T * g.By * g.Bx;
+    const int64_t stride = (int64_t)gridDim.x * kWarps * kBlocks;
+    for (int64_t b0 = ((int64_t)blockIdx.x * kWarps + w) * kBlocks; b0 < n_blocks; b0 += stride) {
+        const int64_t b = b0 + blk;
+        const bool live = b < n_blocks;
+        int L = 0;
+        const uint8_t* sp = g.src;
+        uint8_t* dp = g.dst;
+        if (live) {
+            const int bx = (int)(b % g.Bx);
+            const int64_t q = b / g.Bx;
+            const int by = (int)(q % g.By), t = (int)(q / g.By);
+            int lv = levels[b];
+            lv = lv < 0 ? 0 : (lv >= n_levels ? n_levels - 1 : lv);
+            const int small = __ldg(tables + (size_t)lv * kLevelStride);
+            L = small >= PB ? 0 : 31 - __clz(PB / small);
+            sp += (int64_t)t * g.src_frame + ((int64_t)by * PB + r) * g.src_row + (int64_t)bx * PB + kBytes * h;
+            dp += (int64_t)t * g.dst_frame + ((int64_t)by * PB + r) * g.dst_row + (int64_t)bx * PB + kBytes * h;
+        }
+        uint32_t p0 = 0u, p1 = 0u;
+        if (live) {
+            if (ALIGNED) {
+                if (PB == 16) {
+                    const uint2 v = __ldcs(reinterpret_cast<const uint2*>(sp));
+                    p0 = v.x;
+                    p1 = v.y;
+                } else {
+                    p0 = __ldcs(reinterpret_cast<const uint32_t*>(sp));
+                }
+            } else {
+                p0 = sp[0] | (sp[1] << 8) | (sp[2] << 16) | ((uint32_t)sp[3] << 24);
+                if (PB == 16) p1 = sp[4] | (sp[5] << 8) | (sp[6] << 16) | ((uint32_t)sp[7] << 24);
+            }
+        }
+        // every lane group runs the code of every level present in the warp (shuffles are warp-wide) and keeps its own
+        const int La = __shfl_sync(0xffffffffu, L, 0);
+        const int Lb = kBlocks == 2 ? __shfl_sync(0xffffffffu, L, 16) : La;
+        if (La > 0) {
+            uint32_t q0 = p0, q1 = p1;
+            down_up_pow2_level<PB>(q0, q1, La, gl, base);
+            if (L == La) {
+                p0 = q0;
+                p1 = q1;
+            }
+        }
+        if (Lb > 0 && Lb != La) {
+            uint32_t q0 = p0, q1 = p1;
+            down_up_pow2_level<PB>(q0, q1, Lb, gl, base);
+            if (L == Lb) {
+                p0 = q0;
+                p1 = q1;
+            }
+        }
+        if (live) {
+            if (ALIGNED) {
+                if (PB == 16) __stcs(reinterpret_cast<uint2*>(dp), make_uint2(p0, p1));
+                else __stcs(reinterpret_cast<uint32_t*>(dp), p0);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dp[j] = (uint8_t)(p0 >> (8 * j));
+                    if (PB == 16) dp[4 + j] = (uint8_t)(p1 >> (8 * j));
+                }
+            }
+        }
+    }
+}
+
+// Planar YUV 4:2:0 with 16 x 16 luma blocks, Y, U and V in ONE launch: a warp takes the luma block and then
+// its two 8 x 8 chroma blocks (lanes 0..15 U, 16..31 V), which share the block's level -- no divergence.
+struct YuvGeom {
+    const uint8_t* src[3];
+    uint8_t* dst[3];
+    int64_t src_frame[3], src_row[3], dst_frame[3], dst_row[3];
+    int32_t T, By, Bx;
+};
+
+__global__ void __launch_bounds__(256) downsample_pow2_yuv420_kernel(const YuvGeom g, const int32_t* __restrict__ levels, int max_level) {
+    constexpr int kWarps = 8;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t n_blocks = (int64_t)g.T * g.By * g.Bx;
+    const int64_t stride = (int64_t)gridDim.x * kWarps;
+    for (int64_t b = (int64_t)blockIdx.x * kWarps + w; b < n_blocks; b += stride) {
+        const int bx = (int)(b % g.Bx);
+        const int64_t q = b / g.Bx;
+        const int by = (int)(q % g.By), t = (int)(q / g.By);
+        int L = levels[b];
+        L = L < 0 ? 0 : (L > max_level ? max_level : L);
+        {   // luma: lane = (row, 8-pixel half)
+            const int r = lane >> 1, h = lane & 1;
+            const int64_t so = (int64_t)t * g.src_frame[0] + ((int64_t)by * 16 + r) * g.src_row[0] + (int64_t)bx * 16 + 8 * h;
+            const int64_t dof = (int64_t)t * g.dst_frame[0] + ((int64_t)by * 16 + r) * g.dst_row[0] + (int64_t)bx * 16 + 8 * h;
+            const uint2 v = __ldcs(reinterpret_cast<const uint2*>(g.src[0] + so));
+            uint32_t p0 = v.x, p1 = v.y;
+            if (L > 0) down_up_pow2_level<16>(p0, p1, L > 4 ? 4 : L, lane, 0);
+            __stcs(reinterpret_cast<uint2*>(g.dst[0] + dof), make_uint2(p0, p1));
+        }
+        {   // chroma: lanes 0..15 U, 16..31 V; lane = (row, 4-pixel half) inside its group
+            const int pl = 1 + (lane >> 4), gl = lane & 15, r = gl >> 1, h = gl & 1;
+            const int64_t so = (int64_t)t * g.src_frame[pl] + ((int64_t)by * 8 + r) * g.src_row[pl] + (int64_t)bx * 8 + 4 * h;
+            const int64_t dof = (int64_t)t * g.dst_frame[pl] + ((int64_t)by * 8 + r) * g.dst_row[pl] + (int64_t)bx * 8 + 4 * h;
+            uint32_t p0 = __ldcs(reinterpret_cast<const uint32_t*>(g.src[pl] + so)), p1 = 0u;
+            if (L > 0) down_up_pow2_level<8>(p0, p1, L > 3 ? 3 : L, gl, lane & 16);
+            __stcs(reinterpret_cast<uint32_t*>(g.dst[pl] + dof), p0);
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------- dampen
 // one thread per (8x8 tile, channel): forward AAN, per-coefficient gain, inverse AAN
 template <bool FAST>   // FAST: single channel, 8-byte aligned rows -> 64-bit loads/stores
@@ -648,7 +898,25 @@ extern "C" int elvis_degrade_blur(const elvis_plane* src, const elvis_plane* dst
     cudaStream_t st = as_stream(stream);
     if (int rc = copy_edges(g, st)) return rc;
     const int n = block_px * block_px;
-    if (g.C == 1 && (block_px == 16 || block_px == 8) && !getenv("ELVIS_BLUR_GENERIC")) {
+    const char* blur_impl = getenv("ELVIS_BLUR_IMPL");       // imma (default) | dp4a | generic
+    if (g.C == 1 && (block_px == 16 || block_px == 8) && !(blur_impl && (!strcmp(blur_impl, "dp4a") || !strcmp(blur_impl, "generic"))) &&
+        !getenv("ELVIS_BLUR_GENERIC")) {
+        const bool al4 = aligned_to(g.src, 4) && aligned_to(g.dst, 4) && g.src_frame % 4 == 0 && g.dst_frame % 4 == 0 &&
+                         g.src_row % 4 == 0 && g.dst_row % 4 == 0;
+        const int per = 16 / block_px;
+        const int64_t tiles = (int64_t)n_frames * ((by + per - 1) / per) * ((bx + per - 1) / per);
+        const int grid = grid_for_units(tiles, 8);
+        if (block_px == 16) {
+            if (al4) blur_imma_kernel<16, true><<<grid, 256, 0, st>>>(g, rounds);
+            else blur_imma_kernel<16, false><<<grid, 256, 0, st>>>(g, rounds);
+        } else {
+            if (al4) blur_imma_kernel<8, true><<<grid, 256, 0, st>>>(g, rounds);
+            else blur_imma_kernel<8, false><<<grid, 256, 0, st>>>(g, rounds);
+        }
+        ELVIS_CHECK_LAUNCH();
+        return ELVIS_OK;
+    }
+    if (g.C == 1 && (block_px == 16 || block_px == 8) && !(blur_impl && !strcmp(blur_impl, "generic")) && !getenv("ELVIS_BLUR_GENERIC")) {
         const bool al = aligned_to(g.src, 8) && aligned_to(g.dst, 8) && g.src_frame % 8 == 0 && g.dst_frame % 8 == 0 &&
                         g.src_row % 8 == 0 && g.dst_row % 8 == 0;
         const int64_t blocks = (int64_t)n_frames * by * bx;
@@ -688,6 +956,20 @@ extern "C" int elvis_degrade_downsample(const elvis_plane* src, const elvis_plan
         const bool al = aligned_to(g.src, 8) && aligned_to(g.dst, 8) && g.src_frame % 8 == 0 && g.dst_frame % 8 == 0 &&
                         g.src_row % 8 == 0 && g.dst_row % 8 == 0;
         const int64_t blocks = (int64_t)n_frames * by * bx;
+        if (!getenv("ELVIS_DOWNSAMPLE_TABLE")) {     // closed-form kernel (default); the table-driven one stays selectable
+            const bool al4 = block_px == 16 ? al : (aligned_to(g.src, 4) && aligned_to(g.dst, 4) && g.src_frame % 4 == 0 &&
+                                                    g.dst_frame % 4 == 0 && g.src_row % 4 == 0 && g.dst_row % 4 == 0);
+            const int grid2 = grid_for_units(blocks, 8 * (block_px == 16 ? 1 : 2));
+            if (block_px == 16) {
+                if (al4) downsample_pow2_kernel<16, true><<<grid2, 256, 0, st>>>(g, levels, tables, n_levels);
+                else downsample_pow2_kernel<16, false><<<grid2, 256, 0, st>>>(g, levels, tables, n_levels);
+            } else {
+                if (al4) downsample_pow2_kernel<8, true><<<grid2, 256, 0, st>>>(g, levels, tables, n_levels);
+                else downsample_pow2_kernel<8, false><<<grid2, 256, 0, st>>>(g, levels, tables, n_levels);
+            }
+            ELVIS_CHECK_LAUNCH();
+            return ELVIS_OK;
+        }
         const int grid = grid_for_units(blocks, 8 * (block_px == 16 ? 1 : 4));
         if (block_px == 16) {
             if (al) downsample_fast_kernel<16, true><<<grid, 256, 0, st>>>(g, levels, tables, n_levels);
@@ -743,6 +1025,40 @@ extern "C" int elvis_restore_lanczos(const elvis_plane* src, const elvis_plane* 
     while (wpc > 1 && (size_t)wpc * n * 6 > 48 * 1024) wpc >>= 1;
     const int64_t units = (int64_t)n_frames * by * bx * g.C;
     downsample_kernel<true><<<grid_for_units(units, wpc), wpc * 32, (size_t)wpc * n * 6, st>>>(g, levels, tables, n_levels, wpc);
+    ELVIS_CHECK_LAUNCH();
+    return ELVIS_OK;
+}
+
+// Fused planar 4:2:0 form of the power-of-two downsample: level l reduces the 16 x 16 luma block by
+// 2^min(l, max_level, 4) per axis and its two 8 x 8 chroma blocks by 2^min(l, max_level, 3).
+extern "C" int elvis_degrade_downsample_pow2_yuv420(const elvis_plane* src_yuv, const elvis_plane* dst_yuv, int32_t n_frames,
+                                                    int32_t block_size, int32_t by, int32_t bx, const int32_t* levels,
+                                                    int32_t max_level, elvis_stream_t stream) {
+    if (!src_yuv || !dst_yuv || !levels || n_frames <= 0 || by <= 0 || bx <= 0 || max_level < 0) return ELVIS_ERR_INVALID_ARG;
+    if (block_size != 16) return ELVIS_ERR_UNSUPPORTED;
+    YuvGeom g;
+    for (int i = 0; i < 3; ++i) {
+        const elvis_plane *s = src_yuv + i, *d = dst_yuv + i;
+        if (!plane_ok(s) || !plane_ok(d) || s->channels != 1 || d->channels != 1) return ELVIS_ERR_INVALID_ARG;
+        const int pb = i == 0 ? 16 : 8;
+        // whole blocks only (the per-plane entry point copies partial blocks through)
+        if (s->height != by * pb || s->width != bx * pb || d->height != s->height || d->width != s->width) return ELVIS_ERR_UNSUPPORTED;
+        const int a = i == 0 ? 8 : 4;
+        if (!aligned_to(s->data, a) || !aligned_to(d->data, a) || s->frame_stride % a || d->frame_stride % a || s->row_stride % a ||
+            d->row_stride % a)
+            return ELVIS_ERR_UNSUPPORTED;
+        g.src[i] = static_cast<const uint8_t*>(s->data);
+        g.dst[i] = static_cast<uint8_t*>(d->data);
+        g.src_frame[i] = s->frame_stride;
+        g.src_row[i] = s->row_stride;
+        g.dst_frame[i] = d->frame_stride;
+        g.dst_row[i] = d->row_stride;
+    }
+    g.T = n_frames;
+    g.By = by;
+    g.Bx = bx;
+    const int64_t blocks = (int64_t)n_frames * by * bx;
+    downsample_pow2_yuv420_kernel<<<grid_for_units(blocks, 8), 256, 0, as_stream(stream)>>>(g, levels, max_level);
     ELVIS_CHECK_LAUNCH();
     return ELVIS_OK;
 }

@@ -292,8 +292,8 @@ extern "C" int elvis_score_sc_tc(const elvis_plane* y, int32_t n_frames, const u
     using namespace elvis;
     if (!plane_ok(y) || !sc || !tc || n_frames <= 0) return ELVIS_ERR_INVALID_ARG;
     if (y->channels != 1) return ELVIS_ERR_UNSUPPORTED;
-    if (dct_size != 8) return ELVIS_ERR_UNSUPPORTED;
     if (block_size != 8 && block_size != 16 && block_size != 32) return ELVIS_ERR_UNSUPPORTED;
+    if (dct_size != 8 && dct_size != block_size) return ELVIS_ERR_UNSUPPORTED;   // 8 x 8 tiles, or one transform per block
     const int By = y->height / block_size, Bx = y->width / block_size;
     if (By <= 0 || Bx <= 0) return ELVIS_ERR_SHAPE;
 
@@ -323,6 +323,17 @@ extern "C" int elvis_score_sc_tc(const elvis_plane* y, int32_t n_frames, const u
     auto al = [&](int a) {
         return aligned_to(p.y, a) && p.frame_stride % a == 0 && p.row_stride % a == 0 && (!prev_halo || aligned_to(prev_halo, a));
     };
+    if (dct_size != 8) {       // one block_size x block_size transform per block (score_dctn.cu)
+        p.n_chunks = pick_chunks(n_frames, (long)By * Bx, (long)kNumSMs * 16, getenv("ELVIS_SCORE_CHUNK") ? atoi(getenv("ELVIS_SCORE_CHUNK")) : 0);
+        p.chunk_len = (n_frames + p.n_chunks - 1) / p.n_chunks;
+        p.n_chunks = (n_frames + p.chunk_len - 1) / p.chunk_len;
+        cudaStream_t st = as_stream(stream);
+        if (minmax) {
+            score_minmax_init<<<1, 32, 0, st>>>(p.mm);
+            ELVIS_CHECK_LAUNCH();
+        }
+        return launch_score_dctn(p, block_size, st);
+    }
     enum { SIMT, MMA_DIRECT, MMA_TMA, UMMA } impl = SIMT;
     const long warp_units = (long)By * ((Bx * (block_size / 8) * (block_size / 8) + 31) / 32);
     if (al(16) && warp_units * n_frames >= 8L * kNumSMs * 4) impl = UMMA;

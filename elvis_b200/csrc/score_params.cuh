@@ -26,6 +26,8 @@ int launch_score_simt(ScoreParams p, int block_size, bool aligned8, cudaStream_t
 int launch_score_mma(ScoreParams p, int plane_h, int plane_w, bool use_tma, cudaStream_t st);
 // score_umma.cu: tcgen05 tensor cores, TMA ring, A operand in tensor memory (planes 16-byte aligned)
 int launch_score_umma(ScoreParams p, int block_size, int plane_h, int plane_w, cudaStream_t st);
+// score_dctn.cu: dct_size == block_size in {16, 32}, CUDA cores, one warp per block
+int launch_score_dctn(ScoreParams p, int block_size, cudaStream_t st);
 int score_umma_units_per_cta();
 int score_umma_ctas_per_sm();
 

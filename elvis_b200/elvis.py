@@ -37,12 +37,20 @@ def normalize_array(arr: np.ndarray) -> np.ndarray:
 
 
 # ---------------------------------------------------------------- scoring (elvis.py:968-1224)
+def reference_dct_size(block_size: int, dct_size: int | None = None) -> int:
+    """Transform size of the SC/TC features.  None = what the reference's calls ask EVCA for: the
+    block size itself (`python -m evca.main ... -b block_size`, elvis.py:1022-1023;
+    `EVCAConfig(block_size=bs)`, presley.py:202).  The planar pipelines and the benchmark pass 8
+    explicitly (north_star: "8x8 DCT coefficients"; 16x16 blocks then sum four 8x8 tiles)."""
+    return block_size if dct_size is None else int(dct_size)
+
+
 def removability_from_luma(y: torch.Tensor, block_size: int, alpha: float = 0.5, smoothing_beta: float = 1,
-                           background: torch.Tensor | None = None) -> torch.Tensor:
+                           background: torch.Tensor | None = None, dct_size: int | None = None) -> torch.Tensor:
     """Device-side body of calculate_removability_scores: (T, H, W) uint8 luma ->
     (T, By, Bx) float64 in [0, 1].  background: optional uint8 (T, By, Bx), non-zero =
-    background block (elvis.py:1193)."""
-    sc, tc, norm = ops.score_sc_tc(y, block_size)
+    background block (elvis.py:1193).  dct_size: see reference_dct_size."""
+    sc, tc, norm = ops.score_sc_tc(y, block_size, dct_size=reference_dct_size(block_size, dct_size))
     r, mm = ops.combine_removability(sc, tc, norm, alpha, smoothing_beta, background)
     return ops.normalize_(r, mm)
 
@@ -60,8 +68,8 @@ def removability_from_features(sc: np.ndarray, tc: np.ndarray, alpha: float = 0.
 
 def calculate_removability_scores(raw_video_file: str, reference_frames_folder: str, width: int, height: int,
                                   block_size: int, alpha: float = 0.5, working_dir: str = ".",
-                                  smoothing_beta: float = 1) -> np.ndarray:
-    """elvis.py:968-1224.  Reads the yuv420p file the reference hands to EVCA
+                                  smoothing_beta: float = 1, *, dct_size: int | None = None) -> np.ndarray:
+    """elvis.py:968-1224 (dct_size is this package's extra keyword, see reference_dct_size).  Reads the yuv420p file the reference hands to EVCA
     (elvis.py:1019), computes SC/TC on the GPU instead of the EVCA subprocess, and applies the
     in-tree combine.  Foreground masks are an external model's output (UFO, elvis.py:1109):
     if `<working_dir>/maps/ufo_masks/00001.png ...` exist they are applied exactly like the
@@ -87,7 +95,7 @@ def calculate_removability_scores(raw_video_file: str, reference_frames_folder: 
                 small = ops.resize_nearest(_to_dev(m, np.uint8)[None], by, bx)           # elvis.py:1189-1193
                 bg[i] = (small[0] == 0).cpu().numpy()
         background = _to_dev(bg)
-    return removability_from_luma(y, block_size, alpha, smoothing_beta, background).cpu().numpy()
+    return removability_from_luma(y, block_size, alpha, smoothing_beta, background, dct_size).cpu().numpy()
 
 
 # ---------------------------------------------------------------- block views (elvis.py:1369-1385, 1429-1434)

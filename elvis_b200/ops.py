@@ -19,7 +19,7 @@ from ._lib import (F32, F64, LEVELS_INVERTED_BINS, LEVELS_INVERTED_ROUND, LEVELS
                    REMOVE_LOW, Plane, call)
 
 __all__ = ["score_sc_tc", "minmax", "combine_removability", "normalize_", "importance_scores", "select_rows",
-           "shrink", "stretch", "move_yuv420", "levels_from_scores", "degrade_blur", "degrade_downsample", "dct_dampen",
+           "shrink", "stretch", "move_yuv420", "degrade_yuv420", "levels_from_scores", "degrade_blur", "degrade_downsample", "dct_dampen",
            "restore_unsharp", "restore_lanczos", "temporal_blend_", "pack_mask_bits", "unpack_mask_bits", "pack_levels_2bit", "unpack_levels_2bit",
            "REMOVE_HIGH", "REMOVE_LOW", "LEVELS_ROUND", "LEVELS_INVERTED_ROUND", "LEVELS_INVERTED_BINS"]
 
@@ -34,10 +34,14 @@ def _on_device(fn):
     (one process may drive several GPUs)."""
     @functools.wraps(fn)
     def wrapper(*args, **kwargs):
-        t = args[0] if args else None
-        if isinstance(t, (tuple, list)) and t:
-            t = t[0]
-        if isinstance(t, torch.Tensor) and t.is_cuda and t.device.index != torch.cuda.current_device():
+        t = None
+        for a in args:                      # the first tensor argument (possibly inside a tuple of planes)
+            if isinstance(a, (tuple, list)) and a:
+                a = a[0]
+            if isinstance(a, torch.Tensor):
+                t = a
+                break
+        if t is not None and t.is_cuda and t.device.index != torch.cuda.current_device():
             with torch.cuda.device(t.device):
                 return fn(*args, **kwargs)
         return fn(*args, **kwargs)
@@ -331,6 +335,25 @@ def degrade_downsample(clip: torch.Tensor, levels: torch.Tensor, block_px: int, 
     call("elvis_degrade_downsample", C.byref(src), C.byref(dst), T, block_px, by, bx, _ptr(levels), _ptr(tab),
          len(small_sizes), fast_ok, _stream())
     return out
+
+
+def degrade_yuv420(kind: str, src, dst, block_map: torch.Tensor, block_size: int, param: int = 0) -> bool:
+    """Y, U and V of a planar 4:2:0 clip in one launch (src, dst: 3-tuples of (T, H, W) planes).  kind:
+    "downsample_pow2" (block_map int32 levels, param = max_level).  Returns False when the geometry is not
+    supported by the fused kernel (the caller then uses the per-plane operators)."""
+    T, by, bx = block_map.shape
+    if block_size != 16 or not block_map.is_contiguous():
+        return False
+    s, d = _yuv_planes(src, "src"), _yuv_planes(dst, "dst")
+    name = {"downsample_pow2": "elvis_degrade_downsample_pow2_yuv420"}[kind]
+    _check_cuda(block_map, torch.int32, "block map")
+    args = (s, d, T, block_size, by, bx, _ptr(block_map), int(param), _stream())
+    rc = getattr(_lib.lib, name)(*args)
+    if rc == _lib.ERR_UNSUPPORTED:
+        return False
+    if rc != 0:
+        call(name, *args)   # raises
+    return True
 
 
 def dct_dampen(clip: torch.Tensor, strength: torch.Tensor, block_px: int, out: torch.Tensor | None = None) -> torch.Tensor:
@@ -718,7 +741,7 @@ def refill_map(mask: torch.Tensor, capacity: int) -> torch.Tensor:
 
 # every public operator runs on the device of its first tensor argument
 for _name in ("score_sc_tc", "minmax", "combine_removability", "normalize_", "importance_scores", "select_rows", "shrink",
-              "stretch", "move_yuv420", "levels_from_scores", "degrade_blur", "degrade_downsample", "dct_dampen",
+              "stretch", "move_yuv420", "degrade_yuv420", "levels_from_scores", "degrade_blur", "degrade_downsample", "dct_dampen",
               "restore_unsharp", "restore_lanczos", "temporal_blend_", "pack_mask_bits", "unpack_mask_bits",
               "pack_levels_2bit", "unpack_levels_2bit", "rowcol_plan", "rowcol_expand", "invert_block_map", "gather_blocks",
               "roi_kvazaar", "roi_prepare_f32", "resize_area_f32", "roi_svtav1_offsets", "rgb_to_i420", "area_downscale",

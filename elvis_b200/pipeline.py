@@ -34,10 +34,12 @@ class ElvisV1:
     """score -> per-row top-k mask -> shrink, and stretch (elvis.py:4350-4394, 4550-4557),
     for a planar clip resident on the GPU."""
 
-    def __init__(self, block_size: int = 16, shrink_amount: float = 0.5, alpha: float = 0.5, beta: float = 0.5):
+    def __init__(self, block_size: int = 16, shrink_amount: float = 0.5, alpha: float = 0.5, beta: float = 0.5, dct_size: int = 8):
+        """dct_size: 8 (north_star's 8 x 8 tiles, the benchmarked mode) or block_size (one transform per
+        block, what the reference's EVCA call asks for; elvis.reference_dct_size)."""
         if block_size % 2:
             raise ValueError("4:2:0 chroma needs an even block size")
-        self.bs, self.shrink_amount, self.alpha, self.beta = block_size, shrink_amount, alpha, beta
+        self.bs, self.shrink_amount, self.alpha, self.beta, self.dct_size = block_size, shrink_amount, alpha, beta, dct_size
 
     def grid(self, clip: Yuv420) -> Tuple[int, int, int]:
         h, w = clip.y.shape[1:]
@@ -47,7 +49,7 @@ class ElvisV1:
         return h // self.bs, bx, blocks_to_remove(self.shrink_amount, bx)
 
     def score(self, clip: Yuv420, background: Optional[torch.Tensor] = None) -> torch.Tensor:
-        sc, tc, norm = ops.score_sc_tc(clip.y, self.bs)
+        sc, tc, norm = ops.score_sc_tc(clip.y, self.bs, dct_size=self.dct_size)
         r, mm = ops.combine_removability(sc, tc, norm, self.alpha, self.beta, background)
         return ops.normalize_(r, mm)
 
@@ -207,6 +209,11 @@ class PresleyV2:
     def downsample_pow2(self, clip: Yuv420, levels: torch.Tensor, max_level: int, out: Optional[Yuv420] = None) -> Yuv420:
         """level l reduces a block by 2**l per axis (elvis.py:2147-2163); chroma blocks use
         the same factor on their half-size block."""
+        if out is None:
+            out = Yuv420.empty(clip.y.shape[0], clip.y.shape[1], clip.y.shape[2], clip.y.device)
+        if levels.shape[0] == clip.y.shape[0] and ops.degrade_yuv420("downsample_pow2", clip.planes, out.planes, levels, self.bs, max_level):
+            return out            # Y, U and V in one launch
+
         def fn(p, pb, o):
             smalls = [max(1, pb >> l) for l in range(max_level + 1)]
             ops.degrade_downsample(p, levels, pb, smalls, out=o)

@@ -12,14 +12,16 @@ import torch
 
 from . import ops
 from . import utils as _utils
-from .elvis import _to_dev
+from .elvis import _to_dev, reference_dct_size
 
 
 # ------------------------------------------------------------------ EVCA stand-in
 @dataclass
 class EVCAConfig:
+    """`EVCAConfig(block_size=bs)` of presley.py:202.  dct_size None = one transform per block (the
+    reference's call); 8 = north_star's 8 x 8 tiling."""
     block_size: int = 16
-    dct_size: int = 8
+    dct_size: int | None = None
 
 
 @dataclass
@@ -40,7 +42,7 @@ def analyze_frames(frames: np.ndarray, config: EVCAConfig) -> Complexities:
     luma or (T, H, W, 3) RGB uint8."""
     f = _to_dev(np.asarray(frames), np.uint8)
     y = f if f.dim() == 3 else rgb_to_luma(f)
-    sc, tc, _ = ops.score_sc_tc(y.contiguous(), config.block_size, dct_size=config.dct_size)
+    sc, tc, _ = ops.score_sc_tc(y.contiguous(), config.block_size, dct_size=reference_dct_size(config.block_size, config.dct_size))
     return Complexities(sc.double().cpu().numpy(), tc.double().cpu().numpy())
 
 

@@ -80,8 +80,10 @@ ELVIS_API int         elvis_last_cuda_error(void);
  * presley.py:202; arithmetic defined by oracle/spec_scoring.py -- parity unpinned).
  * y: luma plane, channels must be 1; only the top-left (By*bs) x (Bx*bs) region is read,
  * By = height / bs, Bx = width / bs.  prev_halo: one luma frame (same row_stride) that
- * precedes frame 0, or NULL (then TC[0] = 0).  block_size in {8, 16, 32}; dct_size must be
- * 8.  sc, tc: float32 (T, By, Bx).  minmax: NULL or 4 floats {sc_min, sc_max, tc_min,
+ * precedes frame 0, or NULL (then TC[0] = 0).  block_size in {8, 16, 32}; dct_size = 8 (every
+ * block is tiled into 8 x 8 transforms -- north_star's definition, the benchmarked mode) or
+ * dct_size = block_size (one transform per block, what the reference's `evca.main -b block_size`
+ * call asks EVCA for, elvis.py:1022-1023).  sc, tc: float32 (T, By, Bx).  minmax: NULL or 4 floats {sc_min, sc_max, tc_min,
  * tc_max} over frames [mm_begin, mm_end) -- overwritten, not accumulated.
  * Two kernels sit behind this entry point: the tcgen05 / TMA kernel (plane, strides and halo
  * 16-byte aligned, clip large enough to fill the GPU) and a CUDA-core kernel (anything else);
@@ -181,6 +183,15 @@ ELVIS_API int elvis_degrade_downsample(const elvis_plane* src, const elvis_plane
                              int32_t block_px, int32_t by, int32_t bx, const int32_t* levels,
                              const int32_t* tables, int32_t n_levels, int32_t fast_tables_ok,
                              elvis_stream_t stream);
+
+/* a8 for planar YUV 4:2:0 clips, power-of-two levels, Y, U and V in ONE launch (src_yuv / dst_yuv: arrays
+ * of three planes {Y, U, V}): level l of a 16 x 16 block reduces the luma block by 2^min(l, max_level, 4)
+ * per axis and its two 8 x 8 chroma blocks by 2^min(l, max_level, 3) (cv2 INTER_AREA down, INTER_LINEAR
+ * up, elvis.py:2158-2163).  Needs block_size == 16, planes made of whole blocks, 8-byte aligned luma and
+ * 4-byte aligned chroma; returns ELVIS_ERR_UNSUPPORTED otherwise (use the per-plane entry point). */
+ELVIS_API int elvis_degrade_downsample_pow2_yuv420(const elvis_plane* src_yuv, const elvis_plane* dst_yuv, int32_t n_frames,
+                                         int32_t block_size, int32_t by, int32_t bx, const int32_t* levels,
+                                         int32_t max_level, elvis_stream_t stream);
 
 /* ---- a14: DCT-coefficient dampening (README.md:11,44 only; defined by
  * oracle/spec_dct_dampen.py -- parity unpinned).  strength: float32 (T, By, Bx).

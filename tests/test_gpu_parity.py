@@ -756,9 +756,10 @@ def test_mirrors_resize_mismatched_maps_like_the_reference(dev, tmp_path):
         m = (rng.random((H, W)) > 0.5).astype(np.uint8) * 255
         cv2.imwrite(str(mdir / f"{t + 1:05d}.png"), m)
         bgs.append(cv2.resize(m, (W // bs, H // bs), interpolation=cv2.INTER_NEAREST) == 0)
-    got = E.calculate_removability_scores(str(raw), "", W, H, bs, alpha=0.4, working_dir=str(tmp_path), smoothing_beta=0.5)
-    rsc, rtc = spec_scoring.sc_tc(y, bs)
-    np.testing.assert_allclose(got, P.combine_removability(rsc, rtc, 0.4, 0.5, np.stack(bgs)), rtol=RTOL, atol=1e-9)
+    for dct, n in ((None, bs), (8, 8), (16, 16)):       # default: the reference's `evca.main -b block_size` call
+        got = E.calculate_removability_scores(str(raw), "", W, H, bs, alpha=0.4, working_dir=str(tmp_path), smoothing_beta=0.5, dct_size=dct)
+        rsc, rtc = spec_scoring.sc_tc(y, bs, n)
+        np.testing.assert_allclose(got, P.combine_removability(rsc, rtc, 0.4, 0.5, np.stack(bgs)), rtol=RTOL, atol=1e-9)
 
 
 def test_unsharp_restorer_planar(dev):
@@ -796,13 +797,13 @@ def test_analyze_frames_rgb_and_luma(dev):
     luma = spec_cv.rgb_to_gray(rgb)
     got_luma = presley.rgb_to_luma(to_dev(rgb, dev)).cpu().numpy()
     assert np.array_equal(got_luma, luma)
-    for bs in (8, 16):
-        cx = presley.analyze_frames(list(rgb), presley.EVCAConfig(block_size=bs))
-        rsc, rtc = spec_scoring.sc_tc(luma, bs)
+    for bs, dct in ((8, None), (16, None), (16, 8), (32, None)):
+        cx = presley.analyze_frames(list(rgb), presley.EVCAConfig(block_size=bs, dct_size=dct))
+        rsc, rtc = spec_scoring.sc_tc(luma, bs, bs if dct is None else dct)
         assert cx.SC.dtype == np.float64 and cx.SC.shape == rsc.shape
         np.testing.assert_allclose(cx.SC, rsc, rtol=RTOL, atol=0)
         np.testing.assert_allclose(cx.TC, rtc, rtol=RTOL, atol=0)
-        cy = presley.analyze_frames(luma, presley.EVCAConfig(block_size=bs))
+        cy = presley.analyze_frames(luma, presley.EVCAConfig(block_size=bs, dct_size=dct))
         assert np.array_equal(cx.SC, cy.SC) and np.array_equal(cx.TC, cy.TC)
     # odd widths take the byte path of the luma kernel; strided frames
     odd = rng.integers(0, 256, (2, 9, 13, 3), dtype=np.uint8)
@@ -889,3 +890,44 @@ def test_pack_levels_2bit_saturates(dev):
     packed = ops.pack_levels_2bit(to_dev(lv, dev))
     assert np.array_equal(packed.cpu().numpy(), P.pack_levels_2bit(lv))
     assert ops.unpack_levels_2bit(packed, 7).cpu().numpy().tolist() == [[[3, 0, 3, 3, 2, 0, 1]]]
+
+
+@pytest.mark.parametrize("bs,H,W,T", [(16, 64, 96, 7), (32, 64, 128, 4), (16, 48, 272, 30), (16, 1080, 1920, 3), (32, 96, 528, 13),
+                                      (16, 50, 75, 5)])
+def test_sc_tc_dct_size_equals_block_size(dev, monkeypatch, bs, H, W, T):
+    """dct_size = block_size (one 16 x 16 / 32 x 32 transform per block: the size the reference passes to
+    EVCA, elvis.py:1022-1023) against the spec with n = block_size; chunked runs and halos give the
+    same bits; unaligned planes take the byte-load path."""
+    from elvis_b200 import ops
+    y = synth_luma(T + 1, H, W, seed=bs + T)
+    yd = to_dev(y, dev)
+    rsc, rtc = spec_scoring.sc_tc(y[1:], bs, bs)
+    sc, tc, mm = ops.score_sc_tc(yd[1:], bs, dct_size=bs)
+    sc_n, tc_n, mm = sc.cpu().numpy(), tc.cpu().numpy(), mm.cpu().numpy()
+    np.testing.assert_allclose(sc_n, rsc, rtol=RTOL, atol=1e-6 * rsc.max())
+    np.testing.assert_allclose(tc_n, rtc, rtol=RTOL, atol=1e-6 * rtc.max())
+    assert np.all(tc_n[0] == 0) and mm.tolist() == [sc_n.min(), sc_n.max(), tc_n.min(), tc_n.max()]
+    import torch
+    monkeypatch.setenv("ELVIS_SCORE_CHUNK", "3")
+    sc2, tc2, _ = ops.score_sc_tc(yd[1:], bs, dct_size=bs)
+    assert torch.equal(sc2, sc) and torch.equal(tc2, tc)
+    hsc, htc = spec_scoring.sc_tc(y[1:], bs, bs, prev=y[0])
+    sc3, tc3, _ = ops.score_sc_tc(yd[1:], bs, prev_halo=yd[0], dct_size=bs)
+    assert torch.equal(sc3, sc)
+    np.testing.assert_allclose(tc3.cpu().numpy(), htc, rtol=RTOL, atol=1e-6 * htc.max())
+    with pytest.raises(Exception):
+        ops.score_sc_tc(yd, 32 if bs == 16 else 16, dct_size=bs)          # dct_size must be 8 or the block size
+
+
+def test_pipeline_with_block_sized_transform(dev):
+    from elvis_b200.pipeline import ElvisV1, Yuv420
+    T, H, W, bs = 4, 64, 160, 16
+    y, u, v = synth_yuv420(T, H, W, seed=31)
+    clip = Yuv420(to_dev(y, dev), to_dev(u, dev), to_dev(v, dev))
+    scores, mask, shrunk, full = ElvisV1(bs, 0.5, 0.4, 0.5, dct_size=bs).run(clip)
+    rsc, rtc = spec_scoring.sc_tc(y, bs, bs)
+    scores, mask = scores.cpu().numpy(), mask.cpu().numpy()
+    np.testing.assert_allclose(scores, P.combine_removability(rsc, rtc, 0.4, 0.5), rtol=RTOL, atol=1e-9)
+    assert np.array_equal(mask, P.select_rows(scores, W // bs // 2, P.REMOVE_HIGH))
+    for t in range(T):
+        assert np.array_equal(full.y[t].cpu().numpy(), P.stretch_plane(P.shrink_plane(y[t], mask[t], bs), mask[t], bs))
