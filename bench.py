@@ -361,10 +361,21 @@ def measure_v1(ctx, workload, steps, warmup, with_e2e, with_cpu, with_parity):
     by, bx = H // BLOCK, W // BLOCK
     k = int(SHRINK * bx)
 
+    # N > 1: halo exchange and min / max reductions over peer memory (copy engines + mailbox all-reduce over NVLink,
+    # elvis_b200/peer.py) when CUDA IPC works between the ranks, else over NCCL
+    pg = None
+    if world > 1 and args.transport != "nccl":
+        from elvis_b200 import peer
+        pg = peer.try_create(rank, world, dev)
+        if pg is None and args.transport == "peer":
+            raise RuntimeError("--transport peer: the peer-memory setup failed")
+    transport_name = "peer memory: copy-engine halo copies + mailbox all-reduce over NVLink (elvis_b200.peer)" if pg else \
+        ("NCCL send/recv + all_reduce (torch.distributed)" if world > 1 else "none (one GPU)")
+
     # `distinct` different global clips; rank r owns frames [offset, offset + T) of each; luma lives in a halo buffer
     halos, clips = [], []
     for j in range(distinct):
-        halo = sharding.HaloClip(T, H, W, dev)
+        halo = pg.halo_clip(T, H, W) if pg else sharding.HaloClip(T, H, W, dev)
         chroma = torch.empty((2, T, H // 2, W // 2), dtype=torch.uint8, device=dev)
         clip = Yuv420(halo.owned, chroma[0], chroma[1])
         synth_yuv420(T, H, W, seed=1234 + 17 * j, device=dev, out=clip, frame_offset=offset)
@@ -375,7 +386,7 @@ def measure_v1(ctx, workload, steps, warmup, with_e2e, with_cpu, with_parity):
 
     def score_of(j):
         if world > 1:
-            return sharding.sharded_removability(halos[j], total, BLOCK, ALPHA, BETA, rank, world)
+            return sharding.sharded_removability(halos[j], total, BLOCK, ALPHA, BETA, rank, world, transport=pg)
         return pipe.score(clips[j])
 
     def serial_step(j=0, ev=None):
@@ -411,10 +422,15 @@ def measure_v1(ctx, workload, steps, warmup, with_e2e, with_cpu, with_parity):
     if pipelined:
         score_fn = comm_fn = None
         if world > 1:   # halo exchange ahead of time on the communication stream, reductions inside the score stage
-            comm_fn = lambda c: sharding.exchange_halo(halos[index_of[id(c)]], rank, world)  # noqa: E731
+            if pg:
+                comm_fn = lambda c: pg.exchange_halo(halos[index_of[id(c)]])  # noqa: E731
+            else:
+                comm_fn = lambda c: sharding.exchange_halo(halos[index_of[id(c)]], rank, world)  # noqa: E731
             score_fn = lambda c, slot: sharding.sharded_removability(halos[index_of[id(c)]], total, BLOCK, ALPHA, BETA, rank,  # noqa: E731
-                                                                     world, exchange=False)
-        split = (world == 1) if args.split_stretch is None else args.split_stretch
+                                                                     world, exchange=False, transport=pg)
+        # three stages on one GPU and with the peer transport; two with NCCL (its SM-resident kernels wait for SM slots
+        # next to three resident compute kernels -- measured in round 1)
+        split = (world == 1 or pg is not None) if args.split_stretch is None else args.split_stretch
         depth = (3 if split else 2) if args.depth is None else args.depth
         pp = ElvisV1Pipelined(T, H, W, BLOCK, SHRINK, ALPHA, BETA, dev, depth=depth, score_fn=score_fn,
                               move_ctas_per_sm=args.move_ctas, comm_fn=comm_fn, split_stretch=split,
@@ -500,11 +516,19 @@ def measure_v1(ctx, workload, steps, warmup, with_e2e, with_cpu, with_parity):
             parity = verify.compare_v1(gpu_out, cpu_out, BLOCK, k)
             parity["checked_against"] = "oracle/cpu_baseline.py CpuElvisV1.outputs() on the CPU arm's frames"
     launches_per_clip = 2 + 2 + 1 + 1 + 1 + 1   # score(init+kernel) combine(init+kernel) normalize select shrink(YUV fused) stretch(YUV fused)
+    if pg:
+        launches_per_clip += 2 + 4 + 2 + 2      # halo: 2 ack waits + 2 flag stores (the copies are copy-engine work), 2 arrival waits, 2 acks; 2 all-reduces
+        pg.check()
     del clips, halos, shrunk, full
+    if pipelined:
+        del pp
+    if pg:
+        pg.close()
     torch.cuda.empty_cache()
     return {"value": value, "ms_per_step": ms_per_step, "frames_per_step": frames_per_step, "frames_per_gpu": T, "clocks": clocks,
             "roofline": roof, "e2e": e2e, "cpu_baseline": cb, "parity_check": parity, "sharded_equals_single": sharded_equal,
-            "gpu_launches": launches_per_clip * clips_per_step * steps, "timed_region_s": ms / 1e3, "mode": mode}
+            "gpu_launches": launches_per_clip * clips_per_step * steps, "timed_region_s": ms / 1e3, "mode": mode,
+            "transport": transport_name}
 
 
 def e2e_v1(ctx, clip, halos, T, H, W, total, frames_per_clip, strong):
@@ -607,21 +631,25 @@ def measure_v2(ctx, workload, steps, warmup, with_e2e, with_cpu, with_parity):
     ms_per_step = ms / steps
     value = T * world * steps / (ms / 1e3)
 
-    # dominant kernel alone: the luma launch of the degradation (reads + writes the Y plane of every frame)
+    # dominant kernel alone: the luma launch of the degradation (reads + writes the Y plane of every frame); the
+    # power-of-two downsample handles Y, U and V in ONE launch (reads + writes the whole 4:2:0 frame)
     y_out = outs[0].y
+    k_bytes = 2 * W * H * T
     if kind == "dampen":
         strength = scores[0].float()
-        fn, name, key = (lambda: ops.dct_dampen(clips[0].y, strength, BLOCK, out=y_out)), "dampen_kernel (elvis_dct_dampen, luma launch)", "dampen"
+        fn, name, key = (lambda: ops.dct_dampen(clips[0].y, strength, BLOCK, out=y_out)), \
+            "dampen_hmma_kernel<16> (elvis_dct_dampen, luma launch; mma.sync f16)", "dampen"
     elif kind == "downsample":
         lv = ops.levels_from_scores(scores[0], ops.LEVELS_ROUND, 4)
-        smalls = [max(1, BLOCK >> l) for l in range(4)]
-        fn, name, key = (lambda: ops.degrade_downsample(clips[0].y, lv, BLOCK, smalls, out=y_out)), \
-            "downsample_fast_kernel (elvis_degrade_downsample, luma launch)", "downsample"
+        fn, name, key = (lambda: v2.downsample_pow2(clips[0], lv, 3, outs[0])), \
+            "downsample_pow2_yuv420_kernel (elvis_degrade_downsample_pow2_yuv420, Y+U+V in one launch)", "downsample_pow2_yuv420"
+        k_bytes = 3 * W * H * T
     else:
         rounds = ops.levels_from_scores(scores[0], ops.LEVELS_ROUND, 10)
-        fn, name, key = (lambda: ops.degrade_blur(clips[0].y, rounds, BLOCK, out=y_out)), "blur_fast_kernel (elvis_degrade_blur, luma launch)", "blur"
+        fn, name, key = (lambda: ops.degrade_blur(clips[0].y, rounds, BLOCK, out=y_out)), \
+            "blur_imma_kernel<16> (elvis_degrade_blur, luma launch; mma.sync u8)", "blur_imma"
     k_ms = ctx.time_kernel(fn, max(3, min(steps, 20)))
-    roof = roofline_dict(ctx, name, 2 * W * H * T, k_ms, T, key)
+    roof = roofline_dict(ctx, name, k_bytes, k_ms, T, key)
     alg = v2_bytes_per_frame(W, H, kind == "dampen") * T
     roof["whole_step"] = {"achieved": alg / ms_per_step / 1e6, "frac": alg / ms_per_step / 1e6 / ctx.peak,
                           "algorithmic_bytes": alg, "note": "the whole step as timed (Y, U and V launches + maps), per rank"}
@@ -683,7 +711,7 @@ def measure_v2(ctx, workload, steps, warmup, with_e2e, with_cpu, with_parity):
                                            tol=1 if kind == "dampen" else 0)
             parity["frames"] = sample
             parity["checked_against"] = f"oracle/cpu_baseline.py CpuV2({kind}).outputs() on the CPU arm's frames"
-    launches = {"dampen": 6 + 3, "downsample": 1 + 1 + 3 + 1, "blur": 1 + 3}[kind]
+    launches = {"dampen": 6 + 3, "downsample": 1 + 1 + 1, "blur": 1 + 3}[kind]   # scoring (6) / levels, degrade launches, packer
     del clips, outs, scores
     torch.cuda.empty_cache()
     return {"value": value, "ms_per_step": ms_per_step, "frames_per_step": T * world, "frames_per_gpu": T, "clocks": clocks,
@@ -716,12 +744,16 @@ def run_ours(args):
                           "config": config_dict(wl, world, r["frames_per_gpu"], args), "roofline": r["roofline"], "e2e": r["e2e"],
                           "cpu_baseline": r["cpu_baseline"], "parity_check": r["parity_check"],
                           "sharded_equals_single": r["sharded_equals_single"], "clocks": r["clocks"], "gpu_launches": r["gpu_launches"]}
+            if r.get("transport") and world > 1:
+                extras[wl]["config"]["transport"] = r["transport"]
     if ctx.sampler:
         ctx.sampler.stop()
     if ctx.rank == 0:
         cfg = config_dict(args.workload, world, m["frames_per_gpu"], args)
         cfg["frames_per_step"] = m["frames_per_step"]
         cfg["pipelining"] = m["mode"]
+        if m.get("transport"):
+            cfg["transport"] = m["transport"]
         line = {"metric": spec["metric"], "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": spec["scaling"],
                 "vs_baseline": None, "dtype": "u8 pixels, f32 DCT, f64 scores", "data": "synthetic", "config": cfg,
@@ -756,6 +788,8 @@ def main():
                     help="v1: clips per step (a step is a batch of clips, so that K = 20 steps time >= 2 s of GPU work)")
     ap.add_argument("--distinct", type=int, default=4, help="v1: number of different clips resident in HBM that the steps cycle over")
     ap.add_argument("--e2e-clips", type=int, default=8, help="clips per end-to-end measurement")
+    ap.add_argument("--transport", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: halo exchange + min/max reductions over peer memory (default when CUDA IPC works) or NCCL")
     ap.add_argument("--serial", action="store_true", help="time one clip at a time instead of the stream pipeline")
     ap.add_argument("--depth", type=int, default=None, help="clips in flight in the stream pipeline (default: 3 on one GPU, 2 when sharded)")
     ap.add_argument("--move-ctas", type=int, default=3, help="shrink/stretch CTAs per SM while pipelined")

@@ -13,7 +13,7 @@ OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_SHAPE = 0, -1, -2, -3, -4
 F32, F64 = 0, 1
 REMOVE_HIGH, REMOVE_LOW = 0, 1
 LEVELS_ROUND, LEVELS_INVERTED_ROUND, LEVELS_INVERTED_BINS = 0, 1, 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class Plane(C.Structure):
@@ -73,8 +73,16 @@ SIGNATURES = {
     "elvis_resize_linear_float": [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "elvis_rgb_to_gray": [_PP, _PP, _i32, _vp],
     "elvis_refill_map": [_vp, _i32, _i64, _i64, _vp, _vp],
+    "elvis_peer_alloc": [_i64, C.POINTER(_vp), _vp],
+    "elvis_peer_open": [_vp, C.POINTER(_vp)],
+    "elvis_peer_close": [_vp],
+    "elvis_peer_free": [_vp],
+    "elvis_peer_put": [_vp, _vp, _i64, _vp, C.c_uint32, _vp],
+    "elvis_peer_signal": [_vp, C.c_uint32, _vp],
+    "elvis_peer_wait": [_vp, C.c_uint32, _vp, _vp],
+    "elvis_peer_allreduce_minmax": [_vp, _i32, _i32, _i32, _i32, C.POINTER(_vp), _i32, C.c_uint32, _vp, _vp],
 }
-EXPORTS = ["elvis_abi_version", "elvis_error_string", "elvis_last_cuda_error", *SIGNATURES]
+EXPORTS = ["elvis_abi_version", "elvis_error_string", "elvis_last_cuda_error", "elvis_peer_mailbox_bytes", *SIGNATURES]
 
 
 def _load() -> C.CDLL:
@@ -87,6 +95,7 @@ def _load() -> C.CDLL:
     lib.elvis_error_string.restype = C.c_char_p
     lib.elvis_error_string.argtypes = [C.c_int]
     lib.elvis_last_cuda_error.restype = C.c_int
+    lib.elvis_peer_mailbox_bytes.restype = C.c_int64
     if lib.elvis_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version {lib.elvis_abi_version()} != {ABI_VERSION}; rebuild")
     for name, args in SIGNATURES.items():

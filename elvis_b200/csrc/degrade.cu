@@ -10,6 +10,7 @@
 #include "dct8.cuh"
 #include "down_pow2.cuh"
 #include <cstring>
+#include <cuda_fp16.h>
 
 namespace elvis {
 namespace {
@@ -728,29 +729,46 @@ __global__ void __launch_bounds__(256) downsample_pow2_yuv420_kernel(const YuvGe
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t n_blocks = (int64_t)g.T * g.By * g.Bx;
     const int64_t stride = (int64_t)gridDim.x * kWarps;
-    for (int64_t b = (int64_t)blockIdx.x * kWarps + w; b < n_blocks; b += stride) {
+    // luma: lane = (row, 8-pixel half); chroma: lanes 0..15 U, 16..31 V, lane = (row, 4-pixel half) inside its group
+    const int yr = lane >> 1, yh = lane & 1;
+    const int pl = 1 + (lane >> 4), gl = lane & 15, cr = gl >> 1, ch = gl & 1;
+    struct Item {
+        int64_t yo_s, yo_d, co_s, co_d;
+        uint2 y;
+        uint32_t c;
+        int L;
+    };
+    auto fetch = [&](int64_t b, Item& it) {       // addresses, level and pixels of block b (loads stay in flight)
         const int bx = (int)(b % g.Bx);
         const int64_t q = b / g.Bx;
         const int by = (int)(q % g.By), t = (int)(q / g.By);
-        int L = levels[b];
-        L = L < 0 ? 0 : (L > max_level ? max_level : L);
-        {   // luma: lane = (row, 8-pixel half)
-            const int r = lane >> 1, h = lane & 1;
-            const int64_t so = (int64_t)t * g.src_frame[0] + ((int64_t)by * 16 + r) * g.src_row[0] + (int64_t)bx * 16 + 8 * h;
-            const int64_t dof = (int64_t)t * g.dst_frame[0] + ((int64_t)by * 16 + r) * g.dst_row[0] + (int64_t)bx * 16 + 8 * h;
-            const uint2 v = __ldcs(reinterpret_cast<const uint2*>(g.src[0] + so));
-            uint32_t p0 = v.x, p1 = v.y;
-            if (L > 0) down_up_pow2_level<16>(p0, p1, L > 4 ? 4 : L, lane, 0);
-            __stcs(reinterpret_cast<uint2*>(g.dst[0] + dof), make_uint2(p0, p1));
+        it.yo_s = (int64_t)t * g.src_frame[0] + ((int64_t)by * 16 + yr) * g.src_row[0] + (int64_t)bx * 16 + 8 * yh;
+        it.yo_d = (int64_t)t * g.dst_frame[0] + ((int64_t)by * 16 + yr) * g.dst_row[0] + (int64_t)bx * 16 + 8 * yh;
+        it.co_s = (int64_t)t * g.src_frame[pl] + ((int64_t)by * 8 + cr) * g.src_row[pl] + (int64_t)bx * 8 + 4 * ch;
+        it.co_d = (int64_t)t * g.dst_frame[pl] + ((int64_t)by * 8 + cr) * g.dst_row[pl] + (int64_t)bx * 8 + 4 * ch;
+        it.y = __ldcs(reinterpret_cast<const uint2*>(g.src[0] + it.yo_s));
+        it.c = __ldcs(reinterpret_cast<const uint32_t*>(g.src[pl] + it.co_s));
+        it.L = __ldg(levels + b);
+    };
+    int64_t b = (int64_t)blockIdx.x * kWarps + w;
+    if (b >= n_blocks) return;
+    Item cur, nxt;
+    fetch(b, cur);
+    for (;;) {
+        const int64_t nb = b + stride;
+        const bool more = nb < n_blocks;
+        if (more) fetch(nb, nxt);                 // the next block's loads overlap this block's arithmetic
+        const int L = cur.L < 0 ? 0 : (cur.L > max_level ? max_level : cur.L);
+        uint32_t p0 = cur.y.x, p1 = cur.y.y, c0 = cur.c, c1 = 0u;
+        if (L > 0) {
+            down_up_pow2_level<16>(p0, p1, L > 4 ? 4 : L, lane, 0);
+            down_up_pow2_level<8>(c0, c1, L > 3 ? 3 : L, gl, lane & 16);
         }
-        {   // chroma: lanes 0..15 U, 16..31 V; lane = (row, 4-pixel half) inside its group
-            const int pl = 1 + (lane >> 4), gl = lane & 15, r = gl >> 1, h = gl & 1;
-            const int64_t so = (int64_t)t * g.src_frame[pl] + ((int64_t)by * 8 + r) * g.src_row[pl] + (int64_t)bx * 8 + 4 * h;
-            const int64_t dof = (int64_t)t * g.dst_frame[pl] + ((int64_t)by * 8 + r) * g.dst_row[pl] + (int64_t)bx * 8 + 4 * h;
-            uint32_t p0 = __ldcs(reinterpret_cast<const uint32_t*>(g.src[pl] + so)), p1 = 0u;
-            if (L > 0) down_up_pow2_level<8>(p0, p1, L > 3 ? 3 : L, gl, lane & 16);
-            __stcs(reinterpret_cast<uint32_t*>(g.dst[pl] + dof), p0);
-        }
+        __stcs(reinterpret_cast<uint2*>(g.dst[0] + cur.yo_d), make_uint2(p0, p1));
+        __stcs(reinterpret_cast<uint32_t*>(g.dst[pl] + cur.co_d), c0);
+        if (!more) break;
+        cur = nxt;
+        b = nb;
     }
 }
 
@@ -821,6 +839,154 @@ __global__ void __launch_bounds__(128) dampen_kernel(const BlockGeom g, const fl
         } else {
 #pragma unroll
             for (int k = 0; k < 8; ++k) dp[(int64_t)r * g.dst_row + k * g.C] = (uint8_t)o[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------- dampen on the tensor cores
+// The gain 2^(-4 s (u + v) / 14) = q^u q^v is separable, so dampening an 8 x 8 tile is X' = M X M^T with the
+// 8 x 8 operator M(s) = A^T diag(q^u) A (A = orthonormal DCT-II, q = 2^(-4 s / 14)): per block two small
+// matrix products instead of a forward and an inverse DCT.  A warp owns a 16 x 16 tile -- one luma block
+// (2 x 2 transform tiles, operator diag(M, M)) or two 8 x 8 blocks of a plane with 8-pixel blocks placed on
+// the diagonal quadrants (operator diag(M(s_a), M(s_b))) -- in the accumulator layout of
+// mma.sync.m16n8k16 (f16 x f16 -> f32), chained exactly like the blur above: step 1 M X^T, step 2
+// M (M X^T)^T.  Pixels minus 128 are exact in f16 (M preserves constants, 128 is added back); M and the
+// intermediate are split hi + lo in f16 (lo x lo dropped, 2^-22 relative), fp32 accumulation: the result
+// is within 1e-4 of the float64 reconstruction before rounding (tools/emu/check_dampen_hmma.py), the
+// bar being 0.0255.  10 HMMA per tile; M is built cooperatively (two entries per lane, shared memory).
+__device__ __forceinline__ void hmma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, const float (&c)[4]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%10, %11, %12, %13};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// hi + lo split of two floats: (hi pair, lo pair) as packed f16
+__device__ __forceinline__ void split_half2(float x, float y, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x, y);
+    const float2 back = __half22float2(h);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = pack_half2(x - back.x, y - back.y);
+}
+
+template <int PB>
+__global__ void __launch_bounds__(256) dampen_hmma_kernel(const BlockGeom g, const float* __restrict__ strength) {
+    constexpr int kWarps = 8;
+    constexpr int kSlots = PB == 16 ? 1 : 2;               // operators per tile
+    __shared__ __align__(8) __half s_m[kWarps][2][kSlots][8][8];   // [hi / lo][slot][row][col]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int r0 = imma_tile_row(gq), r1 = imma_tile_row(gq + 8), c0 = 4 * tq;
+    const int hr = gq >= 4, hc = tq >= 2;                  // which half of the tile my rows / columns lie in
+    const bool diag = hr == hc;                            // my 8 pixels sit in a diagonal quadrant
+    // coefficients of this lane's two operator entries: M[i][j] = sum_u q^u A[u][i] A[u][j]
+    float kc[2][8];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int i = (lane >> 3) + 4 * e, j = lane & 7;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float cu = u == 0 ? 0.125f : 0.25f;          // c(u)^2: 1/8 for u = 0, 1/4 otherwise
+            kc[e][u] = cu * cospif((float)((2 * i + 1) * u) / 16.0f) * cospif((float)((2 * j + 1) * u) / 16.0f);
+        }
+    }
+    const int tiles_x = PB == 16 ? g.Bx : (g.Bx + 1) / 2;
+    const int64_t n_tiles = (int64_t)g.T * g.By * tiles_x;
+    const int64_t stride = (int64_t)gridDim.x * kWarps;
+    const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t tile = (int64_t)blockIdx.x * kWarps + w; tile < n_tiles; tile += stride) {
+        const int tx = (int)(tile % tiles_x);
+        const int64_t q = tile / tiles_x;
+        const int by = (int)(q % g.By), t = (int)(q / g.By);
+        // ---- operators of the tile, two entries per lane and slot
+#pragma unroll
+        for (int slot = 0; slot < kSlots; ++slot) {
+            const int bxs = PB == 16 ? tx : 2 * tx + slot;
+            float sv = bxs < g.Bx ? strength[((int64_t)t * g.By + by) * g.Bx + bxs] : 0.f;
+            sv = fminf(fmaxf(sv, 0.f), 1.f);
+            const float qq = exp2f(-4.0f * sv / 14.0f);
+            float pw = 1.f, m0 = 0.f, m1 = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                m0 = fmaf(kc[0][u], pw, m0);
+                m1 = fmaf(kc[1][u], pw, m1);
+                pw *= qq;
+            }
+            const __half h0 = __float2half_rn(m0), h1 = __float2half_rn(m1);
+            s_m[w][0][slot][lane >> 3][lane & 7] = h0;
+            s_m[w][0][slot][4 + (lane >> 3)][lane & 7] = h1;
+            s_m[w][1][slot][lane >> 3][lane & 7] = __float2half_rn(m0 - __half2float(h0));
+            s_m[w][1][slot][4 + (lane >> 3)][lane & 7] = __float2half_rn(m1 - __half2float(h1));
+        }
+        __syncwarp();
+        // ---- my A fragments: rows r0 / r1, columns c0..c0+3 of diag(M, M'); zero off the diagonal quadrants
+        uint32_t ah[4] = {0u, 0u, 0u, 0u}, al[4] = {0u, 0u, 0u, 0u};
+        if (diag) {
+            const int slot = PB == 16 ? 0 : hr;
+            const uint2 h0 = *reinterpret_cast<const uint2*>(&s_m[w][0][slot][r0 & 7][c0 & 7]);
+            const uint2 h1 = *reinterpret_cast<const uint2*>(&s_m[w][0][slot][r1 & 7][c0 & 7]);
+            const uint2 l0 = *reinterpret_cast<const uint2*>(&s_m[w][1][slot][r0 & 7][c0 & 7]);
+            const uint2 l1 = *reinterpret_cast<const uint2*>(&s_m[w][1][slot][r1 & 7][c0 & 7]);
+            ah[0] = h0.x; ah[1] = h1.x; ah[2] = h0.y; ah[3] = h1.y;      // a0 (r0, c0..1)  a1 (r1, c0..1)  a2 (r0, c0+2..3)  a3 (r1, c0+2..3)
+            al[0] = l0.x; al[1] = l1.x; al[2] = l0.y; al[3] = l1.y;
+        }
+        __syncwarp();                                      // the table is free for the next tile
+        // ---- my pixels: luma -- every thread; 8-pixel blocks -- the diagonal quadrants hold blocks 2 tx and 2 tx + 1
+        const int bxq = PB == 16 ? tx : 2 * tx + hr;
+        const bool live = PB == 16 ? true : (diag && bxq < g.Bx);
+        const int64_t col = PB == 16 ? (int64_t)tx * 16 + c0 : (int64_t)bxq * 8 + (c0 & 7);
+        const int rr0 = PB == 16 ? r0 : (r0 & 7), rr1 = PB == 16 ? r1 : (r1 & 7);
+        uint32_t w0 = 0x80808080u, w1 = 0x80808080u;       // 128: zero after centring
+        if (live) {
+            const uint8_t* sp = g.src + (int64_t)t * g.src_frame + (int64_t)by * PB * g.src_row + col;
+            w0 = __ldcs(reinterpret_cast<const uint32_t*>(sp + (int64_t)rr0 * g.src_row));
+            w1 = __ldcs(reinterpret_cast<const uint32_t*>(sp + (int64_t)rr1 * g.src_row));
+        }
+        // bytes -> f16 pairs minus 128: PRMT builds 0x6400 | byte = 1024 + byte, exact subtraction of 1152
+        const __half2 off = __floats2half2_rn(1152.f, 1152.f);
+        auto centred = [&](uint32_t word, int pair) -> uint32_t {
+            const uint32_t e = __byte_perm(word, 0x64646464u, pair ? 0x7372 : 0x7170);
+            const __half2 hv = __hsub2(*reinterpret_cast<const __half2*>(&e), off);
+            return *reinterpret_cast<const uint32_t*>(&hv);
+        };
+        // ---- step 1: M1 = M X^T, n-tile 0 from my first row, n-tile 1 from my second row
+        float m1a[4], m1b[4];
+        {
+            const uint32_t b0 = centred(w0, 0), b1 = centred(w0, 1);
+            hmma_16816(m1a, ah, b0, b1, zero4);
+            hmma_16816(m1a, al, b0, b1, m1a);
+        }
+        {
+            const uint32_t b0 = centred(w1, 0), b1 = centred(w1, 1);
+            hmma_16816(m1b, ah, b0, b1, zero4);
+            hmma_16816(m1b, al, b0, b1, m1b);
+        }
+        // ---- step 2: Z = M M1^T with M1 split hi + lo
+        float z[2][4];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t yh0, yl0, yh1, yl1;
+            split_half2(m1a[2 * half], m1a[2 * half + 1], yh0, yl0);
+            split_half2(m1b[2 * half], m1b[2 * half + 1], yh1, yl1);
+            hmma_16816(z[half], ah, yh0, yh1, zero4);
+            hmma_16816(z[half], al, yh0, yh1, z[half]);
+            hmma_16816(z[half], ah, yl0, yl1, z[half]);
+        }
+        // ---- my first row: (z[0][0], z[0][1], z[1][0], z[1][1]); second row: (z[0][2], z[0][3], z[1][2], z[1][3])
+        if (live) {
+            auto to_byte = [](float v) -> uint32_t {
+                const int i = __float2int_rn(v + 128.f);
+                return (uint32_t)(i < 0 ? 0 : (i > 255 ? 255 : i));
+            };
+            const uint32_t o0 = to_byte(z[0][0]) | (to_byte(z[0][1]) << 8) | (to_byte(z[1][0]) << 16) | (to_byte(z[1][1]) << 24);
+            const uint32_t o1 = to_byte(z[0][2]) | (to_byte(z[0][3]) << 8) | (to_byte(z[1][2]) << 16) | (to_byte(z[1][3]) << 24);
+            uint8_t* dp = g.dst + (int64_t)t * g.dst_frame + (int64_t)by * PB * g.dst_row + col;
+            __stcs(reinterpret_cast<uint32_t*>(dp + (int64_t)rr0 * g.dst_row), o0);
+            __stcs(reinterpret_cast<uint32_t*>(dp + (int64_t)rr1 * g.dst_row), o1);
         }
     }
 }
@@ -999,6 +1165,17 @@ extern "C" int elvis_dct_dampen(const elvis_plane* src, const elvis_plane* dst, 
     if (block_px % 8) return ELVIS_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
     if (int rc = copy_edges(g, st)) return rc;
+    const bool al4 = aligned_to(g.src, 4) && aligned_to(g.dst, 4) && g.src_frame % 4 == 0 && g.dst_frame % 4 == 0 &&
+                     g.src_row % 4 == 0 && g.dst_row % 4 == 0;
+    const char* dampen_impl = getenv("ELVIS_DAMPEN_IMPL");   // hmma (default for planar 16- / 8-pixel blocks) | aan
+    if (g.C == 1 && al4 && (block_px == 16 || block_px == 8) && !(dampen_impl && !strcmp(dampen_impl, "aan"))) {
+        const int64_t tiles = (int64_t)n_frames * by * (block_px == 16 ? bx : (bx + 1) / 2);
+        const int grid = grid_for_units(tiles, 8);
+        if (block_px == 16) dampen_hmma_kernel<16><<<grid, 256, 0, st>>>(g, strength);
+        else dampen_hmma_kernel<8><<<grid, 256, 0, st>>>(g, strength);
+        ELVIS_CHECK_LAUNCH();
+        return ELVIS_OK;
+    }
     const int64_t total = (int64_t)n_frames * (by * block_px / 8) * (bx * block_px / 8) * g.C;
     const bool fast = g.C == 1 && aligned_to(g.src, 8) && aligned_to(g.dst, 8) && g.src_frame % 8 == 0 &&
                       g.dst_frame % 8 == 0 && g.src_row % 8 == 0 && g.dst_row % 8 == 0;

@@ -102,19 +102,31 @@ def allreduce_minmax(mm: torch.Tensor, world: int, group=None) -> torch.Tensor:
 
 def sharded_removability(clip: HaloClip, n_frames_total: int, block_size: int, alpha: float, beta: float,
                          rank: int, world: int, background: Optional[torch.Tensor] = None, kernels=None,
-                         group=None, exchange: bool = True) -> torch.Tensor:
+                         group=None, exchange: bool = True, transport=None) -> torch.Tensor:
     """elvis-mode removability (elvis.py:1160-1220) of the owned frames -> (n, By, Bx) float64.
     background: optional uint8 (n+2, By, Bx) laid out like clip.buf (halo slots filled by the
     caller when it has the neighbours' masks; only slot 0 is ever read).  exchange=False: the
-    caller has already run exchange_halo (e.g. ahead of time on a communication stream)."""
+    caller has already run exchange_halo (e.g. ahead of time on a communication stream).
+    transport: None = NCCL send/recv + all-reduce (torch.distributed); an elvis_b200.peer.PeerGroup =
+    copy-engine peer copies and mailbox all-reduces over NVLink (clip must come from its halo_clip())."""
     if kernels is None:
         from . import ops as kernels
     check_shardable(n_frames_total, world)
-    if exchange:
+    peer = transport if (transport is not None and world > 1) else None
+    if peer is not None:
+        if exchange:
+            peer.exchange_halo(clip)
+        peer.wait_halo(clip)
+    elif exchange:
         exchange_halo(clip, rank, world, group)
     ext, first = clip.extended(rank, world)
     sc, tc, norm = kernels.score_sc_tc(ext, block_size, minmax_range=(first, first + clip.n))
-    allreduce_minmax(norm, world, group)
+    if peer is not None:
+        peer.release_halo(clip)          # stream ordered: the scoring kernel has read the halo slots
+        reduce_ = peer.allreduce_minmax_
+    else:
+        reduce_ = lambda mm: allreduce_minmax(mm, world, group)      # noqa: E731
+    reduce_(norm)
     bg = None
     if background is not None:
         lo = 1 - first
@@ -122,19 +134,26 @@ def sharded_removability(clip: HaloClip, n_frames_total: int, block_size: int, a
     r, mm = kernels.combine_removability(sc, tc, norm, alpha, beta, bg, t_begin=first, t_count=clip.n,
                                          is_first=(rank == 0), is_last=(rank == world - 1),
                                          clip_frames=n_frames_total)
-    allreduce_minmax(mm, world, group)
+    reduce_(mm)
     return kernels.normalize_(r, mm)
 
 
 def sharded_importance(clip: HaloClip, block_size: int, alpha: float, beta: float, rank: int, world: int,
-                       foreground: Optional[torch.Tensor] = None, kernels=None, group=None) -> torch.Tensor:
+                       foreground: Optional[torch.Tensor] = None, kernels=None, group=None, transport=None) -> torch.Tensor:
     """utils-mode importance (utils.py:665-688) of the owned frames: per-frame normalisation,
-    so the halo exchange is the only communication."""
+    so the halo exchange is the only communication (transport: see sharded_removability)."""
     if kernels is None:
         from . import ops as kernels
-    exchange_halo(clip, rank, world, group)
+    peer = transport if (transport is not None and world > 1) else None
+    if peer is not None:
+        peer.exchange_halo(clip)
+        peer.wait_halo(clip)
+    else:
+        exchange_halo(clip, rank, world, group)
     ext, first = clip.extended(rank, world)
     sc, tc, _ = kernels.score_sc_tc(ext, block_size)
+    if peer is not None:
+        peer.release_halo(clip)
     fg = None
     if foreground is not None:
         lo = 1 - first

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ELVIS_B200_ABI_VERSION 4
+#define ELVIS_B200_ABI_VERSION 5
 
 #define ELVIS_OK               0
 #define ELVIS_ERR_INVALID_ARG (-1)   /* NULL pointer, non-positive size, out-of-range parameter   */
@@ -354,6 +354,34 @@ ELVIS_API int elvis_rgb_to_gray(const elvis_plane* rgb, const elvis_plane* y, in
  * kept blocks whose rank is >= capacity (= shrunk_by * shrunk_bx).  Feed it to elvis_gather_blocks. */
 ELVIS_API int elvis_refill_map(const uint8_t* mask, int32_t n_frames, int64_t blocks_per_frame, int64_t capacity, int32_t* map,
                      elvis_stream_t stream);
+
+/* ---- e: frame sharding over peer memory (NVLink / NVSwitch; SURVEY.md 8e, the split of elvis.py:264-278).
+ * These replace the NCCL send/recv halo exchange and the two NCCL all-reduces of the sharded scorer
+ * (elvis_b200/sharding.py keeps both transports).  Memory that other ranks touch comes from
+ * elvis_peer_alloc (cudaMalloc + zero fill + CUDA IPC handle; this one call synchronises the device) and
+ * is mapped by the peers with elvis_peer_open; the 64-byte handles travel over the caller's own channel
+ * (torch.distributed).  Sequence numbers are 32-bit counters that only grow (modular comparison).
+ *   elvis_peer_put     copy-engine peer copy of `bytes` into a peer's buffer, then a release store of `seq`
+ *                      into a flag word in the peer's memory (stream ordered);
+ *   elvis_peer_signal  the release store alone (e.g. "your halo slot is free again");
+ *   elvis_peer_wait    enqueue a wait until a flag word in LOCAL memory has reached `seq`;
+ *   elvis_peer_allreduce_minmax   in-place all-reduce of n <= 8 interleaved {min, max, ...} values (float32 or
+ *                      float64, dtype = ELVIS_F32 / ELVIS_F64) through per-rank mailboxes of
+ *                      elvis_peer_mailbox_bytes() bytes: host_mailboxes[r] = rank r's mailbox as mapped in this
+ *                      process (own included), slot = call counter % 4, seq = call counter (>= 1).  Calls of one
+ *                      rank must be stream ordered.
+ * Waits give up after 4 s and store 1 into *error_word (device memory, may be NULL) instead of hanging. */
+ELVIS_API int64_t elvis_peer_mailbox_bytes(void);
+ELVIS_API int elvis_peer_alloc(int64_t bytes, void** device_ptr, void* host_handle_64_bytes);
+ELVIS_API int elvis_peer_open(const void* host_handle_64_bytes, void** device_ptr);
+ELVIS_API int elvis_peer_close(void* device_ptr);
+ELVIS_API int elvis_peer_free(void* device_ptr);
+ELVIS_API int elvis_peer_put(void* peer_dst, const void* src, int64_t bytes, uint32_t* peer_flag, uint32_t seq, elvis_stream_t stream);
+ELVIS_API int elvis_peer_signal(uint32_t* peer_flag, uint32_t seq, elvis_stream_t stream);
+ELVIS_API int elvis_peer_wait(const uint32_t* local_flag, uint32_t seq, int32_t* error_word, elvis_stream_t stream);
+ELVIS_API int elvis_peer_allreduce_minmax(void* inout, int32_t dtype, int32_t n_values, int32_t rank, int32_t world,
+                                void* const* host_mailboxes, int32_t slot, uint32_t seq, int32_t* error_word,
+                                elvis_stream_t stream);
 
 #ifdef __cplusplus
 }

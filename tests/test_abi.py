@@ -19,7 +19,7 @@ def lib():
 
 def test_every_declared_symbol_is_exported(lib):
     header = open(os.path.join(ROOT, "include", "elvis_b200.h")).read()
-    declared = set(re.findall(r"ELVIS_API\s+(?:const\s+char\*|int)\s+(elvis_\w+)\s*\(", header))
+    declared = set(re.findall(r"ELVIS_API\s+(?:const\s+char\*|int64_t|int)\s+(elvis_\w+)\s*\(", header))
     assert len(declared) >= 19
     assert declared == set(lib.EXPORTS)
     for name in declared:

@@ -1,6 +1,7 @@
 """-m gpu, needs >= 2 GPUs (skipped on a one-GPU box): the frame-sharded scorer on real devices --
-halo exchange and global min / max reductions over NCCL (NVLink) -- must give BIT-IDENTICAL scores
-and masks to one GPU scoring the whole clip (elvis.py:264-278 split)."""
+halo exchange and global min / max reductions over NCCL, and over peer memory (copy-engine peer copies +
+mailbox all-reduces, elvis_b200/peer.py) -- must give BIT-IDENTICAL scores and masks to one GPU scoring
+the whole clip (elvis.py:264-278 split)."""
 import os
 import socket
 
@@ -24,27 +25,33 @@ def _worker(rank, world, port, y_all, bs, transport, results):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        from elvis_b200 import ops, sharding
+        from elvis_b200 import ops, peer, sharding
         T, H, W = y_all.shape
         a, b = sharding.frame_range(T, rank, world)
-        clip = sharding.HaloClip(b - a, H, W, dev)
-        clip.owned.copy_(y_all[a:b])
+        pg = peer.PeerGroup(rank, world, dev) if transport == "peer" else None
+        clip = pg.halo_clip(b - a, H, W) if pg else sharding.HaloClip(b - a, H, W, dev)
         k = (W // bs) // 2
         out = {}
-        for rep in range(2):          # twice: the second pass reuses whatever state the transport keeps
-            r = sharding.sharded_removability(clip, T, bs, 0.5, 0.5, rank, world)
+        for rep in range(3):          # several passes: sequence numbers, acknowledgements and mailbox slots get reused
+            # the first two passes run on different pixels: halos left over from them must not survive into the last
+            clip.owned.copy_(y_all[a:b] if rep == 2 else torch.roll(y_all[a:b], 24, dims=2))
+            r = sharding.sharded_removability(clip, T, bs, 0.5, 0.5, rank, world, transport=pg)
             mask = ops.select_rows(r, k, ops.REMOVE_HIGH)
-            imp = sharding.sharded_importance(clip, bs, 0.5, 0.5, rank, world)
+            imp = sharding.sharded_importance(clip, bs, 0.5, 0.5, rank, world, transport=pg)
             torch.cuda.synchronize()
             out[rep] = (r.cpu().numpy(), mask.cpu().numpy(), imp.cpu().numpy())
-        assert all(np.array_equal(x, y_) for x, y_ in zip(out[0], out[1]))
-        results[rank] = (a, b) + out[1]
+        assert not np.array_equal(out[0][0], out[2][0])
+        if pg:
+            pg.check()
+            pg.close()
+        results[rank] = (a, b) + out[2]
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("transport", ["nccl", "peer"])
 @pytest.mark.parametrize("T,H,W,bs", [(11, 96, 160, 16), (30, 1088, 1920, 16), (9, 64, 256, 8)])
-def test_sharded_equals_single_gpu(T, H, W, bs):
+def test_sharded_equals_single_gpu(T, H, W, bs, transport):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -62,7 +69,7 @@ def test_sharded_equals_single_gpu(T, H, W, bs):
     ref_imp = ops.importance_scores(sc, tc, None, 0.5, 0.5)
     ref, ref_mask, ref_imp = ref.cpu().numpy(), ref_mask.cpu().numpy(), ref_imp.cpu().numpy()
     results = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), torch.from_numpy(y), bs, "nccl", results), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), torch.from_numpy(y), bs, transport, results), nprocs=world, join=True)
     for rank in range(world):
         a, b, r, m, imp = results[rank]
         assert np.array_equal(r, ref[a:b]), (rank, "scores")
