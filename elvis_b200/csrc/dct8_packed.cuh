@@ -42,4 +42,32 @@ __device__ __forceinline__ float2 f2fmas(float2 a, float s, float2 c) { return _
         d7 = f2sub(z11, z4);                                                   \
     } while (0)
 
+// inverse transform of d0..d7 (float2 lvalues, inputs pre-multiplied by kInvScale), in place
+#define ELVIS_IDCT8_X2(d0, d1, d2, d3, d4, d5, d6, d7)                         \
+    do {                                                                       \
+        float2 t10 = f2add(d0, d4), t11 = f2sub(d0, d4);                       \
+        float2 t13 = f2add(d2, d6);                                            \
+        float2 t12 = f2sub(f2muls(f2sub(d2, d6), 1.41421356237309505f), t13);  \
+        float2 e0 = f2add(t10, t13), e3 = f2sub(t10, t13);                     \
+        float2 e1 = f2add(t11, t12), e2 = f2sub(t11, t12);                     \
+        float2 z13 = f2add(d5, d3), z10 = f2sub(d5, d3);                       \
+        float2 z11 = f2add(d1, d7), z12 = f2sub(d1, d7);                       \
+        float2 o7 = f2add(z11, z13);                                           \
+        float2 u11 = f2muls(f2sub(z11, z13), 1.41421356237309505f);            \
+        float2 z5 = f2muls(f2add(z10, z12), 1.84775906502257351f);             \
+        float2 u10 = f2sub(f2muls(z12, 1.08239220029239397f), z5);             \
+        float2 u12 = f2fmas(z10, -2.61312592975275306f, z5);                   \
+        float2 o6 = f2sub(u12, o7);                                            \
+        float2 o5 = f2sub(u11, o6);                                            \
+        float2 o4 = f2add(u10, o5);                                            \
+        d0 = f2add(e0, o7);                                                    \
+        d7 = f2sub(e0, o7);                                                    \
+        d1 = f2add(e1, o6);                                                    \
+        d6 = f2sub(e1, o6);                                                    \
+        d2 = f2add(e2, o5);                                                    \
+        d5 = f2sub(e2, o5);                                                    \
+        d4 = f2add(e3, o4);                                                    \
+        d3 = f2sub(e3, o4);                                                    \
+    } while (0)
+
 }  // namespace elvis

@@ -8,6 +8,7 @@
 // is an explicitly rounded fp32 op in cv2's accumulation order.
 #include "common.cuh"
 #include "dct8.cuh"
+#include "dct8_packed.cuh"
 #include "down_pow2.cuh"
 #include <cstring>
 #include <cuda_fp16.h>
@@ -727,48 +728,45 @@ struct YuvGeom {
 __global__ void __launch_bounds__(256) downsample_pow2_yuv420_kernel(const YuvGeom g, const int32_t* __restrict__ levels, int max_level) {
     constexpr int kWarps = 8;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t n_blocks = (int64_t)g.T * g.By * g.Bx;
-    const int64_t stride = (int64_t)gridDim.x * kWarps;
+    // one CTA per (frame, block row): no index division in the loop, the eight warps walk the row 8 blocks apart
+    const int t = blockIdx.x / g.By, by = blockIdx.x - t * g.By;
     // luma: lane = (row, 8-pixel half); chroma: lanes 0..15 U, 16..31 V, lane = (row, 4-pixel half) inside its group
     const int yr = lane >> 1, yh = lane & 1;
     const int pl = 1 + (lane >> 4), gl = lane & 15, cr = gl >> 1, ch = gl & 1;
-    struct Item {
-        int64_t yo_s, yo_d, co_s, co_d;
-        uint2 y;
-        uint32_t c;
-        int L;
-    };
-    auto fetch = [&](int64_t b, Item& it) {       // addresses, level and pixels of block b (loads stay in flight)
-        const int bx = (int)(b % g.Bx);
-        const int64_t q = b / g.Bx;
-        const int by = (int)(q % g.By), t = (int)(q / g.By);
-        it.yo_s = (int64_t)t * g.src_frame[0] + ((int64_t)by * 16 + yr) * g.src_row[0] + (int64_t)bx * 16 + 8 * yh;
-        it.yo_d = (int64_t)t * g.dst_frame[0] + ((int64_t)by * 16 + yr) * g.dst_row[0] + (int64_t)bx * 16 + 8 * yh;
-        it.co_s = (int64_t)t * g.src_frame[pl] + ((int64_t)by * 8 + cr) * g.src_row[pl] + (int64_t)bx * 8 + 4 * ch;
-        it.co_d = (int64_t)t * g.dst_frame[pl] + ((int64_t)by * 8 + cr) * g.dst_row[pl] + (int64_t)bx * 8 + 4 * ch;
-        it.y = __ldcs(reinterpret_cast<const uint2*>(g.src[0] + it.yo_s));
-        it.c = __ldcs(reinterpret_cast<const uint32_t*>(g.src[pl] + it.co_s));
-        it.L = __ldg(levels + b);
-    };
-    int64_t b = (int64_t)blockIdx.x * kWarps + w;
-    if (b >= n_blocks) return;
-    Item cur, nxt;
-    fetch(b, cur);
+    const uint8_t* ys = g.src[0] + (int64_t)t * g.src_frame[0] + ((int64_t)by * 16 + yr) * g.src_row[0] + 8 * yh;
+    uint8_t* yd = g.dst[0] + (int64_t)t * g.dst_frame[0] + ((int64_t)by * 16 + yr) * g.dst_row[0] + 8 * yh;
+    const uint8_t* cs = g.src[pl] + (int64_t)t * g.src_frame[pl] + ((int64_t)by * 8 + cr) * g.src_row[pl] + 4 * ch;
+    uint8_t* cd = g.dst[pl] + (int64_t)t * g.dst_frame[pl] + ((int64_t)by * 8 + cr) * g.dst_row[pl] + 4 * ch;
+    const int32_t* lv = levels + (int64_t)blockIdx.x * g.Bx;
+    int bx = w;
+    if (bx >= g.Bx) return;
+    uint2 y = __ldcs(reinterpret_cast<const uint2*>(ys + bx * 16));
+    uint32_t c = __ldcs(reinterpret_cast<const uint32_t*>(cs + bx * 8));
+    int L = __ldg(lv + bx);
     for (;;) {
-        const int64_t nb = b + stride;
-        const bool more = nb < n_blocks;
-        if (more) fetch(nb, nxt);                 // the next block's loads overlap this block's arithmetic
-        const int L = cur.L < 0 ? 0 : (cur.L > max_level ? max_level : cur.L);
-        uint32_t p0 = cur.y.x, p1 = cur.y.y, c0 = cur.c, c1 = 0u;
+        const int nx = bx + kWarps;
+        const bool more = nx < g.Bx;
+        uint2 y2 = y;
+        uint32_t c2 = c;
+        int L2 = 0;
+        if (more) {                               // the next block's loads overlap this block's arithmetic
+            y2 = __ldcs(reinterpret_cast<const uint2*>(ys + nx * 16));
+            c2 = __ldcs(reinterpret_cast<const uint32_t*>(cs + nx * 8));
+            L2 = __ldg(lv + nx);
+        }
+        L = L < 0 ? 0 : (L > max_level ? max_level : L);
+        uint32_t p0 = y.x, p1 = y.y, c0 = c, c1 = 0u;
         if (L > 0) {
             down_up_pow2_level<16>(p0, p1, L > 4 ? 4 : L, lane, 0);
             down_up_pow2_level<8>(c0, c1, L > 3 ? 3 : L, gl, lane & 16);
         }
-        __stcs(reinterpret_cast<uint2*>(g.dst[0] + cur.yo_d), make_uint2(p0, p1));
-        __stcs(reinterpret_cast<uint32_t*>(g.dst[pl] + cur.co_d), c0);
+        __stcs(reinterpret_cast<uint2*>(yd + bx * 16), make_uint2(p0, p1));
+        __stcs(reinterpret_cast<uint32_t*>(cd + bx * 8), c0);
         if (!more) break;
-        cur = nxt;
-        b = nb;
+        y = y2;
+        c = c2;
+        L = L2;
+        bx = nx;
     }
 }
 
@@ -840,6 +838,78 @@ __global__ void __launch_bounds__(128) dampen_kernel(const BlockGeom g, const fl
 #pragma unroll
             for (int k = 0; k < 8; ++k) dp[(int64_t)r * g.dst_row + k * g.C] = (uint8_t)o[k];
         }
+    }
+}
+
+// The same per-tile transform for planar, 8-byte aligned planes with half the floating-point instructions
+// where it is free: the tile lives in registers as packed fp32 pairs (row r, columns 2j / 2j+1); the passes
+// along a row are scalar butterflies on the halves, the passes down the columns are ONE packed butterfly per
+// column pair (FADD2 / FMUL2 / FFMA2), the gains multiply pairs, and the bytes come back through the
+// magic-number rounding (x + 1.5 * 2^23: round-half-even like rint, full-rate FADD2 instead of the
+// quarter-rate F2I) and cvt.pack.sat (clamp + pack, two pixels per instruction).
+__device__ __forceinline__ uint32_t pack_sat_u8x4(int a, int b, int c, int d) {     // bytes (a, b, c, d), each clamped to 0..255
+    uint32_t lo, r;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(lo) : "r"(d), "r"(c), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(a), "r"(lo));
+    return r;
+}
+
+__global__ void __launch_bounds__(128) dampen_packed_kernel(const BlockGeom g, const float* __restrict__ strength, const uint32_t magic) {
+    const int tiles_x = g.Bx * g.pb / 8, tiles_y = g.By * g.pb / 8;
+    const int64_t total = (int64_t)g.T * tiles_y * tiles_x;
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    int64_t b = id;
+    const int txi = (int)(b % tiles_x);
+    b /= tiles_x;
+    const int tyi = (int)(b % tiles_y);
+    const int t = (int)(b / tiles_y);
+    const float s = fminf(fmaxf(strength[((int64_t)t * g.By + (tyi * 8) / g.pb) * g.Bx + (txi * 8) / g.pb], 0.f), 1.f);
+    const uint8_t* sp = g.src + (int64_t)t * g.src_frame + (int64_t)tyi * 8 * g.src_row + (int64_t)txi * 8;
+    uint8_t* dp = g.dst + (int64_t)t * g.dst_frame + (int64_t)tyi * 8 * g.dst_row + (int64_t)txi * 8;
+
+    float2 x[8][4];
+    const float2 bias = make_float2(-8388608.f, -8388608.f);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint2 v = __ldcs(reinterpret_cast<const uint2*>(sp + (int64_t)r * g.src_row));
+        x[r][0] = __fadd2_rn(make_float2(byte_as_biased_float<0>(v.x, magic), byte_as_biased_float<1>(v.x, magic)), bias);
+        x[r][1] = __fadd2_rn(make_float2(byte_as_biased_float<2>(v.x, magic), byte_as_biased_float<3>(v.x, magic)), bias);
+        x[r][2] = __fadd2_rn(make_float2(byte_as_biased_float<0>(v.y, magic), byte_as_biased_float<1>(v.y, magic)), bias);
+        x[r][3] = __fadd2_rn(make_float2(byte_as_biased_float<2>(v.y, magic), byte_as_biased_float<3>(v.y, magic)), bias);
+    }
+    // forward: along the rows (scalar), then down the columns (packed)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) ELVIS_FDCT8(x[r][0].x, x[r][0].y, x[r][1].x, x[r][1].y, x[r][2].x, x[r][2].y, x[r][3].x, x[r][3].y);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ELVIS_FDCT8_X2(x[0][j], x[1][j], x[2][j], x[3][j], x[4][j], x[5][j], x[6][j], x[7][j]);
+    // gain 2^(-4 s (u+v)/14) / 64: powers of q = 2^(-4 s / 14); the 1/64 undoes the AAN scaling
+    float gk[15];
+    const float q = exp2f(-4.0f * s / 14.0f);
+    gk[0] = 1.0f / 64.0f;
+#pragma unroll
+    for (int k = 1; k < 15; ++k) gk[k] = gk[k - 1] * q;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[u][j] = __fmul2_rn(x[u][j], make_float2(gk[u + 2 * j], gk[u + 2 * j + 1]));
+    // inverse: down the columns (packed), then along the rows (scalar)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ELVIS_IDCT8_X2(x[0][j], x[1][j], x[2][j], x[3][j], x[4][j], x[5][j], x[6][j], x[7][j]);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) ELVIS_IDCT8(x[r][0].x, x[r][0].y, x[r][1].x, x[r][1].y, x[r][2].x, x[r][2].y, x[r][3].x, x[r][3].y);
+    // round half to even and clamp: x + 1.5 * 2^23 leaves rint(x) in the low mantissa bits (two's complement around 0x4B400000)
+    const float2 rnd = make_float2(12582912.f, 12582912.f);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        int n[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 y = __fadd2_rn(x[r][j], rnd);
+            n[2 * j] = __float_as_int(y.x) - 0x4B400000;
+            n[2 * j + 1] = __float_as_int(y.y) - 0x4B400000;
+        }
+        __stcs(reinterpret_cast<uint2*>(dp + (int64_t)r * g.dst_row), make_uint2(pack_sat_u8x4(n[0], n[1], n[2], n[3]), pack_sat_u8x4(n[4], n[5], n[6], n[7])));
     }
 }
 
@@ -1167,8 +1237,10 @@ extern "C" int elvis_dct_dampen(const elvis_plane* src, const elvis_plane* dst, 
     if (int rc = copy_edges(g, st)) return rc;
     const bool al4 = aligned_to(g.src, 4) && aligned_to(g.dst, 4) && g.src_frame % 4 == 0 && g.dst_frame % 4 == 0 &&
                      g.src_row % 4 == 0 && g.dst_row % 4 == 0;
-    const char* dampen_impl = getenv("ELVIS_DAMPEN_IMPL");   // hmma (default for planar 16- / 8-pixel blocks) | aan
-    if (g.C == 1 && al4 && (block_px == 16 || block_px == 8) && !(dampen_impl && !strcmp(dampen_impl, "aan"))) {
+    // ELVIS_DAMPEN_IMPL=hmma selects the tensor-core variant (correct, but measured 2.8x slower than the CUDA-core
+    // kernel on B200: 0.99 vs 0.35 ms per 30 4K frames -- one dependent chain per tile)
+    const char* dampen_impl = getenv("ELVIS_DAMPEN_IMPL");
+    if (g.C == 1 && al4 && (block_px == 16 || block_px == 8) && dampen_impl && !strcmp(dampen_impl, "hmma")) {
         const int64_t tiles = (int64_t)n_frames * by * (block_px == 16 ? bx : (bx + 1) / 2);
         const int grid = grid_for_units(tiles, 8);
         if (block_px == 16) dampen_hmma_kernel<16><<<grid, 256, 0, st>>>(g, strength);
@@ -1180,7 +1252,9 @@ extern "C" int elvis_dct_dampen(const elvis_plane* src, const elvis_plane* dst, 
     const bool fast = g.C == 1 && aligned_to(g.src, 8) && aligned_to(g.dst, 8) && g.src_frame % 8 == 0 &&
                       g.dst_frame % 8 == 0 && g.src_row % 8 == 0 && g.dst_row % 8 == 0;
     const unsigned grid = (unsigned)((total + 127) / 128);
-    if (fast)
+    if (fast && !(dampen_impl && !strcmp(dampen_impl, "scalar")))      // packed-fp32 kernel (default); ELVIS_DAMPEN_IMPL=scalar: the round-1 kernel
+        dampen_packed_kernel<<<grid, 128, 0, st>>>(g, strength, 0x4B000000u);
+    else if (fast)
         dampen_kernel<true><<<grid, 128, 0, st>>>(g, strength);
     else
         dampen_kernel<false><<<grid, 128, 0, st>>>(g, strength);
@@ -1234,8 +1308,8 @@ extern "C" int elvis_degrade_downsample_pow2_yuv420(const elvis_plane* src_yuv, 
     g.T = n_frames;
     g.By = by;
     g.Bx = bx;
-    const int64_t blocks = (int64_t)n_frames * by * bx;
-    downsample_pow2_yuv420_kernel<<<grid_for_units(blocks, 8), 256, 0, as_stream(stream)>>>(g, levels, max_level);
+    if ((int64_t)n_frames * by > 0x7fffffffLL) return ELVIS_ERR_UNSUPPORTED;
+    downsample_pow2_yuv420_kernel<<<(unsigned)((int64_t)n_frames * by), 256, 0, as_stream(stream)>>>(g, levels, max_level);
     ELVIS_CHECK_LAUNCH();
     return ELVIS_OK;
 }

@@ -498,10 +498,12 @@ def test_mask_bit_packing(dev):
     assert np.array_equal(E.unpack_removal_masks(packed, shape), m)
 
 
+@pytest.mark.parametrize("impl", ["packed", "scalar", "hmma"])      # packed-fp32 kernel (default) / round-1 scalar kernel / tensor-core variant
 @pytest.mark.parametrize("pb", [8, 16])
-def test_dct_dampen(dev, pb):
+def test_dct_dampen(dev, monkeypatch, pb, impl):
     from elvis_b200 import ops
-    T, H, W = 2, pb * 4, pb * 6
+    monkeypatch.setenv("ELVIS_DAMPEN_IMPL", impl)
+    T, H, W = 2, pb * 4, pb * (7 if impl == "hmma" else 6)        # an odd block count leaves the last tile of the hmma path half empty
     y = synth_luma(T, H, W, seed=pb)
     rng = np.random.default_rng(pb)
     s = rng.random((T, H // pb, W // pb)).astype(np.float32)
