@@ -334,11 +334,11 @@ __global__ void __launch_bounds__(256) blur_imma_kernel(const BlockGeom g, const
                 const uint32_t q2 = (uint32_t)m1b[2 * half], q3 = (uint32_t)m1b[2 * half + 1];
                 const uint32_t hi = __byte_perm(__byte_perm(q0, q1, 0x0051), __byte_perm(q2, q3, 0x0051), 0x5410);
                 const uint32_t lo = __byte_perm(__byte_perm(q0, q1, 0x0040), __byte_perm(q2, q3, 0x0040), 0x5410);
-                int acc[4];
+                int acc[4], acl[4];                            // two independent products: shorter dependent chain per round
                 imma_16816(acc, a0, a1, hi, half4);
+                imma_16816(acl, a0, a1, lo, zero4);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i] <<= 8;
-                imma_16816(acc, a0, a1, lo, acc);
+                for (int i = 0; i < 4; ++i) acc[i] = acc[i] * 256 + acl[i];
                 // my first row's word comes from acc[0..1] of both halves, my second row's from acc[2..3]: keep all four
                 z[half] = __byte_perm(__byte_perm((uint32_t)acc[0], (uint32_t)acc[1], 0x0062), __byte_perm((uint32_t)acc[2], (uint32_t)acc[3], 0x0062), 0x5410);
             }
