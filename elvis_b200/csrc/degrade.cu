@@ -738,35 +738,54 @@ __global__ void __launch_bounds__(256) downsample_pow2_yuv420_kernel(const YuvGe
     const uint8_t* cs = g.src[pl] + (int64_t)t * g.src_frame[pl] + ((int64_t)by * 8 + cr) * g.src_row[pl] + 4 * ch;
     uint8_t* cd = g.dst[pl] + (int64_t)t * g.dst_frame[pl] + ((int64_t)by * 8 + cr) * g.dst_row[pl] + 4 * ch;
     const int32_t* lv = levels + (int64_t)blockIdx.x * g.Bx;
-    int bx = w;
-    if (bx >= g.Bx) return;
-    uint2 y = __ldcs(reinterpret_cast<const uint2*>(ys + bx * 16));
-    uint32_t c = __ldcs(reinterpret_cast<const uint32_t*>(cs + bx * 8));
-    int L = __ldg(lv + bx);
+    // two blocks per iteration, the next pair's loads in flight during the arithmetic (bytes in flight per warp: 4 blocks)
+    constexpr int kUnroll = 2;
+    uint2 y[kUnroll];
+    uint32_t c[kUnroll];
+    int L[kUnroll];
+    auto fetch = [&](int bx0, uint2 (&yy)[kUnroll], uint32_t (&cc)[kUnroll], int (&ll)[kUnroll]) {
+#pragma unroll
+        for (int i = 0; i < kUnroll; ++i) {
+            const int bx = bx0 + i * kWarps;
+            if (bx < g.Bx) {
+                yy[i] = __ldcs(reinterpret_cast<const uint2*>(ys + bx * 16));
+                cc[i] = __ldcs(reinterpret_cast<const uint32_t*>(cs + bx * 8));
+                ll[i] = __ldg(lv + bx);
+            }
+        }
+    };
+    int bx0 = w;
+    if (bx0 >= g.Bx) return;
+    fetch(bx0, y, c, L);
     for (;;) {
-        const int nx = bx + kWarps;
+        const int nx = bx0 + kUnroll * kWarps;
         const bool more = nx < g.Bx;
-        uint2 y2 = y;
-        uint32_t c2 = c;
-        int L2 = 0;
-        if (more) {                               // the next block's loads overlap this block's arithmetic
-            y2 = __ldcs(reinterpret_cast<const uint2*>(ys + nx * 16));
-            c2 = __ldcs(reinterpret_cast<const uint32_t*>(cs + nx * 8));
-            L2 = __ldg(lv + nx);
+        uint2 y2[kUnroll];
+        uint32_t c2[kUnroll];
+        int L2[kUnroll];
+        if (more) fetch(nx, y2, c2, L2);
+#pragma unroll
+        for (int i = 0; i < kUnroll; ++i) {
+            const int bx = bx0 + i * kWarps;
+            if (bx < g.Bx) {                      // warp-uniform
+                const int lvl = L[i] < 0 ? 0 : (L[i] > max_level ? max_level : L[i]);
+                uint32_t p0 = y[i].x, p1 = y[i].y, c0 = c[i], c1 = 0u;
+                if (lvl > 0) {
+                    down_up_pow2_level<16>(p0, p1, lvl > 4 ? 4 : lvl, lane, 0);
+                    down_up_pow2_level<8>(c0, c1, lvl > 3 ? 3 : lvl, gl, lane & 16);
+                }
+                __stcs(reinterpret_cast<uint2*>(yd + bx * 16), make_uint2(p0, p1));
+                __stcs(reinterpret_cast<uint32_t*>(cd + bx * 8), c0);
+            }
         }
-        L = L < 0 ? 0 : (L > max_level ? max_level : L);
-        uint32_t p0 = y.x, p1 = y.y, c0 = c, c1 = 0u;
-        if (L > 0) {
-            down_up_pow2_level<16>(p0, p1, L > 4 ? 4 : L, lane, 0);
-            down_up_pow2_level<8>(c0, c1, L > 3 ? 3 : L, gl, lane & 16);
-        }
-        __stcs(reinterpret_cast<uint2*>(yd + bx * 16), make_uint2(p0, p1));
-        __stcs(reinterpret_cast<uint32_t*>(cd + bx * 8), c0);
         if (!more) break;
-        y = y2;
-        c = c2;
-        L = L2;
-        bx = nx;
+#pragma unroll
+        for (int i = 0; i < kUnroll; ++i) {
+            y[i] = y2[i];
+            c[i] = c2[i];
+            L[i] = L2[i];
+        }
+        bx0 = nx;
     }
 }
 

@@ -933,3 +933,40 @@ def test_pipeline_with_block_sized_transform(dev):
     assert np.array_equal(mask, P.select_rows(scores, W // bs // 2, P.REMOVE_HIGH))
     for t in range(T):
         assert np.array_equal(full.y[t].cpu().numpy(), P.stretch_plane(P.shrink_plane(y[t], mask[t], bs), mask[t], bs))
+
+
+def test_host_server_and_client_legs(dev):
+    """HostElvisV1(outputs=("mask", "shrunk"), pack_masks=True) is the reference's server (elvis.py:4389-4418: shrunk
+    frames + np.packbits mask side channel) and HostElvisClient its client (elvis.py:4537-4557): together they must
+    reproduce the composite path, and the packed masks must be np.packbits' bytes."""
+    import torch
+    from elvis_b200.pipeline import ElvisV1, HostElvisClient, HostElvisV1, Yuv420
+    T, H, W, bs = 4, 64, 160, 16
+    y, u, v = synth_yuv420(T, H, W, seed=52)
+    i420 = torch.from_numpy(np.concatenate([y.reshape(T, -1), u.reshape(T, -1), v.reshape(T, -1)], axis=1)).pin_memory()
+    ref = ElvisV1(bs, 0.5, 0.5, 0.5).run(Yuv420(to_dev(y, dev), to_dev(u, dev), to_dev(v, dev)))
+    ref_mask = ref[1].cpu().numpy()
+    server = HostElvisV1(T, H, W, bs, 0.5, 0.5, 0.5, dev, depth=2, outputs=("mask", "shrunk"), pack_masks=True)
+    shrunk_h, full_h, bits_h = server.host_buffers()
+    assert full_h is None and bits_h.numel() == (T * (H // bs) * (W // bs) + 7) // 8
+    assert server.d2h_bytes == shrunk_h.numel() + bits_h.numel() and "full" not in server.slots[0]
+    for _ in range(3):                     # the slots are reused
+        server.process(i420, shrunk_h, None, bits_h).synchronize()
+    assert np.array_equal(bits_h.numpy(), np.packbits(ref_mask))
+    sw = ref[2].y.shape[2]
+    for a, b in zip(Yuv420.from_i420(shrunk_h, H, sw).planes, ref[2].planes):
+        assert torch.equal(a, b.cpu())
+    client = HostElvisClient(T, H, W, bs, 0.5, dev, depth=2)
+    out = torch.empty((T, H * W * 3 // 2), dtype=torch.uint8).pin_memory()
+    for _ in range(3):
+        client.process(shrunk_h, bits_h, out).synchronize()
+    for a, b in zip(Yuv420.from_i420(out, H, W).planes, ref[3].planes):
+        assert torch.equal(a, b.cpu())
+    assert client.h2d_bytes == shrunk_h.numel() + bits_h.numel() and client.d2h_bytes == out.numel()
+    # unpacked masks, stretched only
+    only = HostElvisV1(T, H, W, bs, 0.5, 0.5, 0.5, dev, depth=1, outputs=("stretched",))
+    _, full2, _ = only.host_buffers()
+    only.process(i420, None, full2, None).synchronize()
+    assert torch.equal(full2, out)
+    with pytest.raises(ValueError):
+        HostElvisV1(T, H, W, bs, outputs=("scores",))
