@@ -436,24 +436,33 @@ def measure_v1(ctx, workload, steps, warmup, with_e2e, with_cpu, with_parity):
                               move_ctas_per_sm=args.move_ctas, comm_fn=comm_fn, split_stretch=split,
                               stretch_ctas_per_sm=args.stretch_ctas)
         counter = [0]
+        host_s = [0.0]
 
         def run():
+            t_h = time.perf_counter()
             for _ in range(clips_per_step):
                 pp.submit(clips[counter[0] % distinct])
                 counter[0] += 1
             pp.join()
+            host_s[0] += time.perf_counter() - t_h
         mode = f"{depth} clips in flight on {3 if split else 2} CUDA streams" + (" (+1 for the halo exchange)" if world > 1 else "") + \
                " (elvis_b200.pipeline.ElvisV1Pipelined); every clip takes the full serial path"
     else:
         counter = [0]
+        host_s = [0.0]
 
         def run():
+            t_h = time.perf_counter()
             for _ in range(clips_per_step):
                 serial_step(counter[0] % distinct)
                 counter[0] += 1
+            host_s[0] += time.perf_counter() - t_h
         mode = "one clip at a time on one stream"
     ms, clocks = ctx.timed(run, steps, warmup)
     ms_per_step = ms / steps
+    # host time spent enqueueing one clip (all steps incl. warm-up; the enqueue runs ahead of the GPU, so it only matters
+    # when it approaches the device time per clip)
+    host_enqueue_ms = host_s[0] / ((steps + warmup) * clips_per_step) * 1e3
     frames_per_step = total * clips_per_step
     value = frames_per_step * steps / (ms / 1e3)
 
@@ -463,7 +472,7 @@ def measure_v1(ctx, workload, steps, warmup, with_e2e, with_cpu, with_parity):
     roof = roofline_dict(ctx, "score_umma_kernel<2> (elvis_score_sc_tc, tcgen05)", ab["score"] * T, sc_ms, T, "score_umma_kernel")
     per_clip_ms = ms_per_step / clips_per_step
     roof["whole_step"] = {"achieved": ab["total"] * T / per_clip_ms / 1e6, "frac": ab["total"] * T / per_clip_ms / 1e6 / ctx.peak,
-                          "ms_per_clip": per_clip_ms, "note": "all three stages as timed (" + mode + "), per rank"}
+                          "ms_per_clip": per_clip_ms, "host_enqueue_ms_per_clip": host_enqueue_ms, "note": "all three stages as timed (" + mode + "), per rank"}
     roof["serial_step"] = {"ms": serial_ms, "achieved": ab["total"] * T / serial_ms / 1e6,
                            "frac": ab["total"] * T / serial_ms / 1e6 / ctx.peak, "note": "one clip at a time, one stream"}
     roof["stages"] = {"score_pipeline": {"ms": stage_ms[0], "gbs": ab["score"] * T / stage_ms[0] / 1e6},
@@ -638,7 +647,7 @@ def measure_v2(ctx, workload, steps, warmup, with_e2e, with_cpu, with_parity):
     if kind == "dampen":
         strength = scores[0].float()
         fn, name, key = (lambda: ops.dct_dampen(clips[0].y, strength, BLOCK, out=y_out)), \
-            "dampen_hmma_kernel<16> (elvis_dct_dampen, luma launch; mma.sync f16)", "dampen"
+            "dampen_packed_kernel (elvis_dct_dampen, luma launch; packed fp32 AAN butterflies)", "dampen_packed"
     elif kind == "downsample":
         lv = ops.levels_from_scores(scores[0], ops.LEVELS_ROUND, 4)
         fn, name, key = (lambda: v2.downsample_pow2(clips[0], lv, 3, outs[0])), \
