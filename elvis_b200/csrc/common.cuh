@@ -70,6 +70,23 @@ struct PerDeviceOnce {
 template <typename V> __device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
 template <typename V> __device__ __forceinline__ void st_stream(V* p, V v) { __stcs(p, v); }
 
+// Streaming loads for GATHERS of pieces smaller than an L2 line (the kept 16-byte block rows of shrink): with the
+// default policy B200's L2 fills the whole 128-byte line around any miss -- reading 16 of every 128 bytes moves all
+// 128 from DRAM; the `.L2::64B` prefetch-size hint halves the fill to 64 bytes (tools/micro/gather_granularity.cu under
+// ncu: 1.07 GB instead of 2.15 GB of DRAM reads for a 2 GiB span; cudaLimitMaxL2FetchGranularity alone changes
+// nothing; PTX has no smaller hint).  Dense reads keep the default, which is what they want.
+template <typename V> __device__ __forceinline__ V ld_gather(const V* p) { return __ldcs(p); }
+template <> __device__ __forceinline__ uint4 ld_gather<uint4>(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.cs.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+template <> __device__ __forceinline__ uint2 ld_gather<uint2>(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.global.cs.L2::64B.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+
 // float(2^23 + b) for byte K of w: byte_perm builds the bit pattern 0x4B0000bb directly, so a
 // u8 -> fp32 conversion is one PRMT (and the 2^23 bias cancels in differences).
 template <int K> __device__ __forceinline__ float byte_as_biased_float(uint32_t w) {

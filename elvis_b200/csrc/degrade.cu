@@ -738,39 +738,55 @@ __global__ void __launch_bounds__(256) downsample_pow2_yuv420_kernel(const YuvGe
     const uint8_t* cs = g.src[pl] + (int64_t)t * g.src_frame[pl] + ((int64_t)by * 8 + cr) * g.src_row[pl] + 4 * ch;
     uint8_t* cd = g.dst[pl] + (int64_t)t * g.dst_frame[pl] + ((int64_t)by * 8 + cr) * g.dst_row[pl] + 4 * ch;
     const int32_t* lv = levels + (int64_t)blockIdx.x * g.Bx;
-    // Pixels and level of a block reach the lane through a private 4-deep cp.async ring in shared memory, three blocks
-    // ahead of the one being computed (register prefetch does not survive ptxas: it sinks the loads to their first use,
-    // which left the kernel waiting on global memory -- ncu long-scoreboard stalls, profiles/r2f).  Every lane reads back
-    // only the 16 bytes it copied itself, so cp.async.wait_group is the only synchronisation.
-    constexpr int kStages = 4;
-    __shared__ __align__(16) uint4 s_ring[kWarps][kStages][32];
-    auto issue = [&](int stage, int bx) {
-        if (bx < g.Bx) {
-            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_ring[w][stage][lane]);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(ys + bx * 16) : "memory");
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 8), "l"(cs + bx * 8) : "memory");
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 12), "l"(lv + bx) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");      // always: keeps the group count uniform
-    };
-    int bx = w;
-    if (bx >= g.Bx) return;
+    // two blocks per iteration, the next pair's loads requested before the arithmetic.  (A 4-deep cp.async ring in shared
+    // memory -- 8 + 4 + 4 byte copies per lane -- measured SLOWER: 0.456 vs 0.315 ms per 30 4K frames.)
+    constexpr int kUnroll = 2;
+    uint2 y[kUnroll];
+    uint32_t c[kUnroll];
+    int L[kUnroll];
+    auto fetch = [&](int bx0, uint2 (&yy)[kUnroll], uint32_t (&cc)[kUnroll], int (&ll)[kUnroll]) {
 #pragma unroll
-    for (int sgi = 0; sgi < kStages - 1; ++sgi) issue(sgi, bx + sgi * kWarps);
-    int stage = 0;
-    for (; bx < g.Bx; bx += kWarps) {
-        issue((stage + kStages - 1) % kStages, bx + (kStages - 1) * kWarps);
-        asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
-        const uint4 item = s_ring[w][stage][lane];
-        stage = (stage + 1) % kStages;
-        const int L = (int)item.w < 0 ? 0 : ((int)item.w > max_level ? max_level : (int)item.w);
-        uint32_t p0 = item.x, p1 = item.y, c0 = item.z, c1 = 0u;
-        if (L > 0) {
-            down_up_pow2_level<16>(p0, p1, L > 4 ? 4 : L, lane, 0);
-            down_up_pow2_level<8>(c0, c1, L > 3 ? 3 : L, gl, lane & 16);
+        for (int i = 0; i < kUnroll; ++i) {
+            const int bx = bx0 + i * kWarps;
+            if (bx < g.Bx) {
+                yy[i] = __ldcs(reinterpret_cast<const uint2*>(ys + bx * 16));
+                cc[i] = __ldcs(reinterpret_cast<const uint32_t*>(cs + bx * 8));
+                ll[i] = __ldg(lv + bx);
+            }
         }
-        __stcs(reinterpret_cast<uint2*>(yd + bx * 16), make_uint2(p0, p1));
-        __stcs(reinterpret_cast<uint32_t*>(cd + bx * 8), c0);
+    };
+    int bx0 = w;
+    if (bx0 >= g.Bx) return;
+    fetch(bx0, y, c, L);
+    for (;;) {
+        const int nx = bx0 + kUnroll * kWarps;
+        const bool more = nx < g.Bx;
+        uint2 y2[kUnroll];
+        uint32_t c2[kUnroll];
+        int L2[kUnroll];
+        if (more) fetch(nx, y2, c2, L2);
+#pragma unroll
+        for (int i = 0; i < kUnroll; ++i) {
+            const int bx = bx0 + i * kWarps;
+            if (bx < g.Bx) {                      // warp-uniform
+                const int lvl = L[i] < 0 ? 0 : (L[i] > max_level ? max_level : L[i]);
+                uint32_t p0 = y[i].x, p1 = y[i].y, c0 = c[i], c1 = 0u;
+                if (lvl > 0) {
+                    down_up_pow2_level<16>(p0, p1, lvl > 4 ? 4 : lvl, lane, 0);
+                    down_up_pow2_level<8>(c0, c1, lvl > 3 ? 3 : lvl, gl, lane & 16);
+                }
+                __stcs(reinterpret_cast<uint2*>(yd + bx * 16), make_uint2(p0, p1));
+                __stcs(reinterpret_cast<uint32_t*>(cd + bx * 8), c0);
+            }
+        }
+        if (!more) break;
+#pragma unroll
+        for (int i = 0; i < kUnroll; ++i) {
+            y[i] = y2[i];
+            c[i] = c2[i];
+            L[i] = L2[i];
+        }
+        bx0 = nx;
     }
 }
 

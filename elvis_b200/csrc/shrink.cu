@@ -71,7 +71,7 @@ __device__ __forceinline__ void build_map(const uint8_t* __restrict__ mrow, int 
 
 // Gather one block row: destination unit c of every pixel row <- source unit map[c / upb]*upb + c % upb
 // (zeros when the map says -1).  Four rows in flight per thread: all loads issued before the stores.
-template <typename V>
+template <typename V, bool SPARSE = false>      // SPARSE: the source units are a scattered subset (shrink) -> 64-byte L2 fills
 __device__ __forceinline__ void copy_block_row(const uint8_t* __restrict__ src, int64_t src_row, uint8_t* __restrict__ dst,
                                                int64_t dst_row, const int16_t* s_map, int cols, int upb, int bh, int tx,
                                                int ty, int tx_dim, int ty_dim) {
@@ -88,10 +88,17 @@ __device__ __forceinline__ void copy_block_row(const uint8_t* __restrict__ src, 
         for (; r + 3 * ty_dim < bh; r += 4 * ty_dim) {
             V v0 = zero_v<V>(), v1 = zero_v<V>(), v2 = zero_v<V>(), v3 = zero_v<V>();
             if (sj >= 0) {
-                v0 = ld_stream(sp + (int64_t)r * srow);
-                v1 = ld_stream(sp + (int64_t)(r + ty_dim) * srow);
-                v2 = ld_stream(sp + (int64_t)(r + 2 * ty_dim) * srow);
-                v3 = ld_stream(sp + (int64_t)(r + 3 * ty_dim) * srow);
+                if (SPARSE) {
+                    v0 = ld_gather(sp + (int64_t)r * srow);
+                    v1 = ld_gather(sp + (int64_t)(r + ty_dim) * srow);
+                    v2 = ld_gather(sp + (int64_t)(r + 2 * ty_dim) * srow);
+                    v3 = ld_gather(sp + (int64_t)(r + 3 * ty_dim) * srow);
+                } else {
+                    v0 = ld_stream(sp + (int64_t)r * srow);
+                    v1 = ld_stream(sp + (int64_t)(r + ty_dim) * srow);
+                    v2 = ld_stream(sp + (int64_t)(r + 2 * ty_dim) * srow);
+                    v3 = ld_stream(sp + (int64_t)(r + 3 * ty_dim) * srow);
+                }
             }
             st_stream(dp + (int64_t)r * drow, v0);
             st_stream(dp + (int64_t)(r + ty_dim) * drow, v1);
@@ -100,7 +107,7 @@ __device__ __forceinline__ void copy_block_row(const uint8_t* __restrict__ src, 
         }
         for (; r < bh; r += ty_dim) {
             V v = zero_v<V>();
-            if (sj >= 0) v = ld_stream(sp + (int64_t)r * srow);
+            if (sj >= 0) v = SPARSE ? ld_gather(sp + (int64_t)r * srow) : ld_stream(sp + (int64_t)r * srow);
             st_stream(dp + (int64_t)r * drow, v);
         }
     }
@@ -121,7 +128,7 @@ __global__ void __launch_bounds__(kThreads) move_blocks_kernel(const MoveParams 
         const int by = unit - t * p.By;
         build_map<STRETCH>(p.mask + ((int64_t)t * p.By + by) * p.Bx, p.Bx, p.small_bx, s_map);
         if (ty < p.ty_dim)
-            copy_block_row<V>(p.src + (int64_t)t * p.src_frame + (int64_t)by * p.bh * p.src_row, p.src_row,
+            copy_block_row<V, !STRETCH>(p.src + (int64_t)t * p.src_frame + (int64_t)by * p.bh * p.src_row, p.src_row,
                               p.dst + (int64_t)t * p.dst_frame + (int64_t)by * p.bh * p.dst_row, p.dst_row,
                               s_map, cols, p.upb, p.bh, tx, ty, p.tx_dim, p.ty_dim);
         if (unit + (int)gridDim.x < p.n_units) __syncthreads();   // the column map is rebuilt for the next unit
@@ -204,12 +211,12 @@ __global__ void __launch_bounds__(kThreads) move_yuv420_kernel(const MoveYuvPara
         const int by = unit - t * p.By;
         build_map<STRETCH>(p.mask + ((int64_t)t * p.By + by) * p.Bx, p.Bx, p.small_bx, s_map);
         if (ty < p.ty_dim) {
-            copy_block_row<uint4>(p.src[0] + (int64_t)t * p.src_frame[0] + (int64_t)by * p.bs * p.src_row[0], p.src_row[0],
+            copy_block_row<uint4, !STRETCH>(p.src[0] + (int64_t)t * p.src_frame[0] + (int64_t)by * p.bs * p.src_row[0], p.src_row[0],
                                   p.dst[0] + (int64_t)t * p.dst_frame[0] + (int64_t)by * p.bs * p.dst_row[0], p.dst_row[0],
                                   s_map, cols, upb, p.bs, tx, ty, p.tx_dim, p.ty_dim);
 #pragma unroll
             for (int c = 1; c < 3; ++c)
-                copy_block_row<uint2>(p.src[c] + (int64_t)t * p.src_frame[c] + (int64_t)by * (p.bs / 2) * p.src_row[c], p.src_row[c],
+                copy_block_row<uint2, !STRETCH>(p.src[c] + (int64_t)t * p.src_frame[c] + (int64_t)by * (p.bs / 2) * p.src_row[c], p.src_row[c],
                                       p.dst[c] + (int64_t)t * p.dst_frame[c] + (int64_t)by * (p.bs / 2) * p.dst_row[c], p.dst_row[c],
                                       s_map, cols, upb, p.bs / 2, tx, ty, p.tx_dim, p.ty_dim);
         }

@@ -71,5 +71,6 @@ int main() {
     printf("{\"cudaLimitMaxL2FetchGranularity\": {\"before\": %zu, \"set_32\": \"%s\", \"after\": %zu}}\n", g, cudaGetErrorString(e), g2);
     run<0>("lim32_cs", buf, bytes, sink);
     run<1>("lim32_plain", buf, bytes, sink);
+    run<3>("lim32_cs_64", buf, bytes, sink);
     return 0;
 }
