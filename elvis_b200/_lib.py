@@ -112,8 +112,11 @@ def call(name: str, *args) -> None:
     """Invoke an entry point and raise on a non-zero return code (ValueError for the
     reference's own dimension check, elvis.py:1376)."""
     rc = getattr(lib, name)(*args)
-    if rc == OK:
-        return
+    if rc != OK:
+        raise_for(name, rc)
+
+
+def raise_for(name: str, rc: int) -> None:
     detail = lib.elvis_error_string(rc).decode()
     if rc == ERR_CUDA:
         detail += f" (cudaError {lib.elvis_last_cuda_error()})"

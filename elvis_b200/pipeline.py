@@ -7,15 +7,44 @@ removal mask / level map computed from luma is applied to the co-located chroma 
 half the block size (SURVEY.md appendix "Layout")."""
 from __future__ import annotations
 
+import ctypes as C
 import os
 
 from typing import Optional, Tuple
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from .elvis import blocks_to_remove
 from .yuv import Yuv420
+
+
+class _Prepared:
+    """One C-ABI call with its ctypes arguments built once.  The wrappers of ops.py validate and convert their
+    arguments on every call (20-40 us of Python each); a clip that flows through the stream pipeline makes ten of
+    them, which is most of the host time per clip (0.6-0.7 ms against ~1 ms of device time at 4K x 120).  The
+    pipeline therefore validates a (clip, slot) pair once through the ops wrappers' own checks and afterwards replays
+    the raw calls; the objects in `keep` pin every buffer and struct the raw pointers refer to."""
+    __slots__ = ("name", "fn", "args", "keep")
+
+    def __init__(self, name: str, args: tuple, keep: tuple = ()):
+        self.name, self.fn, self.args, self.keep = name, getattr(_lib.lib, name), args, keep
+
+    def __call__(self) -> None:
+        rc = self.fn(*self.args)
+        if rc:
+            _lib.raise_for(self.name, rc)
+
+
+def _fused_move_ok(clip: Yuv420, bs: int) -> bool:
+    """Geometry the one-launch Y+U+V move kernels accept (elvis_shrink_yuv420 / elvis_stretch_yuv420)."""
+    if bs % 16:
+        return False
+    for i, p in enumerate(clip.planes):
+        al = 16 if i == 0 else 8
+        if p.dim() != 3 or p.stride(2) != 1 or p.data_ptr() % al or p.stride(0) % al or p.stride(1) % al:
+            return False
+    return True
 
 
 def move_planes(src: Yuv420, dst: Yuv420, mask: torch.Tensor, bs: int, small_bx: int, stretch_: bool,
@@ -93,8 +122,15 @@ class ElvisV1Pipelined:
 
     def __init__(self, n_frames: int, height: int, width: int, block_size: int = 16, shrink_amount: float = 0.5,
                  alpha: float = 0.5, beta: float = 0.5, device="cuda", depth: int = 2, score_fn=None,
-                 move_ctas_per_sm: int = 3, comm_fn=None, split_stretch: bool = False, stretch_ctas_per_sm: int | None = None):
+                 move_ctas_per_sm: int = 3, comm_fn=None, split_stretch: bool = False, stretch_ctas_per_sm: int | None = None,
+                 prepared: bool = True):
+        """prepared: replay pre-built C-ABI calls for (clip, slot) pairs seen before instead of going through the
+        ops wrappers every time (same kernels, same arguments, a fraction of the host time); only without score_fn."""
         self.pipe = ElvisV1(block_size, shrink_amount, alpha, beta)
+        self.prepared = prepared
+        self._programs: dict = {}
+        d = torch.device(device)
+        self._dev_index = d.index if d.index is not None else torch.cuda.current_device()
         self.dev = torch.device(device)
         # footprint of the shrink/stretch kernels per SM while they share it with the scoring
         # kernel: 3 x 256 threads keeps ~85 % of their stand-alone bandwidth and leaves the two
@@ -130,15 +166,93 @@ class ElvisV1Pipelined:
                 "mask": torch.empty((n_frames, by, bx), dtype=torch.uint8, device=self.dev),
                 "shrunk": Yuv420.empty(n_frames, height, sw, self.dev),
                 "full": Yuv420.empty(n_frames, height, width, self.dev),
-                "scored": torch.cuda.Event(), "shrunk_ev": torch.cuda.Event(), "done": torch.cuda.Event(), "used": False,
+                "scored": torch.cuda.Event(), "shrunk_ev": torch.cuda.Event(), "done": torch.cuda.Event(), "ready": torch.cuda.Event(),
+                "used": False,
             })
         self._next = 0
+
+    # ------------------------------------------------------------------ prepared calls
+    def _program(self, clip: Yuv420, index: int):
+        """The six C-ABI calls of one clip through slot `index`, arguments converted once (None when the clip's
+        geometry needs the generic per-plane path)."""
+        key = (index,) + tuple((p.data_ptr(), p.stride(0), p.stride(1)) for p in clip.planes) + tuple(clip.y.shape)
+        prog = self._programs.get(key)
+        if prog is not None or key in self._programs:
+            return prog
+        slot, p = self.slots[index], self.pipe
+        T, H, W = clip.y.shape
+        by, bx = H // p.bs, W // p.bs
+        small_bx = bx - self.k
+        ok = ((T, H, W) == (self.T, self.H, self.W) and small_bx > 0 and _fused_move_ok(clip, p.bs)
+              and _fused_move_ok(slot["shrunk"], p.bs) and _fused_move_ok(slot["full"], p.bs) and clip.y.is_cuda)
+        if not ok:
+            if len(self._programs) > 256:
+                self._programs.clear()
+            self._programs[key] = None
+            return None
+        vp, i32 = C.c_void_p, C.c_int32
+        st = {"score": vp(self.s_score.cuda_stream), "move": vp(self.s_move.cuda_stream),
+              "stretch": vp((self.s_stretch or self.s_move).cuda_stream)}
+        y_plane = ops.plane_of(clip.y, "y")
+        src = (_lib.Plane * 3)(*[ops.plane_of(t, "clip") for t in clip.planes])
+        shr = (_lib.Plane * 3)(*[ops.plane_of(t, "shrunk") for t in slot["shrunk"].planes])
+        ful = (_lib.Plane * 3)(*[ops.plane_of(t, "full") for t in slot["full"].planes])
+        ptr = lambda t: vp(t.data_ptr())       # noqa: E731
+        smooth = int(p.beta < 1 and T >= 2)
+        prog = (
+            _Prepared("elvis_score_sc_tc", (C.byref(y_plane), i32(T), vp(0), i32(p.bs), i32(p.dct_size), ptr(slot["sc"]), ptr(slot["tc"]),
+                                            ptr(slot["norm"]), i32(0), i32(T), st["score"]), (y_plane, clip.y)),
+            _Prepared("elvis_combine_removability", (ptr(slot["sc"]), ptr(slot["tc"]), i32(_lib.F32), ptr(slot["norm"]), i32(T), i32(by), i32(bx),
+                                                     i32(0), i32(T), i32(1), i32(1), vp(0), C.c_double(p.alpha), C.c_double(p.beta), i32(smooth),
+                                                     ptr(slot["scores"]), ptr(slot["smm"]), st["score"])),
+            _Prepared("elvis_normalize", (ptr(slot["scores"]), C.c_int64(slot["scores"].numel()), ptr(slot["smm"]), st["score"])),
+            _Prepared("elvis_select_rows", (ptr(slot["scores"]), i32(T), i32(by), i32(bx), vp(0), i32(self.k), i32(ops.REMOVE_HIGH),
+                                            ptr(slot["mask"]), st["move"])),
+            _Prepared("elvis_shrink_yuv420", (src, shr, i32(T), i32(p.bs), i32(by), i32(bx), i32(small_bx), ptr(slot["mask"]),
+                                              i32(self.move_ctas), st["move"]), (src, shr, clip)),
+            _Prepared("elvis_stretch_yuv420", (shr, ful, i32(T), i32(p.bs), i32(by), i32(bx), i32(small_bx), ptr(slot["mask"]),
+                                               i32(self.stretch_ctas if self.s_stretch is not None else self.move_ctas), st["stretch"]), (shr, ful)),
+        )
+        if len(self._programs) > 256:
+            self._programs.clear()
+        self._programs[key] = prog
+        return prog
+
+    def _submit_prepared(self, slot: dict, prog) -> dict:
+        score, combine, normalize, select, shrink, stretch = prog
+        ready = slot["ready"]
+        ready.record()                                        # inputs produced on the caller's stream
+        self.s_score.wait_event(ready)
+        if slot["used"]:
+            self.s_score.wait_event(slot["done"])             # the slot's previous clip has left the move stage
+        score()
+        combine()
+        normalize()
+        slot["scored"].record(self.s_score)
+        self.s_move.wait_event(slot["scored"])
+        select()
+        shrink()
+        if self.s_stretch is None:
+            stretch()
+            slot["done"].record(self.s_move)
+        else:
+            slot["shrunk_ev"].record(self.s_move)
+            self.s_stretch.wait_event(slot["shrunk_ev"])
+            stretch()
+            slot["done"].record(self.s_stretch)
+        slot["used"] = True
+        return slot
 
     def submit(self, clip: Yuv420) -> dict:
         """Enqueue one clip; returns its slot (dict with `scores`, `mask`, `shrunk`, `full`,
         and the `done` event).  The clip must stay unmodified until `done` fires."""
-        slot = self.slots[self._next]
+        index = self._next
+        slot = self.slots[index]
         self._next = (self._next + 1) % len(self.slots)
+        if self.prepared and self.score_fn is None and self.comm_fn is None and torch.cuda.current_device() == self._dev_index:
+            prog = self._program(clip, index)
+            if prog is not None:
+                return self._submit_prepared(slot, prog)
         ready = torch.cuda.Event()
         ready.record()                                   # inputs produced on the caller's stream
         comm_done = None

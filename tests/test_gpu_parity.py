@@ -585,8 +585,9 @@ def test_score_tightness(dev, monkeypatch):
         assert e_sc < 2e-5 and e_tc < 2e-5
 
 
+@pytest.mark.parametrize("prepared", [True, False])
 @pytest.mark.parametrize("depth,split", [(2, False), (3, True)])
-def test_pipelined_equals_serial(dev, depth, split):
+def test_pipelined_equals_serial(dev, depth, split, prepared):
     """Clips in flight on two (score | move) or three (score | shrink | stretch) streams must give
     exactly the serial results."""
     import torch
@@ -598,7 +599,13 @@ def test_pipelined_equals_serial(dev, depth, split):
         clips.append(Yuv420(to_dev(y, dev), to_dev(u, dev), to_dev(v, dev)))
     serial = ElvisV1(bs, 0.5, 0.5, 0.5)
     ref = [serial.run(c) for c in clips]
-    pp = ElvisV1Pipelined(T, H, W, bs, 0.5, 0.5, 0.5, dev, depth=depth, split_stretch=split)
+    pp = ElvisV1Pipelined(T, H, W, bs, 0.5, 0.5, 0.5, dev, depth=depth, split_stretch=split, prepared=prepared)
+    for rep in range(2):            # the second round replays the prepared calls of (clip, slot) pairs seen before
+        for i, c in enumerate(clips * 2):
+            slot = pp.submit(c)
+            slot["done"].synchronize()
+            assert torch.equal(slot["mask"], ref[i % 3][1]) and torch.equal(slot["full"].y, ref[i % 3][3].y)
+    assert (len(pp._programs) > 0) == prepared
     for i, c in enumerate(clips):
         slot = pp.submit(c)
         slot["done"].synchronize()      # read the slot before it is reused
