@@ -434,35 +434,39 @@ def measure_v1(ctx, workload, steps, warmup, with_e2e, with_cpu, with_parity):
         depth = (3 if split else 2) if args.depth is None else args.depth
         pp = ElvisV1Pipelined(T, H, W, BLOCK, SHRINK, ALPHA, BETA, dev, depth=depth, score_fn=score_fn,
                               move_ctas_per_sm=args.move_ctas, comm_fn=comm_fn, split_stretch=split,
-                              stretch_ctas_per_sm=args.stretch_ctas)
+                              stretch_ctas_per_sm=args.stretch_ctas, prepared=not args.no_prepared)
         counter = [0]
-        host_s = [0.0]
 
         def run():
-            t_h = time.perf_counter()
             for _ in range(clips_per_step):
                 pp.submit(clips[counter[0] % distinct])
                 counter[0] += 1
             pp.join()
-            host_s[0] += time.perf_counter() - t_h
         mode = f"{depth} clips in flight on {3 if split else 2} CUDA streams" + (" (+1 for the halo exchange)" if world > 1 else "") + \
                " (elvis_b200.pipeline.ElvisV1Pipelined); every clip takes the full serial path"
     else:
         counter = [0]
-        host_s = [0.0]
 
         def run():
-            t_h = time.perf_counter()
             for _ in range(clips_per_step):
                 serial_step(counter[0] % distinct)
                 counter[0] += 1
-            host_s[0] += time.perf_counter() - t_h
         mode = "one clip at a time on one stream"
     ms, clocks = ctx.timed(run, steps, warmup)
     ms_per_step = ms / steps
-    # host time spent enqueueing one clip (all steps incl. warm-up; the enqueue runs ahead of the GPU, so it only matters
-    # when it approaches the device time per clip)
-    host_enqueue_ms = host_s[0] / ((steps + warmup) * clips_per_step) * 1e3
+    # host time spent enqueueing one clip, measured on an EMPTY launch queue (inside the timed region the host runs ahead
+    # until the queue is full and then blocks, so its wall time there says nothing about its own cost): it only matters
+    # when it approaches the device time per clip
+    host_enqueue_ms = None
+    if pipelined:
+        ctx.barrier()
+        n_probe = 16
+        t_h = time.perf_counter()
+        for i in range(n_probe):
+            pp.submit(clips[i % distinct])
+        host_enqueue_ms = (time.perf_counter() - t_h) / n_probe * 1e3
+        pp.join()
+        ctx.barrier()
     frames_per_step = total * clips_per_step
     value = frames_per_step * steps / (ms / 1e3)
 
@@ -807,6 +811,7 @@ def main():
     ap.add_argument("--no-split-stretch", dest="split_stretch", action="store_false",
                     help="two pipeline stages (score | shrink+stretch); default when sharded")
     ap.add_argument("--stretch-ctas", type=int, default=None)
+    ap.add_argument("--no-prepared", action="store_true", help="pipeline: go through the ops wrappers for every clip instead of replaying prepared calls")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
