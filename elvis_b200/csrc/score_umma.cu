@@ -65,7 +65,8 @@ constexpr uint32_t kGroupBar = 40;       // per group: a_full[2] +0, d_full[3] +
 constexpr uint32_t kUnitBar = 16 * kUmmaRing;   // per unit: ring_full[] +0, ring_empty[] +8 kUmmaRing
 constexpr uint32_t kOffUnitBar = kOffBar + kGroups * kGroupBar;
 constexpr uint32_t kOffXchg = kOffUnitBar + kUnitsPerCta * kUnitBar;   // per unit: 2 x 32 float2 partial sums
-constexpr uint32_t kOffTmem = kOffXchg + kUnitsPerCta * 512;
+constexpr uint32_t kOffXbar = kOffXchg + kUnitsPerCta * 512;         // per unit: x_full[2] mbarriers of the exchange slots
+constexpr uint32_t kOffTmem = kOffXbar + kUnitsPerCta * 16;
 constexpr uint32_t kUmmaSmem = kOffTmem + 16 + 1024;   // + slack to align the base to 1024 B (128 B swizzle atom)
 // instruction descriptor: D fp32, A/B fp16 K-major, N = 64, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
@@ -139,7 +140,10 @@ __device__ __forceinline__ uint64_t b_descriptor(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int R>
+// XBAR: how the upper-half warp of a unit hands its partial sums to the lower-half warp.  false: a 64-thread named
+// barrier per frame (round 1; both warps wait for each other).  true: a one-way mbarrier per exchange slot -- the
+// upper half arrives and moves on, only the lower half ever waits.
+template <int R, bool XBAR>
 __global__ void __launch_bounds__(kUmmaThreads, kCtasPerSm)
 score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_constant__ CUtensorMap tm_halo, const ScoreParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -177,6 +181,10 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
                     mbar_init(base + kOffUnitBar + kUnitBar * u + 8 * s, 1);                   // ring_full: expect_tx
                     mbar_init(base + kOffUnitBar + kUnitBar * u + 8 * (kUmmaRing + s), 64);    // ring_empty: both reader warps
                 }
+            for (int u = 0; u < kUnitsPerCta; ++u) {
+                mbar_init(base + kOffXbar + 16 * u, 32);          // x_full[0], x_full[1]: the 32 lanes of the upper-half warp
+                mbar_init(base + kOffXbar + 16 * u + 8, 32);
+            }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_clip) : "memory");
         }
@@ -320,7 +328,8 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
         // Each thread covers 32 of the tile's 64 coefficients (rows 4 role .. 4 role + 3): SC part
         // = sum w |C_t|, TC part = sum w |C_t - C_{t-1}| with C_{t-1} = the D buffer written one
         // frame earlier.  2 x 4 independent FMA chains, fixed order => deterministic.
-        auto consume = [&](const int t, const int dbuf, const uint32_t d_parity, const int xslot, auto role_c) {
+        const uint32_t bar_x = base + kOffXbar + 16 * unit_local;
+        auto consume = [&](const int t, const int dbuf, const uint32_t d_parity, const int xslot, const uint32_t x_parity, auto role_c) {
             constexpr int ROLE = decltype(role_c)::value;
             mbar_wait(bar_d + 8 * dbuf, d_parity);
             tc_fence_after();
@@ -355,8 +364,16 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
             }
             // the upper half hands its sums to the lower half through one of two slots: the write two
             // frames later comes after the next barrier, which the reader reaches after this read
+            // The slot written for frame t is reused for frame t + 2.  By then the lower half has read it: its read of
+            // frame t precedes (program order) its own A(t + 2) store, which the MMA of t + 2 -- and with it the upper
+            // half's D(t + 2) wait -- depends on.
             if (ROLE == 1) xchg[32 * xslot] = make_float2(s, d);
-            pair_barrier(unit_local);
+            if (XBAR) {
+                if (ROLE == 1) mbar_arrive(bar_x + 8 * xslot);
+                else mbar_wait(bar_x + 8 * xslot, x_parity);
+            } else {
+                pair_barrier(unit_local);
+            }
             if (ROLE == 0) {
                 const float2 o = xchg[32 * xslot];
                 s += o.x;
@@ -393,7 +410,8 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
                     const int it = it0 + i;
                     if (it >= n_iter) break;
                     if (it + 1 < n_iter) produce((i + 1) % 6, (i + 1) & 1, i == 5 ? round_parity ^ 1u : round_parity);
-                    consume(t_start + it, i % 3, (uint32_t)(i / 3) & 1u, i & 1, role_c);
+                    // exchange slot i & 1 has been used (it >> 1) times before: its phase parity is round ^ (i >> 1)
+                    consume(t_start + it, i % 3, (uint32_t)(i / 3) & 1u, i & 1, round_parity ^ ((uint32_t)(i >> 1) & 1u), role_c);
                 }
                 round_parity ^= 1u;
             }
@@ -453,17 +471,17 @@ bool make_unit_map(CUtensorMap* m, const uint8_t* ptr, int W, int H, int T, int6
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int R>
+template <int R, bool XBAR>
 int launch_umma(const ScoreParams& p, const CUtensorMap& tm_clip, const CUtensorMap& tm_halo, cudaStream_t st) {
     // no carve-out preference: a kernel that forces its own L1 / shared split cannot overlap with the
     // shrink / stretch kernels of the other stream (measured: pipelined step 1.32 instead of 1.07 ms)
     static PerDeviceOnce configured;   // the attribute is per (kernel, device)
     const cudaError_t e = configured.run([] {
-        return cudaFuncSetAttribute(score_umma_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem);
+        return cudaFuncSetAttribute(score_umma_kernel<R, XBAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem);
     });
     if (e != cudaSuccess) return cuda_fail(e);
     const int ctas_per_chunk = (p.By * p.tiles_x + kUnitsPerCta - 1) / kUnitsPerCta;
-    score_umma_kernel<R><<<ctas_per_chunk * p.n_chunks, kUmmaThreads, kUmmaSmem, st>>>(tm_clip, tm_halo, p);
+    score_umma_kernel<R, XBAR><<<ctas_per_chunk * p.n_chunks, kUmmaThreads, kUmmaSmem, st>>>(tm_clip, tm_halo, p);
     ELVIS_CHECK_LAUNCH();
     return ELVIS_OK;
 }
@@ -486,10 +504,12 @@ int launch_score_umma(ScoreParams p, int block_size, int plane_h, int plane_w, c
     memset(&tm_halo, 0, sizeof(tm_halo));
     if (!make_unit_map(&tm_clip, p.y, plane_w, plane_h, p.T, p.row_stride, p.frame_stride, R)) return ELVIS_ERR_UNSUPPORTED;
     if (!make_unit_map(&tm_halo, p.halo ? p.halo : p.y, plane_w, plane_h, 1, p.row_stride, p.frame_stride, R)) return ELVIS_ERR_UNSUPPORTED;
+    const char* xe = getenv("ELVIS_UMMA_XBAR");        // 1 (default): one-way mbarrier exchange; 0: the round-1 named barrier
+    const bool xbar = !(xe && xe[0] == '0');
     switch (R) {
-        case 1: return launch_umma<1>(p, tm_clip, tm_halo, st);
-        case 2: return launch_umma<2>(p, tm_clip, tm_halo, st);
-        default: return launch_umma<4>(p, tm_clip, tm_halo, st);
+        case 1: return xbar ? launch_umma<1, true>(p, tm_clip, tm_halo, st) : launch_umma<1, false>(p, tm_clip, tm_halo, st);
+        case 2: return xbar ? launch_umma<2, true>(p, tm_clip, tm_halo, st) : launch_umma<2, false>(p, tm_clip, tm_halo, st);
+        default: return xbar ? launch_umma<4, true>(p, tm_clip, tm_halo, st) : launch_umma<4, false>(p, tm_clip, tm_halo, st);
     }
 }
 
