@@ -725,68 +725,93 @@ struct YuvGeom {
     int32_t T, By, Bx;
 };
 
+// Shared-memory tile of eight horizontally adjacent blocks: 16 luma rows x 128 bytes, 8 + 8 chroma rows x 64 bytes and
+// the eight levels.  Row pitches are padded (144 / 72 bytes) so that the warp-per-block reads below -- 8 bytes of luma
+// per lane, rows 16 bytes apart in the tile; 4 bytes of chroma -- are free of bank conflicts, V sits 16 banks after U.
+struct __align__(16) DownTile {
+    uint8_t y[16][144];
+    uint8_t u[8][72];
+    uint8_t v[8][72];
+    int32_t lv[8];
+};
+
+// WHY the staging: a warp that reads its own block straight from global memory touches 16 different 128-byte lines
+// with every load or store instruction (16 rows x 16 bytes), and L1 looks its tags up one line at a time -- ncu showed
+// the register-prefetch version of this kernel (146 instructions per block, issue 41 %) waiting on exactly that
+// (37 % of all stall samples on the first use of a prefetched value; 11 sectors per request).  Here the CTA moves
+// whole tiles with coalesced 16-byte cp.async copies (one per thread, three tiles ahead) and coalesced 16-byte
+// stores (4 lines per warp instruction), and the warps talk to shared memory only.
 __global__ void __launch_bounds__(256) downsample_pow2_yuv420_kernel(const YuvGeom g, const int32_t* __restrict__ levels, int max_level) {
-    constexpr int kWarps = 8;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    // one CTA per (frame, block row): no index division in the loop, the eight warps walk the row 8 blocks apart
+    constexpr int kStages = 4;
+    __shared__ DownTile s_in[kStages];
+    __shared__ DownTile s_out[2];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int t = blockIdx.x / g.By, by = blockIdx.x - t * g.By;
-    // luma: lane = (row, 8-pixel half); chroma: lanes 0..15 U, 16..31 V, lane = (row, 4-pixel half) inside its group
-    const int yr = lane >> 1, yh = lane & 1;
-    const int pl = 1 + (lane >> 4), gl = lane & 15, cr = gl >> 1, ch = gl & 1;
-    const uint8_t* ys = g.src[0] + (int64_t)t * g.src_frame[0] + ((int64_t)by * 16 + yr) * g.src_row[0] + 8 * yh;
-    uint8_t* yd = g.dst[0] + (int64_t)t * g.dst_frame[0] + ((int64_t)by * 16 + yr) * g.dst_row[0] + 8 * yh;
-    const uint8_t* cs = g.src[pl] + (int64_t)t * g.src_frame[pl] + ((int64_t)by * 8 + cr) * g.src_row[pl] + 4 * ch;
-    uint8_t* cd = g.dst[pl] + (int64_t)t * g.dst_frame[pl] + ((int64_t)by * 8 + cr) * g.dst_row[pl] + 4 * ch;
+    const int n_groups = (g.Bx + 7) / 8;
     const int32_t* lv = levels + (int64_t)blockIdx.x * g.Bx;
-    // two blocks per iteration, the next pair's loads requested before the arithmetic.  (A 4-deep cp.async ring in shared
-    // memory -- 8 + 4 + 4 byte copies per lane -- measured SLOWER: 0.456 vs 0.315 ms per 30 4K frames.)
-    constexpr int kUnroll = 2;
-    uint2 y[kUnroll];
-    uint32_t c[kUnroll];
-    int L[kUnroll];
-    auto fetch = [&](int bx0, uint2 (&yy)[kUnroll], uint32_t (&cc)[kUnroll], int (&ll)[kUnroll]) {
-#pragma unroll
-        for (int i = 0; i < kUnroll; ++i) {
-            const int bx = bx0 + i * kWarps;
-            if (bx < g.Bx) {
-                yy[i] = __ldcs(reinterpret_cast<const uint2*>(ys + bx * 16));
-                cc[i] = __ldcs(reinterpret_cast<const uint32_t*>(cs + bx * 8));
-                ll[i] = __ldg(lv + bx);
-            }
-        }
+
+    // ---- mover role of this thread: one 16-byte luma piece (threads 0..127) or one 8-byte chroma piece (128..255) of a tile
+    const bool mv_luma = tid < 128;
+    const int mk = mv_luma ? tid : (tid - 128) & 63;
+    const int mrow = mk >> 3, mseg = mk & 7;                  // row inside the tile, block inside the group
+    const int mpl = mv_luma ? 0 : 1 + ((tid - 128) >> 6);     // plane
+    const int mbytes = mv_luma ? 16 : 8;
+    const int64_t mrow_px = mv_luma ? (int64_t)by * 16 + mrow : (int64_t)by * 8 + mrow;
+    const uint8_t* msrc = g.src[mpl] + (int64_t)t * g.src_frame[mpl] + mrow_px * g.src_row[mpl] + mseg * mbytes;
+    uint8_t* mdst = g.dst[mpl] + (int64_t)t * g.dst_frame[mpl] + mrow_px * g.dst_row[mpl] + mseg * mbytes;
+    auto tile_slot = [&](DownTile& tile) -> uint8_t* {
+        return mv_luma ? &tile.y[mrow][16 * mseg] : (mpl == 1 ? &tile.u[mrow][8 * mseg] : &tile.v[mrow][8 * mseg]);
     };
-    int bx0 = w;
-    if (bx0 >= g.Bx) return;
-    fetch(bx0, y, c, L);
-    for (;;) {
-        const int nx = bx0 + kUnroll * kWarps;
-        const bool more = nx < g.Bx;
-        uint2 y2[kUnroll];
-        uint32_t c2[kUnroll];
-        int L2[kUnroll];
-        if (more) fetch(nx, y2, c2, L2);
-#pragma unroll
-        for (int i = 0; i < kUnroll; ++i) {
-            const int bx = bx0 + i * kWarps;
-            if (bx < g.Bx) {                      // warp-uniform
-                const int lvl = L[i] < 0 ? 0 : (L[i] > max_level ? max_level : L[i]);
-                uint32_t p0 = y[i].x, p1 = y[i].y, c0 = c[i], c1 = 0u;
-                if (lvl > 0) {
-                    down_up_pow2_level<16>(p0, p1, lvl > 4 ? 4 : lvl, lane, 0);
-                    down_up_pow2_level<8>(c0, c1, lvl > 3 ? 3 : lvl, gl, lane & 16);
-                }
-                __stcs(reinterpret_cast<uint2*>(yd + bx * 16), make_uint2(p0, p1));
-                __stcs(reinterpret_cast<uint32_t*>(cd + bx * 8), c0);
+    auto issue = [&](int grp) {
+        if (grp < n_groups) {
+            DownTile& tile = s_in[grp % kStages];
+            const int bx = grp * 8 + mseg;
+            if (bx < g.Bx) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile_slot(tile));
+                if (mv_luma) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(msrc + (int64_t)grp * 128) : "memory");
+                else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(msrc + (int64_t)grp * 64) : "memory");
+            }
+            if (tid < 8 && grp * 8 + tid < g.Bx) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tile.lv[tid]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(lv + grp * 8 + tid) : "memory");
             }
         }
-        if (!more) break;
+        asm volatile("cp.async.commit_group;" ::: "memory");      // always: keeps the group count uniform
+    };
+
+    // ---- worker role: warp w owns block 8 grp + w; luma lane = (row, 8-pixel half), chroma lanes 0..15 U / 16..31 V
+    const int yr = lane >> 1, yh = lane & 1;
+    const int cpl = lane >> 4, gl = lane & 15, cr = gl >> 1, ch = gl & 1;
+
 #pragma unroll
-        for (int i = 0; i < kUnroll; ++i) {
-            y[i] = y2[i];
-            c[i] = c2[i];
-            L[i] = L2[i];
+    for (int sgi = 0; sgi < kStages - 1; ++sgi) issue(sgi);
+    for (int grp = 0; grp < n_groups; ++grp) {
+        issue(grp + kStages - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
+        __syncthreads();                                          // tile grp is complete for every warp
+        const DownTile& in = s_in[grp % kStages];
+        DownTile& out = s_out[grp & 1];
+        const int bx = grp * 8 + w;
+        if (bx < g.Bx) {                                          // warp-uniform
+            const uint2 y = *reinterpret_cast<const uint2*>(&in.y[yr][16 * w + 8 * yh]);
+            uint32_t c0 = *reinterpret_cast<const uint32_t*>(cpl ? &in.v[cr][8 * w + 4 * ch] : &in.u[cr][8 * w + 4 * ch]);
+            int L = in.lv[w];
+            L = L < 0 ? 0 : (L > max_level ? max_level : L);
+            uint32_t p0 = y.x, p1 = y.y, c1 = 0u;
+            if (L > 0) {
+                down_up_pow2_level<16>(p0, p1, L > 4 ? 4 : L, lane, 0);
+                down_up_pow2_level<8>(c0, c1, L > 3 ? 3 : L, gl, lane & 16);
+            }
+            *reinterpret_cast<uint2*>(&out.y[yr][16 * w + 8 * yh]) = make_uint2(p0, p1);
+            *reinterpret_cast<uint32_t*>(cpl ? &out.v[cr][8 * w + 4 * ch] : &out.u[cr][8 * w + 4 * ch]) = c0;
         }
-        bx0 = nx;
+        __syncthreads();                                          // the output tile is complete; s_in[grp % kStages] is free again
+        if (grp * 8 + mseg < g.Bx) {
+            const uint8_t* from = tile_slot(out);
+            if (mv_luma) __stcs(reinterpret_cast<uint4*>(mdst + (int64_t)grp * 128), *reinterpret_cast<const uint4*>(from));
+            else __stcs(reinterpret_cast<uint2*>(mdst + (int64_t)grp * 64), *reinterpret_cast<const uint2*>(from));
+        }
+        // s_out[grp & 1] is rewritten two iterations later, after two more barriers
     }
 }
 
@@ -1314,7 +1339,7 @@ extern "C" int elvis_degrade_downsample_pow2_yuv420(const elvis_plane* src_yuv, 
         const int pb = i == 0 ? 16 : 8;
         // whole blocks only (the per-plane entry point copies partial blocks through)
         if (s->height != by * pb || s->width != bx * pb || d->height != s->height || d->width != s->width) return ELVIS_ERR_UNSUPPORTED;
-        const int a = i == 0 ? 8 : 4;
+        const int a = i == 0 ? 16 : 8;          // the tile movers copy 16-byte luma and 8-byte chroma pieces
         if (!aligned_to(s->data, a) || !aligned_to(d->data, a) || s->frame_stride % a || d->frame_stride % a || s->row_stride % a ||
             d->row_stride % a)
             return ELVIS_ERR_UNSUPPORTED;

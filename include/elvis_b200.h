@@ -187,8 +187,8 @@ ELVIS_API int elvis_degrade_downsample(const elvis_plane* src, const elvis_plane
 /* a8 for planar YUV 4:2:0 clips, power-of-two levels, Y, U and V in ONE launch (src_yuv / dst_yuv: arrays
  * of three planes {Y, U, V}): level l of a 16 x 16 block reduces the luma block by 2^min(l, max_level, 4)
  * per axis and its two 8 x 8 chroma blocks by 2^min(l, max_level, 3) (cv2 INTER_AREA down, INTER_LINEAR
- * up, elvis.py:2158-2163).  Needs block_size == 16, planes made of whole blocks, 8-byte aligned luma and
- * 4-byte aligned chroma; returns ELVIS_ERR_UNSUPPORTED otherwise (use the per-plane entry point). */
+ * up, elvis.py:2158-2163).  Needs block_size == 16, planes made of whole blocks, 16-byte aligned luma and
+ * 8-byte aligned chroma; returns ELVIS_ERR_UNSUPPORTED otherwise (use the per-plane entry point). */
 ELVIS_API int elvis_degrade_downsample_pow2_yuv420(const elvis_plane* src_yuv, const elvis_plane* dst_yuv, int32_t n_frames,
                                          int32_t block_size, int32_t by, int32_t bx, const int32_t* levels,
                                          int32_t max_level, elvis_stream_t stream);
