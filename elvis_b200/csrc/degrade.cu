@@ -10,6 +10,7 @@
 #include "dct8.cuh"
 #include "dct8_packed.cuh"
 #include "down_pow2.cuh"
+#include <cstddef>
 #include <cstring>
 #include <cuda_fp16.h>
 
@@ -759,24 +760,29 @@ __global__ void __launch_bounds__(256) downsample_pow2_yuv420_kernel(const YuvGe
     const int64_t mrow_px = mv_luma ? (int64_t)by * 16 + mrow : (int64_t)by * 8 + mrow;
     const uint8_t* msrc = g.src[mpl] + (int64_t)t * g.src_frame[mpl] + mrow_px * g.src_row[mpl] + mseg * mbytes;
     uint8_t* mdst = g.dst[mpl] + (int64_t)t * g.dst_frame[mpl] + mrow_px * g.dst_row[mpl] + mseg * mbytes;
-    auto tile_slot = [&](DownTile& tile) -> uint8_t* {
-        return mv_luma ? &tile.y[mrow][16 * mseg] : (mpl == 1 ? &tile.u[mrow][8 * mseg] : &tile.v[mrow][8 * mseg]);
-    };
-    auto issue = [&](int grp) {
-        if (grp < n_groups) {
-            DownTile& tile = s_in[grp % kStages];
-            const int bx = grp * 8 + mseg;
-            if (bx < g.Bx) {
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile_slot(tile));
-                if (mv_luma) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(msrc + (int64_t)grp * 128) : "memory");
-                else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(msrc + (int64_t)grp * 64) : "memory");
+    // byte offset of this thread's piece inside a tile, shared-memory addresses of the rings, running global pointers
+    const uint32_t slot_off = mv_luma ? (uint32_t)(mrow * 144 + 16 * mseg)
+                                      : (uint32_t)((mpl == 1 ? offsetof(DownTile, u) : offsetof(DownTile, v)) + mrow * 72 + 8 * mseg);
+    const uint32_t in_base = (uint32_t)__cvta_generic_to_shared(&s_in[0]);
+    const uint8_t* const out_base = reinterpret_cast<const uint8_t*>(&s_out[0]);
+    const int mstep = mv_luma ? 128 : 64;
+    const int m_last = g.Bx - mseg;                           // this thread moves a piece of group grp iff 8 grp < m_last
+    const uint8_t* src_next = msrc;                           // piece of the next group to be requested
+    int grp_next = 0;
+    auto issue = [&]() {
+        if (grp_next < n_groups) {
+            const uint32_t tile = in_base + (uint32_t)(grp_next % kStages) * (uint32_t)sizeof(DownTile);
+            if (8 * grp_next < m_last) {
+                if (mv_luma) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tile + slot_off), "l"(src_next) : "memory");
+                else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tile + slot_off), "l"(src_next) : "memory");
             }
-            if (tid < 8 && grp * 8 + tid < g.Bx) {
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tile.lv[tid]);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(lv + grp * 8 + tid) : "memory");
-            }
+            if (tid < 8 && grp_next * 8 + tid < g.Bx)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tile + (uint32_t)offsetof(DownTile, lv) + 4u * tid),
+                             "l"(lv + grp_next * 8 + tid) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");      // always: keeps the group count uniform
+        src_next += mstep;
+        ++grp_next;
     };
 
     // ---- worker role: warp w owns block 8 grp + w; luma lane = (row, 8-pixel half), chroma lanes 0..15 U / 16..31 V
@@ -784,9 +790,9 @@ __global__ void __launch_bounds__(256) downsample_pow2_yuv420_kernel(const YuvGe
     const int cpl = lane >> 4, gl = lane & 15, cr = gl >> 1, ch = gl & 1;
 
 #pragma unroll
-    for (int sgi = 0; sgi < kStages - 1; ++sgi) issue(sgi);
+    for (int sgi = 0; sgi < kStages - 1; ++sgi) issue();
     for (int grp = 0; grp < n_groups; ++grp) {
-        issue(grp + kStages - 1);
+        issue();
         asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
         __syncthreads();                                          // tile grp is complete for every warp
         const DownTile& in = s_in[grp % kStages];
@@ -806,11 +812,12 @@ __global__ void __launch_bounds__(256) downsample_pow2_yuv420_kernel(const YuvGe
             *reinterpret_cast<uint32_t*>(cpl ? &out.v[cr][8 * w + 4 * ch] : &out.u[cr][8 * w + 4 * ch]) = c0;
         }
         __syncthreads();                                          // the output tile is complete; s_in[grp % kStages] is free again
-        if (grp * 8 + mseg < g.Bx) {
-            const uint8_t* from = tile_slot(out);
-            if (mv_luma) __stcs(reinterpret_cast<uint4*>(mdst + (int64_t)grp * 128), *reinterpret_cast<const uint4*>(from));
-            else __stcs(reinterpret_cast<uint2*>(mdst + (int64_t)grp * 64), *reinterpret_cast<const uint2*>(from));
+        if (8 * grp < m_last) {
+            const uint8_t* from = out_base + (grp & 1) * sizeof(DownTile) + slot_off;
+            if (mv_luma) __stcs(reinterpret_cast<uint4*>(mdst), *reinterpret_cast<const uint4*>(from));
+            else __stcs(reinterpret_cast<uint2*>(mdst), *reinterpret_cast<const uint2*>(from));
         }
+        mdst += mstep;
         // s_out[grp & 1] is rewritten two iterations later, after two more barriers
     }
 }
@@ -955,6 +962,73 @@ __global__ void __launch_bounds__(128) dampen_packed_kernel(const BlockGeom g, c
             n[2 * j + 1] = __float_as_int(y.y) - 0x4B400000;
         }
         __stcs(reinterpret_cast<uint2*>(dp + (int64_t)r * g.dst_row), make_uint2(pack_sat_u8x4(n[0], n[1], n[2], n[3]), pack_sat_u8x4(n[4], n[5], n[6], n[7])));
+    }
+}
+
+// Two horizontally adjacent tiles per thread, packed ELEMENT-WISE: x[r][c] = (tile A [r][c], tile B [r][c]).  All four
+// passes are then packed butterflies with no register transposes at all (the row passes of dampen_packed_kernel are
+// scalar because its pairs run along a row): half the floating-point instructions of the scalar kernel per tile, at
+// the price of 128 live registers for the two tiles.
+__global__ void __launch_bounds__(128) dampen_pair_kernel(const BlockGeom g, const float* __restrict__ strength, const uint32_t magic) {
+    const int pairs_x = g.Bx * g.pb / 16, tiles_y = g.By * g.pb / 8;     // width in tile pairs (Bx * pb is a multiple of 16 here)
+    const int64_t total = (int64_t)g.T * tiles_y * pairs_x;
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    int64_t b = id;
+    const int pxi = (int)(b % pairs_x);
+    b /= pairs_x;
+    const int tyi = (int)(b % tiles_y);
+    const int t = (int)(b / tiles_y);
+    const float* srow = strength + ((int64_t)t * g.By + (tyi * 8) / g.pb) * g.Bx;
+    const float sa = fminf(fmaxf(srow[(pxi * 16) / g.pb], 0.f), 1.f), sb = fminf(fmaxf(srow[(pxi * 16 + 8) / g.pb], 0.f), 1.f);
+    const uint8_t* sp = g.src + (int64_t)t * g.src_frame + (int64_t)tyi * 8 * g.src_row + (int64_t)pxi * 16;
+    uint8_t* dp = g.dst + (int64_t)t * g.dst_frame + (int64_t)tyi * 8 * g.dst_row + (int64_t)pxi * 16;
+
+    float2 x[8][8];
+    const float2 bias = make_float2(-8388608.f, -8388608.f);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4*>(sp + (int64_t)r * g.src_row));
+        x[r][0] = __fadd2_rn(make_float2(byte_as_biased_float<0>(v.x, magic), byte_as_biased_float<0>(v.z, magic)), bias);
+        x[r][1] = __fadd2_rn(make_float2(byte_as_biased_float<1>(v.x, magic), byte_as_biased_float<1>(v.z, magic)), bias);
+        x[r][2] = __fadd2_rn(make_float2(byte_as_biased_float<2>(v.x, magic), byte_as_biased_float<2>(v.z, magic)), bias);
+        x[r][3] = __fadd2_rn(make_float2(byte_as_biased_float<3>(v.x, magic), byte_as_biased_float<3>(v.z, magic)), bias);
+        x[r][4] = __fadd2_rn(make_float2(byte_as_biased_float<0>(v.y, magic), byte_as_biased_float<0>(v.w, magic)), bias);
+        x[r][5] = __fadd2_rn(make_float2(byte_as_biased_float<1>(v.y, magic), byte_as_biased_float<1>(v.w, magic)), bias);
+        x[r][6] = __fadd2_rn(make_float2(byte_as_biased_float<2>(v.y, magic), byte_as_biased_float<2>(v.w, magic)), bias);
+        x[r][7] = __fadd2_rn(make_float2(byte_as_biased_float<3>(v.y, magic), byte_as_biased_float<3>(v.w, magic)), bias);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) ELVIS_FDCT8_X2(x[r][0], x[r][1], x[r][2], x[r][3], x[r][4], x[r][5], x[r][6], x[r][7]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) ELVIS_FDCT8_X2(x[0][c], x[1][c], x[2][c], x[3][c], x[4][c], x[5][c], x[6][c], x[7][c]);
+    // gains 2^(-4 s (u+v)/14) / 64 of the two tiles, packed
+    float2 gk[15];
+    const float2 q = make_float2(exp2f(-4.0f * sa / 14.0f), exp2f(-4.0f * sb / 14.0f));
+    gk[0] = make_float2(1.0f / 64.0f, 1.0f / 64.0f);
+#pragma unroll
+    for (int k = 1; k < 15; ++k) gk[k] = __fmul2_rn(gk[k - 1], q);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int v = 0; v < 8; ++v) x[u][v] = __fmul2_rn(x[u][v], gk[u + v]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) ELVIS_IDCT8_X2(x[0][c], x[1][c], x[2][c], x[3][c], x[4][c], x[5][c], x[6][c], x[7][c]);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) ELVIS_IDCT8_X2(x[r][0], x[r][1], x[r][2], x[r][3], x[r][4], x[r][5], x[r][6], x[r][7]);
+    const float2 rnd = make_float2(12582912.f, 12582912.f);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        int na[8], nb[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float2 y = __fadd2_rn(x[r][c], rnd);
+            na[c] = __float_as_int(y.x) - 0x4B400000;
+            nb[c] = __float_as_int(y.y) - 0x4B400000;
+        }
+        __stcs(reinterpret_cast<uint4*>(dp + (int64_t)r * g.dst_row),
+               make_uint4(pack_sat_u8x4(na[0], na[1], na[2], na[3]), pack_sat_u8x4(na[4], na[5], na[6], na[7]),
+                          pack_sat_u8x4(nb[0], nb[1], nb[2], nb[3]), pack_sat_u8x4(nb[4], nb[5], nb[6], nb[7])));
     }
 }
 
@@ -1297,7 +1371,12 @@ extern "C" int elvis_dct_dampen(const elvis_plane* src, const elvis_plane* dst, 
     const bool fast = g.C == 1 && aligned_to(g.src, 8) && aligned_to(g.dst, 8) && g.src_frame % 8 == 0 &&
                       g.dst_frame % 8 == 0 && g.src_row % 8 == 0 && g.dst_row % 8 == 0;
     const unsigned grid = (unsigned)((total + 127) / 128);
-    if (fast && !(dampen_impl && !strcmp(dampen_impl, "scalar")))      // packed-fp32 kernel (default); ELVIS_DAMPEN_IMPL=scalar: the round-1 kernel
+    const bool al16 = aligned_to(g.src, 16) && aligned_to(g.dst, 16) && g.src_frame % 16 == 0 && g.dst_frame % 16 == 0 &&
+                      g.src_row % 16 == 0 && g.dst_row % 16 == 0 && (bx * block_px) % 16 == 0;
+    if (fast && al16 && dampen_impl && !strcmp(dampen_impl, "pair")) {   // two tiles per thread, element-wise packed (experimental)
+        const int64_t pairs = total / 2;
+        dampen_pair_kernel<<<(unsigned)((pairs + 127) / 128), 128, 0, st>>>(g, strength, 0x4B000000u);
+    } else if (fast && !(dampen_impl && !strcmp(dampen_impl, "scalar")))      // packed-fp32 kernel (default); ELVIS_DAMPEN_IMPL=scalar: the round-1 kernel
         dampen_packed_kernel<<<grid, 128, 0, st>>>(g, strength, 0x4B000000u);
     else if (fast)
         dampen_kernel<true><<<grid, 128, 0, st>>>(g, strength);

@@ -498,7 +498,7 @@ def test_mask_bit_packing(dev):
     assert np.array_equal(E.unpack_removal_masks(packed, shape), m)
 
 
-@pytest.mark.parametrize("impl", ["packed", "scalar", "hmma"])      # packed-fp32 kernel (default) / round-1 scalar kernel / tensor-core variant
+@pytest.mark.parametrize("impl", ["packed", "pair", "scalar", "hmma"])      # packed fp32 / two tiles per thread / round-1 scalar kernel / tensor cores
 @pytest.mark.parametrize("pb", [8, 16])
 def test_dct_dampen(dev, monkeypatch, pb, impl):
     from elvis_b200 import ops

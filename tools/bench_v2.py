@@ -37,7 +37,15 @@ cases["blur rounds 0..10 (elvis filter_frame_gaussian)"] = lambda: v2.blur(clip,
 cases["blur rounds 0..4 (presley blur_block)"] = lambda: v2.blur(clip, rounds4, out)
 cases["downsample pow2 levels 0..4 (elvis filter_frame_downsample)"] = lambda: v2.downsample_pow2(clip, lv5, 4, out)
 cases["downsample pow2 levels 0..3 (2-bit map)"] = lambda: v2.downsample_pow2(clip, lv2bit, 3, out)
+def dampen_with(impl):
+    def run():
+        os.environ["ELVIS_DAMPEN_IMPL"] = impl
+        v2.dampen(clip, strength, out)
+        os.environ.pop("ELVIS_DAMPEN_IMPL")
+    return run
 cases["dct dampen"] = lambda: v2.dampen(clip, strength, out)
+cases["dct dampen (ELVIS_DAMPEN_IMPL=pair)"] = dampen_with("pair")
+cases["dct dampen (ELVIS_DAMPEN_IMPL=packed)"] = dampen_with("packed")
 cases["levels_from_scores + pack 2-bit"] = lambda: ops.pack_levels_2bit(ops.levels_from_scores(scores, ops.LEVELS_ROUND, 3))
 for name, fn in cases.items():
     ms = timed(fn)
