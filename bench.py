@@ -528,7 +528,9 @@ def measure_v1(ctx, workload, steps, warmup, with_e2e, with_cpu, with_parity):
                 gpu_out["s" + tag], gpu_out["f" + tag] = s_.cpu().numpy(), f_.cpu().numpy()
             parity = verify.compare_v1(gpu_out, cpu_out, BLOCK, k)
             parity["checked_against"] = "oracle/cpu_baseline.py CpuElvisV1.outputs() on the CPU arm's frames"
-    launches_per_clip = 2 + 2 + 1 + 1 + 1 + 1   # score(init+kernel) combine(init+kernel) normalize select shrink(YUV fused) stretch(YUV fused)
+    # score(init+kernel) combine(init+kernel) [normalize: its own launch in the sharded scorer and the serial path, else folded into] select
+    # shrink(YUV fused) stretch(YUV fused)
+    launches_per_clip = 2 + 2 + (1 if world > 1 or not pipelined else 0) + 1 + 1 + 1
     if pg:
         launches_per_clip += 2 + 4 + 2 + 2      # halo: 2 ack waits + 2 flag stores (the copies are copy-engine work), 2 arrival waits, 2 acks; 2 all-reduces
         pg.check()

@@ -80,9 +80,9 @@ template <typename T> __global__ void __launch_bounds__(kThreads) minmax_kernel(
     block_minmax_commit(lo, hi, out);
 }
 
-// normalize_array applied to one value (elvis.py:864-867)
-__device__ __forceinline__ double norm01(double v, double lo, double hi) {
-    return hi > lo ? __ddiv_rn(__dsub_rn(v, lo), __dsub_rn(hi, lo)) : v;
+// normalize_array applied to one value (elvis.py:864-867); sp = InvariantDivisor(hi - lo)
+__device__ __forceinline__ double norm01(double v, double lo, double hi, const InvariantDivisor& sp) {
+    return hi > lo ? sp.divide(__dsub_rn(v, lo)) : v;
 }
 
 struct CombineParams {
@@ -97,15 +97,21 @@ struct CombineParams {
     double* out_minmax;
 };
 
+struct NormRange {
+    double lo, hi;
+    InvariantDivisor span;
+};
+__device__ __forceinline__ NormRange norm_range(double lo, double hi) { return NormRange{lo, hi, InvariantDivisor(__dsub_rn(hi, lo))}; }
+
 template <typename T> __device__ __forceinline__ double removability_at(const CombineParams& p, int t, int64_t i, bool last_frame,
-                                                                         double sc_lo, double sc_hi, double tc_lo, double tc_hi) {
+                                                                         const NormRange& scn, const NormRange& tcn) {
     const int64_t o = (int64_t)t * p.frame + i;
-    const double s = norm01(ld<T>(p.sc, o), sc_lo, sc_hi);
+    const double s = norm01(ld<T>(p.sc, o), scn.lo, scn.hi, scn.span);
     double r;
     if (last_frame) {
         r = s;                                                       // elvis.py:1183
     } else {
-        const double tn = norm01(ld<T>(p.tc, o + p.frame), tc_lo, tc_hi);
+        const double tn = norm01(ld<T>(p.tc, o + p.frame), tcn.lo, tcn.hi, tcn.span);
         r = __dadd_rn(__dmul_rn(p.alpha, s), __dmul_rn(p.one_minus_alpha, tn));   // elvis.py:1180
     }
     if (p.background && p.background[o]) r = __dmul_rn(r, 10.0);     // elvis.py:1195
@@ -114,10 +120,10 @@ template <typename T> __device__ __forceinline__ double removability_at(const Co
 
 // One thread owns one block position and walks a chunk of consecutive frames, so that the
 // un-smoothed value of frame t is computed once and carried in a register into frame t+1
-// (each value costs two correctly rounded fp64 divisions -- the kernel's whole cost).
+// (each value costs two correctly rounded fp64 divisions, by the two spans: InvariantDivisor).
 template <typename T> __global__ void __launch_bounds__(kThreads) combine_kernel(const CombineParams p) {
     const T* nm = static_cast<const T*>(p.norm);
-    const double sc_lo = (double)nm[0], sc_hi = (double)nm[1], tc_lo = (double)nm[2], tc_hi = (double)nm[3];
+    const NormRange scn = norm_range((double)nm[0], (double)nm[1]), tcn = norm_range((double)nm[2], (double)nm[3]);
     double lo = __longlong_as_double(0x7ff0000000000000LL), hi = __longlong_as_double(0xfff0000000000000LL);
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int tl0 = blockIdx.y * p.chunk_len;
@@ -125,11 +131,11 @@ template <typename T> __global__ void __launch_bounds__(kThreads) combine_kernel
     if (i < p.frame && tl0 < tl1) {
         double r_prev = 0.0;
         if (p.smooth && !(p.is_first && tl0 == 0))
-            r_prev = removability_at<T>(p, p.t_begin + tl0 - 1, i, false, sc_lo, sc_hi, tc_lo, tc_hi);
+            r_prev = removability_at<T>(p, p.t_begin + tl0 - 1, i, false, scn, tcn);
         for (int tl = tl0; tl < tl1; ++tl) {
             const bool clip_last = p.is_last && tl == p.t_count - 1;
             const bool clip_first = p.is_first && tl == 0;
-            const double r = removability_at<T>(p, p.t_begin + tl, i, clip_last, sc_lo, sc_hi, tc_lo, tc_hi);
+            const double r = removability_at<T>(p, p.t_begin + tl, i, clip_last, scn, tcn);
             double v = r;
             if (p.smooth && !clip_first)                                 // elvis.py:1206-1213
                 v = __dadd_rn(__dmul_rn(p.beta, r), __dmul_rn(p.one_minus_beta, r_prev));
@@ -145,9 +151,9 @@ template <typename T> __global__ void __launch_bounds__(kThreads) combine_kernel
 __global__ void __launch_bounds__(kThreads) normalize_kernel(double* x, int64_t n, const double* mm) {
     const double lo = mm[0], hi = mm[1];
     if (!(hi > lo)) return;
-    const double span = __dsub_rn(hi, lo);
+    const InvariantDivisor span(__dsub_rn(hi, lo));
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
-        x[i] = __ddiv_rn(__dsub_rn(x[i], lo), span);
+        x[i] = span.divide(__dsub_rn(x[i], lo));
 }
 
 // ---- a3 ----------------------------------------------------------------------------------
@@ -200,9 +206,9 @@ template <typename T> __global__ void __launch_bounds__(kThreads) importance_ker
     block_minmax_commit(lo, hi, s_mm);
     __syncthreads();
     const double mn = s_mm[0];
-    const double den = __dadd_rn(__dsub_rn(s_mm[1], mn), 1e-8);               // utils.py:686
+    const InvariantDivisor den(__dadd_rn(__dsub_rn(s_mm[1], mn), 1e-8));      // utils.py:686
     for (int64_t i = threadIdx.x; i < p.frame; i += kThreads)
-        p.out[(int64_t)tl * p.frame + i] = __ddiv_rn(__dsub_rn(value(i), mn), den);
+        p.out[(int64_t)tl * p.frame + i] = den.divide(__dsub_rn(value(i), mn));
 }
 
 // ---- level maps --------------------------------------------------------------------------

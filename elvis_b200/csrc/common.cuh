@@ -101,4 +101,31 @@ template <int K> __device__ __forceinline__ float byte_as_biased_float(uint32_t 
     return __uint_as_float(r);
 }
 
+// Correctly rounded fp64 division by a divisor that is the same for every element of a launch (the min-max spans
+// of elvis.py:864-867 and utils.py:686): a / d == __ddiv_rn(a, d) bit for bit, at 5 fused operations instead of the
+// ~30 of a general division.  y = RN(1/d) once; then q0 = RN(a y), two residual corrections q <- RN(q + RN(a - d q) y).
+// After the first correction q is a faithful quotient, and by Markstein's theorem (IBM J. R&D 34, 1990; Muller et al.,
+// Handbook of Floating-Point Arithmetic, 5.3) one more correction with a correctly rounded reciprocal and an exact
+// residual (the FMA) yields the correctly rounded quotient.  The residuals are exact only away from the over- and
+// underflow thresholds, so operands outside [2^-500, 2^500] (and NaN / infinity) take the general division; zeros
+// keep their sign.  tests/test_gpu_parity.py::test_invariant_division compares the two on adversarial operands.
+struct InvariantDivisor {
+    double d, y;
+    bool fast;
+    __device__ explicit InvariantDivisor(double divisor) : d(divisor) {
+        fast = divisor >= 0x1p-500 && divisor <= 0x1p500;
+        y = fast ? __drcp_rn(divisor) : 0.0;
+    }
+    __device__ __forceinline__ double divide(double a) const {
+        const double m = fabs(a);
+        if (fast && m >= 0x1p-500 && m <= 0x1p500) {
+            double q = __dmul_rn(a, y);
+            q = __fma_rn(__fma_rn(-d, q, a), y, q);
+            return __fma_rn(__fma_rn(-d, q, a), y, q);
+        }
+        if (fast && m == 0.0) return a;          // d > 0
+        return __ddiv_rn(a, d);
+    }
+};
+
 }  // namespace elvis

@@ -28,24 +28,45 @@ __device__ __forceinline__ unsigned long long row_key(double v, int polarity) {
 
 constexpr int select_threads(int n) { return n / 2 > 512 ? 512 : (n / 2 < 32 ? 32 : n / 2); }
 
+// Min-max normalisation folded into the selection (elvis_normalize_select_rows): the row is normalised as it is
+// loaded, written back, and ranked on the normalised values -- the same numbers, one pass over the scores less.
+struct RowNormalizer {
+    double lo;
+    InvariantDivisor span;
+    bool on;
+    __device__ explicit RowNormalizer(const double* mm) : lo(mm ? mm[0] : 0.0), span(mm ? mm[1] - mm[0] : 1.0), on(mm && mm[1] > mm[0]) {}
+    __device__ __forceinline__ double load(double* p) const {
+        double v = *p;
+        if (on) {
+            v = span.divide(__dsub_rn(v, lo));
+            *p = v;
+        }
+        return v;
+    }
+};
+
 template <int N>   // N = padded row length (power of two)
 __global__ void __launch_bounds__(select_threads(N)) select_rows_kernel(
-        const double* __restrict__ scores, int by, int bx, const int32_t* __restrict__ k_per_row, int k_uniform,
+        double* __restrict__ scores, const double* __restrict__ minmax, int by, int bx, const int32_t* __restrict__ k_per_row, int k_uniform,
         int polarity, uint8_t* __restrict__ mask) {
     __shared__ unsigned long long s_key[N];
     __shared__ uint16_t s_col[N];
+    const RowNormalizer norm(minmax);
     const int64_t row = blockIdx.x;
     const int k = k_per_row ? k_per_row[row % by] : k_uniform;
-    const double* src = scores + row * bx;
+    double* src = scores + row * bx;
     uint8_t* dst = mask + row * bx;
     if (k <= 0 || k >= bx) {   // nothing or everything removed: no ranking needed
-        for (int i = threadIdx.x; i < bx; i += blockDim.x) dst[i] = k >= bx ? 1 : 0;
+        for (int i = threadIdx.x; i < bx; i += blockDim.x) {
+            norm.load(src + i);
+            dst[i] = k >= bx ? 1 : 0;
+        }
         return;
     }
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         unsigned long long key = ~0ULL;
         if (i < bx) {
-            key = row_key(src[i], polarity);
+            key = row_key(norm.load(src + i), polarity);
         }
         s_key[i] = key;
         s_col[i] = (uint16_t)i;
@@ -80,13 +101,14 @@ __global__ void __launch_bounds__(select_threads(N)) select_rows_kernel(
 // One warp per row; slot j of lane l holds column j*32 + l.
 template <int E>
 __global__ void __launch_bounds__(256) select_rows_warp_kernel(
-        const double* __restrict__ scores, int64_t rows, int by, int bx, const int32_t* __restrict__ k_per_row,
-        int k_uniform, int polarity, uint8_t* __restrict__ mask) {
+        double* __restrict__ scores, const double* __restrict__ minmax, int64_t rows, int by, int bx,
+        const int32_t* __restrict__ k_per_row, int k_uniform, int polarity, uint8_t* __restrict__ mask) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
+    const RowNormalizer norm(minmax);
     const int k = k_per_row ? k_per_row[row % by] : k_uniform;
-    const double* src = scores + row * bx;
+    double* src = scores + row * bx;
     uint8_t* dst = mask + row * bx;
 
     unsigned long long key[E];
@@ -96,7 +118,7 @@ __global__ void __launch_bounds__(256) select_rows_warp_kernel(
         const int c = j * 32 + lane;
         key[j] = ~0ULL;
         if (c < bx) {
-            key[j] = row_key(src[c], polarity);
+            key[j] = row_key(norm.load(src + c), polarity);
             valid |= 1u << j;
         }
     }
@@ -167,9 +189,9 @@ __global__ void __launch_bounds__(256) select_rows_warp_kernel(
 }
 
 template <int E>
-int launch_select_warp(const double* scores, int64_t rows, int by, int bx, const int32_t* kpr, int ku, int pol, uint8_t* mask, cudaStream_t st) {
+int launch_select_warp(double* scores, const double* mm, int64_t rows, int by, int bx, const int32_t* kpr, int ku, int pol, uint8_t* mask, cudaStream_t st) {
     const unsigned grid = (unsigned)((rows + 7) / 8);
-    select_rows_warp_kernel<E><<<grid, 256, 0, st>>>(scores, rows, by, bx, kpr, ku, pol, mask);
+    select_rows_warp_kernel<E><<<grid, 256, 0, st>>>(scores, mm, rows, by, bx, kpr, ku, pol, mask);
     ELVIS_CHECK_LAUNCH();
     return ELVIS_OK;
 }
@@ -224,8 +246,8 @@ inline int grid_for(int64_t n) {
 }
 
 template <int N>
-int launch_select(const double* scores, int64_t rows, int by, int bx, const int32_t* kpr, int ku, int pol, uint8_t* mask, cudaStream_t st) {
-    select_rows_kernel<N><<<(unsigned)rows, select_threads(N), 0, st>>>(scores, by, bx, kpr, ku, pol, mask);
+int launch_select(double* scores, const double* mm, int64_t rows, int by, int bx, const int32_t* kpr, int ku, int pol, uint8_t* mask, cudaStream_t st) {
+    select_rows_kernel<N><<<(unsigned)rows, select_threads(N), 0, st>>>(scores, mm, by, bx, kpr, ku, pol, mask);
     ELVIS_CHECK_LAUNCH();
     return ELVIS_OK;
 }
@@ -235,9 +257,10 @@ int launch_select(const double* scores, int64_t rows, int by, int bx, const int3
 
 using namespace elvis;
 
-extern "C" int elvis_select_rows(const double* scores, int32_t n_frames, int32_t by, int32_t bx,
-                                 const int32_t* k_per_row, int32_t k_uniform, int32_t polarity,
-                                 uint8_t* mask, elvis_stream_t stream) {
+namespace {
+// scores are written only when minmax is given
+int select_rows(double* scores, const double* minmax, int32_t n_frames, int32_t by, int32_t bx, const int32_t* k_per_row,
+                int32_t k_uniform, int32_t polarity, uint8_t* mask, elvis_stream_t stream) {
     if (!scores || !mask || n_frames <= 0 || by <= 0 || bx <= 0) return ELVIS_ERR_INVALID_ARG;
     if (polarity != ELVIS_REMOVE_HIGH && polarity != ELVIS_REMOVE_LOW) return ELVIS_ERR_INVALID_ARG;
     if (bx > 4096) return ELVIS_ERR_UNSUPPORTED;
@@ -245,18 +268,32 @@ extern "C" int elvis_select_rows(const double* scores, int32_t n_frames, int32_t
     cudaStream_t st = as_stream(stream);
     const bool force_sort = getenv("ELVIS_SELECT_SORT") != nullptr;   // test hook: exercise the CTA path on short rows
     if (!force_sort) {
-        if (bx <= 64) return launch_select_warp<2>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
-        if (bx <= 128) return launch_select_warp<4>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
-        if (bx <= 256) return launch_select_warp<8>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
-        if (bx <= 512) return launch_select_warp<16>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+        if (bx <= 64) return launch_select_warp<2>(scores, minmax, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+        if (bx <= 128) return launch_select_warp<4>(scores, minmax, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+        if (bx <= 256) return launch_select_warp<8>(scores, minmax, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+        if (bx <= 512) return launch_select_warp<16>(scores, minmax, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
     }
-    if (bx <= 64) return launch_select<64>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
-    if (bx <= 128) return launch_select<128>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
-    if (bx <= 256) return launch_select<256>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
-    if (bx <= 512) return launch_select<512>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
-    if (bx <= 1024) return launch_select<1024>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
-    if (bx <= 2048) return launch_select<2048>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
-    return launch_select<4096>(scores, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+    if (bx <= 64) return launch_select<64>(scores, minmax, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+    if (bx <= 128) return launch_select<128>(scores, minmax, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+    if (bx <= 256) return launch_select<256>(scores, minmax, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+    if (bx <= 512) return launch_select<512>(scores, minmax, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+    if (bx <= 1024) return launch_select<1024>(scores, minmax, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+    if (bx <= 2048) return launch_select<2048>(scores, minmax, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+    return launch_select<4096>(scores, minmax, rows, by, bx, k_per_row, k_uniform, polarity, mask, st);
+}
+}  // namespace
+
+extern "C" int elvis_select_rows(const double* scores, int32_t n_frames, int32_t by, int32_t bx,
+                                 const int32_t* k_per_row, int32_t k_uniform, int32_t polarity,
+                                 uint8_t* mask, elvis_stream_t stream) {
+    return select_rows(const_cast<double*>(scores), nullptr, n_frames, by, bx, k_per_row, k_uniform, polarity, mask, stream);
+}
+
+extern "C" int elvis_normalize_select_rows(double* scores, const double* minmax, int32_t n_frames, int32_t by, int32_t bx,
+                                           const int32_t* k_per_row, int32_t k_uniform, int32_t polarity,
+                                           uint8_t* mask, elvis_stream_t stream) {
+    if (!minmax) return ELVIS_ERR_INVALID_ARG;
+    return select_rows(scores, minmax, n_frames, by, bx, k_per_row, k_uniform, polarity, mask, stream);
 }
 
 extern "C" int elvis_pack_mask_bits(const uint8_t* mask, int64_t n, uint8_t* packed, elvis_stream_t stream) {

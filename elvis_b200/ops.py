@@ -190,8 +190,11 @@ def importance_scores(sc: torch.Tensor, tc: torch.Tensor, foreground: torch.Tens
 
 
 # ------------------------------------------------------------------------------ a4-a7
-def select_rows(scores: torch.Tensor, k, polarity: int = REMOVE_HIGH, out: torch.Tensor | None = None) -> torch.Tensor:
-    """(T, By, Bx) float64 -> uint8 mask, 1 = removed.  k: int, or int32 CUDA tensor (By,)."""
+def select_rows(scores: torch.Tensor, k, polarity: int = REMOVE_HIGH, out: torch.Tensor | None = None,
+                normalize_with: torch.Tensor | None = None) -> torch.Tensor:
+    """(T, By, Bx) float64 -> uint8 mask, 1 = removed.  k: int, or int32 CUDA tensor (By,).
+    normalize_with: {min, max} float64 on the device -- normalize_(scores, mm) folded into the same pass
+    (the scores are normalised IN PLACE and ranked on the normalised values)."""
     _check_cuda(scores, torch.float64, "scores")
     if scores.dim() != 3 or not scores.is_contiguous():
         raise ValueError("scores must be contiguous (T, By, Bx)")
@@ -203,9 +206,14 @@ def select_rows(scores: torch.Tensor, k, polarity: int = REMOVE_HIGH, out: torch
         _check_cuda(k, torch.int32, "k")
         if k.shape != (by,) or not k.is_contiguous():
             raise ValueError("per-row k must be a contiguous (By,) tensor")
-        call("elvis_select_rows", _ptr(scores), T, by, bx, _ptr(k), 0, polarity, _ptr(mask), _stream())
+        k_rows, k_all = _ptr(k), 0
     else:
-        call("elvis_select_rows", _ptr(scores), T, by, bx, _ptr(None), int(k), polarity, _ptr(mask), _stream())
+        k_rows, k_all = _ptr(None), int(k)
+    if normalize_with is not None:
+        _check_cuda(normalize_with, torch.float64, "minmax")
+        call("elvis_normalize_select_rows", _ptr(scores), _ptr(normalize_with), T, by, bx, k_rows, k_all, polarity, _ptr(mask), _stream())
+    else:
+        call("elvis_select_rows", _ptr(scores), T, by, bx, k_rows, k_all, polarity, _ptr(mask), _stream())
     return mask
 
 

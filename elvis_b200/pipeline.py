@@ -173,7 +173,7 @@ class ElvisV1Pipelined:
 
     # ------------------------------------------------------------------ prepared calls
     def _program(self, clip: Yuv420, index: int):
-        """The six C-ABI calls of one clip through slot `index`, arguments converted once (None when the clip's
+        """The five C-ABI calls of one clip through slot `index`, arguments converted once (None when the clip's
         geometry needs the generic per-plane path)."""
         key = (index,) + tuple((p.data_ptr(), p.stride(0), p.stride(1)) for p in clip.planes) + tuple(clip.y.shape)
         prog = self._programs.get(key)
@@ -205,9 +205,8 @@ class ElvisV1Pipelined:
             _Prepared("elvis_combine_removability", (ptr(slot["sc"]), ptr(slot["tc"]), i32(_lib.F32), ptr(slot["norm"]), i32(T), i32(by), i32(bx),
                                                      i32(0), i32(T), i32(1), i32(1), vp(0), C.c_double(p.alpha), C.c_double(p.beta), i32(smooth),
                                                      ptr(slot["scores"]), ptr(slot["smm"]), st["score"])),
-            _Prepared("elvis_normalize", (ptr(slot["scores"]), C.c_int64(slot["scores"].numel()), ptr(slot["smm"]), st["score"])),
-            _Prepared("elvis_select_rows", (ptr(slot["scores"]), i32(T), i32(by), i32(bx), vp(0), i32(self.k), i32(ops.REMOVE_HIGH),
-                                            ptr(slot["mask"]), st["move"])),
+            _Prepared("elvis_normalize_select_rows", (ptr(slot["scores"]), ptr(slot["smm"]), i32(T), i32(by), i32(bx), vp(0), i32(self.k),
+                                                      i32(ops.REMOVE_HIGH), ptr(slot["mask"]), st["move"])),
             _Prepared("elvis_shrink_yuv420", (src, shr, i32(T), i32(p.bs), i32(by), i32(bx), i32(small_bx), ptr(slot["mask"]),
                                               i32(self.move_ctas), st["move"]), (src, shr, clip)),
             _Prepared("elvis_stretch_yuv420", (shr, ful, i32(T), i32(p.bs), i32(by), i32(bx), i32(small_bx), ptr(slot["mask"]),
@@ -219,7 +218,7 @@ class ElvisV1Pipelined:
         return prog
 
     def _submit_prepared(self, slot: dict, prog) -> dict:
-        score, combine, normalize, select, shrink, stretch = prog
+        score, combine, select, shrink, stretch = prog
         ready = slot["ready"]
         ready.record()                                        # inputs produced on the caller's stream
         self.s_score.wait_event(ready)
@@ -227,7 +226,6 @@ class ElvisV1Pipelined:
             self.s_score.wait_event(slot["done"])             # the slot's previous clip has left the move stage
         score()
         combine()
-        normalize()
         slot["scored"].record(self.s_score)
         self.s_move.wait_event(slot["scored"])
         select()
@@ -275,11 +273,12 @@ class ElvisV1Pipelined:
                 ops.score_sc_tc(clip.y, p.bs, out=(slot["sc"], slot["tc"], slot["norm"]))
                 ops.combine_removability(slot["sc"], slot["tc"], slot["norm"], p.alpha, p.beta,
                                          out=(slot["scores"], slot["smm"]))
-                ops.normalize_(slot["scores"], slot["smm"])
             slot["scored"].record()
         with torch.cuda.stream(self.s_move):
             self.s_move.wait_event(slot["scored"])
-            ops.select_rows(slot["scores"], self.k, ops.REMOVE_HIGH, out=slot["mask"])
+            # the final normalisation (elvis.py:1218) rides on the ranking pass unless the scorer already applied it
+            ops.select_rows(slot["scores"], self.k, ops.REMOVE_HIGH, out=slot["mask"],
+                            normalize_with=None if self.score_fn is not None else slot["smm"])
             sh, fu, bs = slot["shrunk"], slot["full"], self.pipe.bs
             move_planes(clip, sh, slot["mask"], bs, sh.y.shape[2] // bs, False, self.move_ctas)
             if self.s_stretch is None:

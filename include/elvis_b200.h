@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ELVIS_B200_ABI_VERSION 5
+#define ELVIS_B200_ABI_VERSION 6
 
 #define ELVIS_OK               0
 #define ELVIS_ERR_INVALID_ARG (-1)   /* NULL pointer, non-positive size, out-of-range parameter   */
@@ -130,6 +130,13 @@ ELVIS_API int elvis_importance_scores(const void* sc, const void* tc, const void
 ELVIS_API int elvis_select_rows(const double* scores, int32_t n_frames, int32_t by, int32_t bx,
                       const int32_t* k_per_row, int32_t k_uniform, int32_t polarity,
                       uint8_t* mask, elvis_stream_t stream);
+
+/* elvis_normalize followed by elvis_select_rows in one pass over the scores (elvis.py:1218 then 1399-1415): every
+ * score is normalised in place with `minmax` (2 float64 on the device, the same rule and the same bits as
+ * elvis_normalize) as its row is loaded for ranking, and the mask is selected on the normalised values. */
+ELVIS_API int elvis_normalize_select_rows(double* scores, const double* minmax, int32_t n_frames, int32_t by, int32_t bx,
+                                const int32_t* k_per_row, int32_t k_uniform, int32_t polarity,
+                                uint8_t* mask, elvis_stream_t stream);
 
 /* ---- a4/a6: shrink -- left-compact the kept blocks of every block row
  * (elvis.py:1418-1425; utils.py:727-735).  Plane block = block_px x block_px pixels.

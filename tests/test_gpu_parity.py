@@ -521,6 +521,59 @@ def test_dct_dampen(dev, monkeypatch, pb, impl):
     assert np.array_equal(outp[..., 1], out)
 
 
+def test_invariant_division_is_the_correctly_rounded_quotient(dev):
+    """normalize_ divides by a per-launch constant with a reciprocal + two FMA corrections (csrc/common.cuh
+    InvariantDivisor): it must equal IEEE division bit for bit, including divisors whose significand is all ones
+    or a power of two, numerators at the extremes, zeros, NaN and infinity, and spans that take the general path."""
+    import torch
+    from elvis_b200 import ops
+    rng = np.random.default_rng(2024)
+    n = 1 << 20
+    ones = np.frombuffer(np.uint64(0x3FFFFFFFFFFFFFFF).tobytes(), dtype=np.float64)[0]      # 1.999..., significand all ones
+    spans = [1.0, ones, ones * 2.0 ** -7, 3.0, 1.0 / 3.0, 0.1, float(np.nextafter(1.0, 2.0)), 7.3e12, 2.0 ** -400, 2.0 ** 499,
+             2.0 ** -600, 2.0 ** 600, 5e-324 * 2 ** 20] + list(np.exp(rng.uniform(-40, 40, 12)))
+    for i, span in enumerate(spans):
+        lo = [0.0, -1.5, 0.37][i % 3] if 2.0 ** -60 < span < 2.0 ** 60 else 0.0
+        hi = lo + span
+        x = lo + rng.random(n) * (hi - lo)
+        bits = rng.integers(0, 1 << 52, n // 4, dtype=np.uint64) | (np.uint64(1023) << np.uint64(52))
+        x[: n // 4] = lo + (bits.view(np.float64) - 1.0) * (hi - lo)            # full-width significands
+        x[-8:] = [lo, hi, 0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324]
+        x[-16:-8] = lo + np.array([2.0 ** -700, 2.0 ** -510, 2.0 ** -490, 2.0 ** 490, 2.0 ** 510, 2.0 ** 700, 1e-310, 1.0])
+        with np.errstate(all="ignore"):
+            want = (x - lo) / (hi - lo)
+        got = ops.normalize_(to_dev(x, dev), torch.tensor([lo, hi], dtype=torch.float64, device=dev)).cpu().numpy()
+        same = (got.view(np.uint64) == want.view(np.uint64)) | (np.isnan(got) & np.isnan(want))
+        assert same.all(), (span, x[~same][:4], got[~same][:4], want[~same][:4])
+
+
+@pytest.mark.parametrize("sort_path", [False, True])
+def test_normalize_select_rows_equals_the_two_calls(dev, monkeypatch, sort_path):
+    """elvis_normalize_select_rows == elvis_normalize then elvis_select_rows: same normalised scores (bits), same mask."""
+    import torch
+    from elvis_b200 import ops
+    if sort_path:
+        monkeypatch.setenv("ELVIS_SELECT_SORT", "1")
+    rng = np.random.default_rng(5)
+    for bx, ties in ((240, "none"), (120, "quantised"), (37, "all"), (300, "none")):
+        raw = random_scores(rng, (3, 7, bx), ties) * 3.7 - 1.2
+        mm = torch.tensor([raw.min(), raw.max()], dtype=torch.float64, device=dev)
+        for pol in (P.REMOVE_HIGH, P.REMOVE_LOW):
+            for k in (0, 1, bx // 2, bx):
+                two = ops.normalize_(to_dev(raw, dev), mm)
+                mask2 = ops.select_rows(two, k, pol)
+                one = to_dev(raw, dev)
+                mask1 = ops.select_rows(one, k, pol, normalize_with=mm)
+                assert torch.equal(one, two) and torch.equal(mask1, mask2)
+                ref = (raw - raw.min()) / (raw.max() - raw.min()) if raw.max() > raw.min() else raw
+                assert np.array_equal(one.cpu().numpy(), ref)
+                assert np.array_equal(mask1.cpu().numpy(), P.select_rows(ref, k, pol))
+        kr = rng.integers(0, bx + 1, 7).astype(np.int32)                      # per-row k
+        one = to_dev(raw, dev)
+        mask1 = ops.select_rows(one, to_dev(kr, dev), P.REMOVE_LOW, normalize_with=mm)
+        assert np.array_equal(mask1.cpu().numpy(), P.select_rows((raw - raw.min()) / (raw.max() - raw.min()) if raw.max() > raw.min() else raw, kr, P.REMOVE_LOW))
+
+
 def test_select_rows_cta_sort_path(dev, monkeypatch):
     """Short rows normally take the warp quickselect; force the CTA bitonic path as well."""
     from elvis_b200 import ops
