@@ -103,24 +103,38 @@ struct NormRange {
 };
 __device__ __forceinline__ NormRange norm_range(double lo, double hi) { return NormRange{lo, hi, InvariantDivisor(__dsub_rn(hi, lo))}; }
 
-template <typename T> __device__ __forceinline__ double removability_at(const CombineParams& p, int t, int64_t i, bool last_frame,
-                                                                         const NormRange& scn, const NormRange& tcn) {
-    const int64_t o = (int64_t)t * p.frame + i;
-    const double s = norm01(ld<T>(p.sc, o), scn.lo, scn.hi, scn.span);
+// un-smoothed removability of one block from its raw SC (frame t) and TC (frame t + 1) values
+__device__ __forceinline__ double removability_of(const CombineParams& p, double sc_raw, double tc_raw, bool last_frame, bool in_background,
+                                                  const NormRange& scn, const NormRange& tcn) {
+    const double s = norm01(sc_raw, scn.lo, scn.hi, scn.span);
     double r;
     if (last_frame) {
         r = s;                                                       // elvis.py:1183
     } else {
-        const double tn = norm01(ld<T>(p.tc, o + p.frame), tcn.lo, tcn.hi, tcn.span);
+        const double tn = norm01(tc_raw, tcn.lo, tcn.hi, tcn.span);
         r = __dadd_rn(__dmul_rn(p.alpha, s), __dmul_rn(p.one_minus_alpha, tn));   // elvis.py:1180
     }
-    if (p.background && p.background[o]) r = __dmul_rn(r, 10.0);     // elvis.py:1195
+    if (in_background) r = __dmul_rn(r, 10.0);                       // elvis.py:1195
     return r;
 }
 
+// raw inputs of one block in frame t (extended-range index): SC(t), TC(t + 1) unless t is the clip's last frame, background flag
+template <typename T> struct RawBlock {
+    T sc, tc;
+    bool bg;
+    __device__ __forceinline__ void load(const CombineParams& p, int t, int64_t i, bool last_frame) {
+        const int64_t o = (int64_t)t * p.frame + i;
+        sc = static_cast<const T*>(p.sc)[o];
+        tc = last_frame ? T(0) : static_cast<const T*>(p.tc)[o + p.frame];
+        bg = p.background && p.background[o];
+    }
+};
+
 // One thread owns one block position and walks a chunk of consecutive frames, so that the
-// un-smoothed value of frame t is computed once and carried in a register into frame t+1
-// (each value costs two correctly rounded fp64 divisions, by the two spans: InvariantDivisor).
+// un-smoothed value of frame t is computed once and carried in a register into frame t+1.
+// Each value costs two correctly rounded fp64 divisions by the two spans (InvariantDivisor);
+// the raw inputs of frame t+1 are loaded before frame t is computed, so the load latency
+// overlaps the dependent fp64 chain.
 template <typename T> __global__ void __launch_bounds__(kThreads) combine_kernel(const CombineParams p) {
     const T* nm = static_cast<const T*>(p.norm);
     const NormRange scn = norm_range((double)nm[0], (double)nm[1]), tcn = norm_range((double)nm[2], (double)nm[3]);
@@ -129,13 +143,19 @@ template <typename T> __global__ void __launch_bounds__(kThreads) combine_kernel
     const int tl0 = blockIdx.y * p.chunk_len;
     const int tl1 = min(p.t_count, tl0 + p.chunk_len);
     if (i < p.frame && tl0 < tl1) {
+        RawBlock<T> next, cur;
+        next.load(p, p.t_begin + tl0, i, p.is_last && tl0 == p.t_count - 1);
         double r_prev = 0.0;
-        if (p.smooth && !(p.is_first && tl0 == 0))
-            r_prev = removability_at<T>(p, p.t_begin + tl0 - 1, i, false, scn, tcn);
+        if (p.smooth && !(p.is_first && tl0 == 0)) {
+            cur.load(p, p.t_begin + tl0 - 1, i, false);
+            r_prev = removability_of(p, (double)cur.sc, (double)cur.tc, false, cur.bg, scn, tcn);
+        }
         for (int tl = tl0; tl < tl1; ++tl) {
             const bool clip_last = p.is_last && tl == p.t_count - 1;
             const bool clip_first = p.is_first && tl == 0;
-            const double r = removability_at<T>(p, p.t_begin + tl, i, clip_last, scn, tcn);
+            cur = next;
+            if (tl + 1 < tl1) next.load(p, p.t_begin + tl + 1, i, p.is_last && tl + 1 == p.t_count - 1);
+            const double r = removability_of(p, (double)cur.sc, (double)cur.tc, clip_last, cur.bg, scn, tcn);
             double v = r;
             if (p.smooth && !clip_first)                                 // elvis.py:1206-1213
                 v = __dadd_rn(__dmul_rn(p.beta, r), __dmul_rn(p.one_minus_beta, r_prev));
@@ -286,9 +306,9 @@ extern "C" int elvis_combine_removability(const void* sc, const void* tc, int32_
     cudaStream_t st = as_stream(stream);
     minmax_init<<<1, 32, 0, st>>>(out_minmax);
     ELVIS_CHECK_LAUNCH();
-    // enough CTAs for ~4 per SM; every chunk recomputes one carried value, so keep chunks >= 8 frames
+    // enough CTAs for ~8 per SM; every chunk recomputes one carried value, so keep chunks >= 8 frames
     const int gx = (int)((p.frame + kThreads - 1) / kThreads);
-    int chunks = (4 * kNumSMs + gx - 1) / gx;
+    int chunks = (8 * kNumSMs + gx - 1) / gx;
     if (chunks > (t_count + 7) / 8) chunks = (t_count + 7) / 8;
     if (chunks < 1) chunks = 1;
     p.chunk_len = (t_count + chunks - 1) / chunks;

@@ -117,13 +117,16 @@ struct InvariantDivisor {
         y = fast ? __drcp_rn(divisor) : 0.0;
     }
     __device__ __forceinline__ double divide(double a) const {
-        const double m = fabs(a);
-        if (fast && m >= 0x1p-500 && m <= 0x1p500) {
-            double q = __dmul_rn(a, y);
-            q = __fma_rn(__fma_rn(-d, q, a), y, q);
-            return __fma_rn(__fma_rn(-d, q, a), y, q);
+        // range tests on the exponent field: integer work, the fp64 pipe is the scarce one
+        const unsigned hi = (unsigned)__double2hiint(a);
+        if (fast) {
+            if (((hi >> 20) & 0x7ffu) - 523u <= 1000u) {                 // 2^-500 <= |a| < 2^501
+                double q = __dmul_rn(a, y);
+                q = __fma_rn(__fma_rn(-d, q, a), y, q);
+                return __fma_rn(__fma_rn(-d, q, a), y, q);
+            }
+            if (((hi << 1) | (unsigned)__double2loint(a)) == 0u) return a;   // +-0 / d, d > 0
         }
-        if (fast && m == 0.0) return a;          // d > 0
         return __ddiv_rn(a, d);
     }
 };

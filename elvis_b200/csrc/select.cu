@@ -7,7 +7,7 @@
 // in that order -- a SELECTION problem, not a sort:
 //   * rows of up to 512 blocks: one WARP per (frame, block-row), the row held in registers
 //     (32 columns per register slot), randomised quickselect with ballot/shuffle counting --
-//     about 2 ln(Bx) rounds of Bx/32 compares per lane, no shared memory, no barriers;
+//     about 2 ln(Bx) rounds of Bx/32 compares per lane (~100 instructions each), no shared memory, no barriers;
 //   * longer rows: one CTA per row, shared-memory bitonic sort of (key, column) pairs.
 #include "common.cuh"
 
@@ -126,60 +126,49 @@ __global__ void __launch_bounds__(256) select_rows_warp_kernel(
     if (k >= bx) {
         selected = valid;
     } else if (k > 0) {
+        // Invariant: the k smallest are `selected` plus the `need` smallest of the `total` candidates in `active`.
         unsigned active = valid;
-        int need = k;
-        unsigned round = 0;
-        while (need > 0) {
-            // inclusive scan of the per-lane active counts
-            const int cnt = __popc(active);
-            int pre = cnt;
+        int need = k, total = bx;
+        unsigned h = (unsigned)row * 2654435761u + 0x7F4A7C15u;
+        while (total > need) {
+            // pivot: a pseudo-random (reproducible) candidate -- the first lane at or after a random position that
+            // still has candidates, and in it the first candidate slot at or after a random slot
+            h = h * 1664525u + 1013904223u;
+            const unsigned has = __ballot_sync(0xffffffffu, active != 0);
+            const int s1 = (int)(h >> 27);
+            const int src_lane = (__ffs(__funnelshift_r(has, has, s1)) - 1 + s1) & 31;
+            const int s2 = (int)((h >> 20) & (E - 1));
+            int pslot = (__ffs((active | (active << E)) >> s2) - 1 + s2) & (E - 1);
+            unsigned long long pick[E / 2];
 #pragma unroll
-            for (int m = 1; m < 32; m <<= 1) {
-                const int o = __shfl_up_sync(0xffffffffu, pre, m);
-                if (lane >= m) pre += o;
-            }
-            const int total = __shfl_sync(0xffffffffu, pre, 31);
-            if (total <= need) {   // (== by the loop invariant) every remaining candidate is removed
-                selected |= active;
-                break;
-            }
-            // pivot: the r-th active element, r pseudo-random but reproducible
-            const unsigned h = ((unsigned)row * 2654435761u) ^ (round * 0x9E3779B9u + 0x7F4A7C15u);
-            const int r = (int)__umulhi(h * 2246822519u, (unsigned)total);
-            const bool mine = (pre - cnt <= r) && (r < pre);
-            const int src_lane = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
-            unsigned long long pk = 0;
-            int pslot = 0;
-            if (mine) {
-                unsigned a = active;
-                for (int skip = r - (pre - cnt); skip > 0; --skip) a &= a - 1;   // drop the lowest set bits
-                pslot = __ffs(a) - 1;
+            for (int j = 0; j < E / 2; ++j) pick[j] = (pslot & (E / 2)) ? key[j + E / 2] : key[j];
 #pragma unroll
-                for (int j = 0; j < E; ++j)
-                    if (j == pslot) pk = key[j];
-            }
-            pk = __shfl_sync(0xffffffffu, pk, src_lane);
+            for (int w = E / 4; w >= 1; w >>= 1)
+#pragma unroll
+                for (int j = 0; j < w; ++j) pick[j] = (pslot & w) ? pick[j + w] : pick[j];
+            const unsigned long long pk = __shfl_sync(0xffffffffu, pick[0], src_lane);
             pslot = __shfl_sync(0xffffffffu, pslot, src_lane);
-            const int pcol = pslot * 32 + src_lane;
-            // candidates at or before the pivot in (key, column) order
+            // candidates at or before the pivot in (key, column) order: key < pk + [column <= pivot column]
+            // (a pivot is never the padding key ~0, so pk + 1 does not wrap)
+            const unsigned col_le = ((1u << pslot) - 1u) | ((unsigned)(lane <= src_lane) << pslot);
+            const unsigned long long pk1 = pk + 1;
             unsigned le = 0;
 #pragma unroll
-            for (int j = 0; j < E; ++j) {
-                const bool b = key[j] < pk || (key[j] == pk && j * 32 + lane <= pcol);
-                le |= (unsigned)b << j;
-            }
+            for (int j = 0; j < E; ++j) le |= (unsigned)(key[j] < (((col_le >> j) & 1u) ? pk1 : pk)) << j;
             le &= active;
             const int c_le = __reduce_add_sync(0xffffffffu, __popc(le));
             if (c_le <= need) {          // all of them belong to the k smallest
                 selected |= le;
                 need -= c_le;
+                total -= c_le;
                 active &= ~le;
             } else {                     // the k-th smallest lies strictly before the pivot
                 active = le;
-                if (mine) active &= ~(1u << pslot);
+                if (lane == src_lane) active &= ~(1u << pslot);
+                total = c_le - 1;
             }
-            ++round;
         }
+        if (need > 0) selected |= active;    // total == need: every remaining candidate is removed
     }
 #pragma unroll
     for (int j = 0; j < E; ++j) {
