@@ -10,6 +10,7 @@
 #include "dct8.cuh"
 #include "dct8_packed.cuh"
 #include "down_pow2.cuh"
+#include "tma.cuh"
 #include <cstddef>
 #include <cstring>
 #include <cuda_fp16.h>
@@ -822,6 +823,87 @@ __global__ void __launch_bounds__(256) downsample_pow2_yuv420_kernel(const YuvGe
     }
 }
 
+// The same kernel with the tile traffic handed to the TMA unit (default when the planes can be described by tensor
+// maps: 16-byte aligned bases and strides).  One thread issues three box loads per tile of 8 blocks -- 16 rows x 128 bytes
+// of luma with the 128-byte swizzle, 8 rows x 64 bytes of U and of V with the 64-byte swizzle -- onto an mbarrier of a
+// 4-deep ring, and three box stores of the finished tile; nobody else executes a mover instruction (the cp.async version
+// above spends 70 of its 216 instructions per block on moving).  The swizzles replace the padded pitches: warp w reads 16-byte
+// chunk w of every luma row, which the hardware has placed at chunk w ^ (row & 7), so the sixteen rows of a block
+// spread over all banks; chroma likewise with chunk (w >> 1) ^ ((row >> 1) & 3).  Partial tiles at the right edge need no code:
+// loads zero-fill and stores clip at the tensor bounds.
+struct DownMaps {
+    CUtensorMap in[3], out[3];
+};
+
+__global__ void __launch_bounds__(256) downsample_pow2_yuv420_tma_kernel(const __grid_constant__ DownMaps m, const int By, const int Bx,
+                                                                         const int32_t* __restrict__ levels, const int max_level) {
+    constexpr int kStages = 4;
+    constexpr uint32_t kTile = 3072, kOffU = 2048, kOffV = 2560;     // luma 16 x 128, U 8 x 64, V 8 x 64
+    __shared__ __align__(1024) uint8_t s_in[kStages * kTile];
+    __shared__ __align__(1024) uint8_t s_out[2 * kTile];
+    __shared__ __align__(8) uint64_t s_full[kStages];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int t = blockIdx.x / By, by = blockIdx.x - t * By;
+    const int n_groups = (Bx + 7) / 8;
+    const int32_t* lv = levels + (int64_t)blockIdx.x * Bx;
+    const uint32_t in_base = tma::smem_u32(s_in), out_base = tma::smem_u32(s_out), bar = tma::smem_u32(s_full);
+
+    auto issue_load = [&](int grp) {                                  // thread 0 only
+        const uint32_t dst = in_base + (uint32_t)(grp % kStages) * kTile, b = bar + 8u * (uint32_t)(grp % kStages);
+        tma::mbar_arrive_expect_tx(b, kTile);
+        tma::load_3d(dst, &m.in[0], grp * 128, by * 16, t, b);
+        tma::load_3d(dst + kOffU, &m.in[1], grp * 64, by * 8, t, b);
+        tma::load_3d(dst + kOffV, &m.in[2], grp * 64, by * 8, t, b);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int sgi = 0; sgi < kStages; ++sgi) tma::mbar_init(bar + 8u * sgi, 1);
+        tma::mbar_init_fence();
+        for (int grp = 0; grp < kStages && grp < n_groups; ++grp) issue_load(grp);
+    }
+    __syncthreads();                                                  // the barriers are initialised for everyone
+
+    // worker role: warp w owns block 8 grp + w; luma lane = (row, 8-pixel half), chroma lanes 0..15 U / 16..31 V
+    const int yr = lane >> 1, yh = lane & 1;
+    const int cpl = lane >> 4, gl = lane & 15, cr = gl >> 1, ch = gl & 1;
+    const uint32_t y_off = (uint32_t)(yr * 128 + (((w ^ (yr & 7)) << 4) | (yh << 3)));
+    const uint32_t c_off = (cpl ? kOffV : kOffU) + (uint32_t)(cr * 64 + ((((w >> 1) ^ ((cr >> 1) & 3)) << 4) | ((w & 1) << 3) | (ch << 2)));
+    int L_next = w < Bx ? lv[w] : 0;
+    for (int grp = 0; grp < n_groups; ++grp) {
+        const int slot = grp % kStages;
+        const int bx = grp * 8 + w;
+        int L = L_next;
+        L_next = bx + 8 < Bx ? lv[bx + 8] : 0;
+        tma::mbar_wait(bar + 8u * slot, (uint32_t)(grp / kStages) & 1u);
+        const uint8_t* in = s_in + slot * kTile;
+        uint8_t* out = s_out + (grp & 1) * kTile;
+        if (bx < Bx) {                                                // warp-uniform
+            const uint2 y = *reinterpret_cast<const uint2*>(in + y_off);
+            uint32_t c0 = *reinterpret_cast<const uint32_t*>(in + c_off);
+            L = L < 0 ? 0 : (L > max_level ? max_level : L);
+            uint32_t p0 = y.x, p1 = y.y, c1 = 0u;
+            if (L > 0) {
+                down_up_pow2_level<16>(p0, p1, L > 4 ? 4 : L, lane, 0);
+                down_up_pow2_level<8>(c0, c1, L > 3 ? 3 : L, gl, lane & 16);
+            }
+            *reinterpret_cast<uint2*>(out + y_off) = make_uint2(p0, p1);
+            *reinterpret_cast<uint32_t*>(out + c_off) = c0;
+        }
+        tma::fence_proxy_async();                                     // my tile writes, before the TMA store reads them
+        if (tid == 0) tma::store_wait_read<0>();                      // the store of tile grp - 1 has left s_out[(grp + 1) & 1]
+        __syncthreads();                                              // out tile complete; in slot read by everyone; other out tile free
+        if (tid == 0) {
+            const uint32_t src = out_base + (uint32_t)(grp & 1) * kTile;
+            tma::store_3d(&m.out[0], grp * 128, by * 16, t, src);
+            tma::store_3d(&m.out[1], grp * 64, by * 8, t, src + kOffU);
+            tma::store_3d(&m.out[2], grp * 64, by * 8, t, src + kOffV);
+            tma::store_commit();
+            if (grp + kStages < n_groups) issue_load(grp + kStages);
+        }
+    }
+    if (tid == 0) tma::store_wait<0>();                               // shared memory must outlive the last store's reads
+}
+
 // ----------------------------------------------------------------------------- dampen
 // one thread per (8x8 tile, channel): forward AAN, per-coefficient gain, inverse AAN
 template <bool FAST>   // FAST: single channel, 8-byte aligned rows -> 64-bit loads/stores
@@ -1433,7 +1515,25 @@ extern "C" int elvis_degrade_downsample_pow2_yuv420(const elvis_plane* src_yuv, 
     g.By = by;
     g.Bx = bx;
     if ((int64_t)n_frames * by > 0x7fffffffLL) return ELVIS_ERR_UNSUPPORTED;
-    downsample_pow2_yuv420_kernel<<<(unsigned)((int64_t)n_frames * by), 256, 0, as_stream(stream)>>>(g, levels, max_level);
+    const unsigned grid = (unsigned)((int64_t)n_frames * by);
+    // TMA version when every plane can be described by a tensor map (ELVIS_DOWNSAMPLE_TMA=0: the cp.async movers)
+    const char* use_tma = getenv("ELVIS_DOWNSAMPLE_TMA");
+    if (!(use_tma && use_tma[0] == '0')) {
+        DownMaps m;
+        bool ok = true;
+        for (int i = 0; i < 3 && ok; ++i) {
+            const int pb = i == 0 ? 16 : 8, box_w = i == 0 ? 128 : 64;
+            const CUtensorMapSwizzle sw = i == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+            ok = tma::make_plane_map(&m.in[i], g.src[i], bx * pb, by * pb, n_frames, g.src_row[i], g.src_frame[i], box_w, pb, sw) &&
+                 tma::make_plane_map(&m.out[i], g.dst[i], bx * pb, by * pb, n_frames, g.dst_row[i], g.dst_frame[i], box_w, pb, sw);
+        }
+        if (ok) {
+            downsample_pow2_yuv420_tma_kernel<<<grid, 256, 0, as_stream(stream)>>>(m, by, bx, levels, max_level);
+            ELVIS_CHECK_LAUNCH();
+            return ELVIS_OK;
+        }
+    }
+    downsample_pow2_yuv420_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, levels, max_level);
     ELVIS_CHECK_LAUNCH();
     return ELVIS_OK;
 }

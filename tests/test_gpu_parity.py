@@ -465,6 +465,34 @@ def test_presley_degrade_video(dev):
     assert np.array_equal(Pr.blur_block(blk, 2), P.presley_degrade_frame(blk, np.array([[2]]), 16, "blur"))
 
 
+@pytest.mark.parametrize("movers", ["tma", "cp.async"])
+@pytest.mark.parametrize("W", [48, 96, 128, 272, 400])       # 3 / 6 / 8 / 17 / 25 blocks per row: partial tiles, several tiles, odd chroma pitch
+def test_fused_downsample_movers(dev, monkeypatch, movers, W):
+    """The fused Y+U+V power-of-two downsample through both tile movers (TMA boxes with swizzle; cp.async pieces),
+    levels 0..4, on contiguous planes and on planes that are windows of wider buffers."""
+    import torch
+    from elvis_b200.pipeline import PresleyV2, Yuv420
+    monkeypatch.setenv("ELVIS_DOWNSAMPLE_TMA", "1" if movers == "tma" else "0")
+    T, H, bs = 2, 48, 16
+    y, u, v = synth_yuv420(T, H, W, seed=W)
+    rng = np.random.default_rng(W)
+    y[1] = rng.integers(0, 256, y[1].shape, dtype=np.uint8)
+    levels = rng.integers(0, 5, (T, H // bs, W // bs)).astype(np.int32)
+    v2 = PresleyV2(bs)
+
+    def windowed(a, pad):                    # the same pixels as a window of a wider, taller buffer (row pitch > width)
+        big = torch.full((a.shape[0], a.shape[1] + 2, a.shape[2] + pad), 7, dtype=torch.uint8, device=dev)
+        big[:, 1:-1, 16:16 + a.shape[2]] = to_dev(a, dev)
+        return big[:, 1:-1, 16:16 + a.shape[2]]
+
+    for clip in (Yuv420(to_dev(y, dev), to_dev(u, dev), to_dev(v, dev)), Yuv420(windowed(y, 48), windowed(u, 32), windowed(v, 32))):
+        d = v2.downsample_pow2(clip, to_dev(levels, dev), 4)
+        for name, plane, pb, cap in (("y", y, bs, 4), ("u", u, bs // 2, 3), ("v", v, bs // 2, 3)):
+            for t in range(T):
+                small = np.maximum(1, pb >> np.minimum(levels[t], cap))
+                assert np.array_equal(getattr(d, name)[t].cpu().numpy(), P.downsample_plane(plane[t], small, pb)), (name, t)
+
+
 def test_planar_degrade(dev):
     from elvis_b200 import ops
     from elvis_b200.pipeline import PresleyV2, Yuv420
