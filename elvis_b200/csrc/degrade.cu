@@ -279,6 +279,124 @@ __device__ __forceinline__ uint32_t blur_operator_entry(int PB, int m, int c) {
 // tile-row owned by accumulator-layout row i (the same map orders the columns: 4 q + j <-> layout 2 q + j, 8 + 2 q + j - 2)
 __device__ __forceinline__ int imma_tile_row(int i) { return 4 * ((i & 7) >> 1) + (i & 1) + (i >= 8 ? 2 : 0); }
 
+// `nr` blur rounds (per thread: the rounds of the block its 8 pixels belong to) on the warp's tile, held as the words
+// w0 / w1 of the thread's two rows; every lane of the warp must call it (the IMMAs are warp-wide).
+__device__ __forceinline__ void blur_imma_rounds(uint32_t& w0, uint32_t& w1, const uint32_t a0, const uint32_t a1, const int nr) {
+    const int zero4[4] = {0, 0, 0, 0}, half4[4] = {128, 128, 128, 128};
+    int max_r = nr;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) max_r = max(max_r, __shfl_xor_sync(0xffffffffu, max_r, m));
+    for (int k = 0; k < max_r; ++k) {
+        int m1a[4], m1b[4];                               // M1 = G X^T: n-tile 0 (from my first row) and 1 (second row)
+        imma_16816(m1a, a0, a1, w0, zero4);
+        imma_16816(m1b, a0, a1, w1, zero4);
+        uint32_t z[2];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {            // layout rows g / g + 8 of M1 feed n-tile `half` of step 2
+            const uint32_t q0 = (uint32_t)m1a[2 * half], q1 = (uint32_t)m1a[2 * half + 1];
+            const uint32_t q2 = (uint32_t)m1b[2 * half], q3 = (uint32_t)m1b[2 * half + 1];
+            const uint32_t hi = __byte_perm(__byte_perm(q0, q1, 0x0051), __byte_perm(q2, q3, 0x0051), 0x5410);
+            const uint32_t lo = __byte_perm(__byte_perm(q0, q1, 0x0040), __byte_perm(q2, q3, 0x0040), 0x5410);
+            int acc[4], acl[4];                            // two independent products: shorter dependent chain per round
+            imma_16816(acc, a0, a1, hi, half4);
+            imma_16816(acl, a0, a1, lo, zero4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = acc[i] * 256 + acl[i];
+            // my first row's word comes from acc[0..1] of both halves, my second row's from acc[2..3]: keep all four
+            z[half] = __byte_perm(__byte_perm((uint32_t)acc[0], (uint32_t)acc[1], 0x0062), __byte_perm((uint32_t)acc[2], (uint32_t)acc[3], 0x0062), 0x5410);
+        }
+        // z[half] = (row g: cols 2q,2q+1 of n-tile half | row g+8: the same) -> words of my two rows
+        const uint32_t n0 = __byte_perm(z[0], z[1], 0x5410), n1 = __byte_perm(z[0], z[1], 0x7632);
+        if (k < nr) {
+            w0 = n0;
+            w1 = n1;
+        }
+    }
+}
+
+// The same tile arithmetic with TMA doing the moving (default when the plane can be described by a tensor map).  Every
+// warp runs its own pipeline -- no CTA-wide barrier, because the tiles of a CTA need anything from 0 to 10 rounds: a
+// ring of four 16 x 16-byte boxes in flight per warp (one mbarrier each, lane 0 issues), the tile's words read from
+// and written to shared memory, and a box store per finished tile (two output slots, reused once the bulk group
+// that read them has drained).  The direct version above loads each tile when it is needed -- 16 rows of 16 bytes,
+// sixteen 128-byte lines per instruction -- and so exposes the full memory latency once per tile, which is what bounds
+// the few-rounds case (presley: 0..4 rounds, ~400 cycles per tile and scheduler for ~270 of work).
+template <int PB>
+__global__ void __launch_bounds__(256) blur_imma_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+                                                            const int T, const int By, const int Bx, const int32_t* __restrict__ rounds) {
+    constexpr int kWarps = 8, kStages = 4;
+    constexpr int kPerTile = 16 / PB;
+    constexpr uint32_t kTile = 256;
+    __shared__ __align__(128) uint8_t s_in[kWarps][kStages][kTile];
+    __shared__ __align__(128) uint8_t s_out[kWarps][2][kTile];
+    __shared__ __align__(8) uint64_t s_full[kWarps][kStages];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int r0 = imma_tile_row(gq), r1 = imma_tile_row(gq + 8), c0 = 4 * tq;
+    uint32_t a0 = 0u, a1 = 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        a0 |= blur_operator_entry(PB, r0, c0 + i) << (8 * i);
+        a1 |= blur_operator_entry(PB, r1, c0 + i) << (8 * i);
+    }
+    const int tiles_x = (Bx + kPerTile - 1) / kPerTile, tiles_y = (By + kPerTile - 1) / kPerTile;
+    const int64_t n_tiles = (int64_t)T * tiles_y * tiles_x;
+    const int64_t stride = (int64_t)gridDim.x * kWarps, first = (int64_t)blockIdx.x * kWarps + w;
+    const uint32_t in_base = tma::smem_u32(&s_in[w][0][0]), out_base = tma::smem_u32(&s_out[w][0][0]), bar = tma::smem_u32(&s_full[w][0]);
+    const uint32_t off0 = (uint32_t)(r0 * 16 + c0), off1 = (uint32_t)(r1 * 16 + c0);
+
+    auto issue = [&](int64_t tile, int slot) {                       // lane 0 only
+        const int tx = (int)(tile % tiles_x);
+        const int64_t q = tile / tiles_x;
+        tma::mbar_arrive_expect_tx(bar + 8u * slot, kTile);
+        tma::load_3d(in_base + (uint32_t)slot * kTile, &tm_in, tx * 16, (int)(q % tiles_y) * 16, (int)(q / tiles_y), bar + 8u * slot);
+    };
+    // rounds of the block my 8 pixels belong to (they lie in ONE block of the tile: rows r0, r1 share a half, columns 4q..4q+3 too)
+    auto rounds_of = [&](int64_t tile) -> int {
+        if (tile >= n_tiles) return 0;
+        const int tx = (int)(tile % tiles_x);
+        const int64_t q = tile / tiles_x;
+        const int ty = (int)(q % tiles_y), t = (int)(q / tiles_y);
+        const int byq = ty * kPerTile + (PB == 8 ? (gq >= 4) : 0), bxq = tx * kPerTile + (PB == 8 ? (tq >= 2) : 0);
+        return byq < By && bxq < Bx ? rounds[((int64_t)t * By + byq) * Bx + bxq] : 0;
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int sgi = 0; sgi < kStages; ++sgi) tma::mbar_init(bar + 8u * sgi, 1);
+        tma::mbar_init_fence();
+#pragma unroll
+        for (int sgi = 0; sgi < kStages; ++sgi)
+            if (first + sgi * stride < n_tiles) issue(first + sgi * stride, sgi);
+    }
+    __syncwarp();
+    int nr_next = rounds_of(first);
+    int it = 0;
+    for (int64_t tile = first; tile < n_tiles; tile += stride, ++it) {
+        const int slot = it % kStages;
+        const int nr = nr_next;
+        nr_next = rounds_of(tile + stride);
+        tma::mbar_wait(bar + 8u * slot, (uint32_t)(it / kStages) & 1u);
+        uint32_t w0 = *reinterpret_cast<const uint32_t*>(&s_in[w][slot][off0]);
+        uint32_t w1 = *reinterpret_cast<const uint32_t*>(&s_in[w][slot][off1]);
+        blur_imma_rounds(w0, w1, a0, a1, nr);
+        if (lane == 0) tma::store_wait_read<1>();                    // the box store that read this output slot two tiles ago is done
+        __syncwarp();
+        uint8_t* o = &s_out[w][it & 1][0];
+        *reinterpret_cast<uint32_t*>(o + off0) = w0;
+        *reinterpret_cast<uint32_t*>(o + off1) = w1;
+        tma::fence_proxy_async();
+        __syncwarp();                                                // the tile is complete; everyone has consumed the input slot
+        if (lane == 0) {
+            const int tx = (int)(tile % tiles_x);
+            const int64_t q = tile / tiles_x;
+            tma::store_3d(&tm_out, tx * 16, (int)(q % tiles_y) * 16, (int)(q / tiles_y), out_base + (uint32_t)(it & 1) * kTile);
+            tma::store_commit();
+            if (tile + kStages * stride < n_tiles) issue(tile + kStages * stride, slot);
+        }
+    }
+    if (lane == 0) tma::store_wait<0>();                             // shared memory must outlive the last stores' reads
+}
+
 template <int PB, bool ALIGNED>
 __global__ void __launch_bounds__(256) blur_imma_kernel(const BlockGeom g, const int32_t* __restrict__ rounds) {
     constexpr int kWarps = 8;
@@ -295,7 +413,6 @@ __global__ void __launch_bounds__(256) blur_imma_kernel(const BlockGeom g, const
     const int tiles_x = (g.Bx + kPerTile - 1) / kPerTile, tiles_y = (g.By + kPerTile - 1) / kPerTile;
     const int64_t n_tiles = (int64_t)g.T * tiles_y * tiles_x;
     const int64_t stride = (int64_t)gridDim.x * kWarps;
-    const int zero4[4] = {0, 0, 0, 0}, half4[4] = {128, 128, 128, 128};
     for (int64_t tile = (int64_t)blockIdx.x * kWarps + w; tile < n_tiles; tile += stride) {
         const int tx = (int)(tile % tiles_x);
         const int64_t q = tile / tiles_x;
@@ -322,35 +439,7 @@ __global__ void __launch_bounds__(256) blur_imma_kernel(const BlockGeom g, const
                 w1 = p1[0] | (p1[1] << 8) | (p1[2] << 16) | ((uint32_t)p1[3] << 24);
             }
         }
-        int max_r = nr;
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) max_r = max(max_r, __shfl_xor_sync(0xffffffffu, max_r, m));
-        for (int k = 0; k < max_r; ++k) {
-            int m1a[4], m1b[4];                               // M1 = G X^T: n-tile 0 (from my first row) and 1 (second row)
-            imma_16816(m1a, a0, a1, w0, zero4);
-            imma_16816(m1b, a0, a1, w1, zero4);
-            uint32_t z[2];
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {            // layout rows g / g + 8 of M1 feed n-tile `half` of step 2
-                const uint32_t q0 = (uint32_t)m1a[2 * half], q1 = (uint32_t)m1a[2 * half + 1];
-                const uint32_t q2 = (uint32_t)m1b[2 * half], q3 = (uint32_t)m1b[2 * half + 1];
-                const uint32_t hi = __byte_perm(__byte_perm(q0, q1, 0x0051), __byte_perm(q2, q3, 0x0051), 0x5410);
-                const uint32_t lo = __byte_perm(__byte_perm(q0, q1, 0x0040), __byte_perm(q2, q3, 0x0040), 0x5410);
-                int acc[4], acl[4];                            // two independent products: shorter dependent chain per round
-                imma_16816(acc, a0, a1, hi, half4);
-                imma_16816(acl, a0, a1, lo, zero4);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i] = acc[i] * 256 + acl[i];
-                // my first row's word comes from acc[0..1] of both halves, my second row's from acc[2..3]: keep all four
-                z[half] = __byte_perm(__byte_perm((uint32_t)acc[0], (uint32_t)acc[1], 0x0062), __byte_perm((uint32_t)acc[2], (uint32_t)acc[3], 0x0062), 0x5410);
-            }
-            // z[half] = (row g: cols 2q,2q+1 of n-tile half | row g+8: the same) -> words of my two rows
-            const uint32_t n0 = __byte_perm(z[0], z[1], 0x5410), n1 = __byte_perm(z[0], z[1], 0x7632);
-            if (k < nr) {
-                w0 = n0;
-                w1 = n1;
-            }
-        }
+        blur_imma_rounds(w0, w1, a0, a1, nr);
         if (live) {
             uint8_t *p0 = dp + (int64_t)r0 * g.dst_row, *p1 = dp + (int64_t)r1 * g.dst_row;
             if (ALIGNED) {
@@ -1343,6 +1432,16 @@ extern "C" int elvis_degrade_blur(const elvis_plane* src, const elvis_plane* dst
         const int per = 16 / block_px;
         const int64_t tiles = (int64_t)n_frames * ((by + per - 1) / per) * ((bx + per - 1) / per);
         const int grid = grid_for_units(tiles, 8);
+        const char* use_tma = getenv("ELVIS_BLUR_TMA");            // 0: direct loads and stores
+        CUtensorMap tm_in, tm_out;
+        if (!(use_tma && use_tma[0] == '0') &&
+            tma::make_plane_map(&tm_in, g.src, bx * block_px, by * block_px, n_frames, g.src_row, g.src_frame, 16, 16, CU_TENSOR_MAP_SWIZZLE_NONE) &&
+            tma::make_plane_map(&tm_out, g.dst, bx * block_px, by * block_px, n_frames, g.dst_row, g.dst_frame, 16, 16, CU_TENSOR_MAP_SWIZZLE_NONE)) {
+            if (block_px == 16) blur_imma_tma_kernel<16><<<grid, 256, 0, st>>>(tm_in, tm_out, n_frames, by, bx, rounds);
+            else blur_imma_tma_kernel<8><<<grid, 256, 0, st>>>(tm_in, tm_out, n_frames, by, bx, rounds);
+            ELVIS_CHECK_LAUNCH();
+            return ELVIS_OK;
+        }
         if (block_px == 16) {
             if (al4) blur_imma_kernel<16, true><<<grid, 256, 0, st>>>(g, rounds);
             else blur_imma_kernel<16, false><<<grid, 256, 0, st>>>(g, rounds);

@@ -493,6 +493,32 @@ def test_fused_downsample_movers(dev, monkeypatch, movers, W):
                 assert np.array_equal(getattr(d, name)[t].cpu().numpy(), P.downsample_plane(plane[t], small, pb)), (name, t)
 
 
+@pytest.mark.parametrize("movers", ["tma", "direct"])
+@pytest.mark.parametrize("pb,by,bx", [(16, 3, 6), (16, 1, 17), (8, 5, 7), (8, 2, 16), (8, 1, 1)])
+def test_blur_tensor_core_movers(dev, monkeypatch, movers, pb, by, bx):
+    """The tensor-core blur with TMA boxes (per-warp pipeline) and with direct loads / stores: rounds 0..10, odd block
+    counts (half-empty chroma tiles), contiguous planes and windows of wider buffers."""
+    import torch
+    from elvis_b200 import ops
+    monkeypatch.setenv("ELVIS_BLUR_TMA", "1" if movers == "tma" else "0")
+    T, H, W = 3, by * pb, bx * pb
+    rng = np.random.default_rng(pb * 1000 + by * 31 + bx)
+    plane = rng.integers(0, 256, (T, H, W), dtype=np.uint8)
+    plane[0] = synth_luma(1, H, W, seed=bx)[0]
+    rounds = rng.integers(0, 11, (T, by, bx)).astype(np.int32)
+    rounds[0, 0, 0] = 0
+    want = np.stack([P.blur_plane(plane[t], rounds[t], pb) for t in range(T)])
+    got = ops.degrade_blur(to_dev(plane, dev), to_dev(rounds, dev), pb)
+    assert np.array_equal(got.cpu().numpy(), want)
+    big = torch.full((T, H + 3, (W + 48 + 15) // 16 * 16), 9, dtype=torch.uint8, device=dev)   # row pitch a multiple of 16: TMA-capable even for odd W
+    big[:, 2:2 + H, 32:32 + W] = to_dev(plane, dev)
+    out = torch.zeros_like(big)
+    ops.degrade_blur(big[:, 2:2 + H, 32:32 + W], to_dev(rounds, dev), pb, out=out[:, 2:2 + H, 32:32 + W])
+    assert np.array_equal(out[:, 2:2 + H, 32:32 + W].cpu().numpy(), want)
+    out[:, 2:2 + H, 32:32 + W] = 0
+    assert int(out.count_nonzero()) == 0                                          # nothing written outside the window
+
+
 def test_planar_degrade(dev):
     from elvis_b200 import ops
     from elvis_b200.pipeline import PresleyV2, Yuv420
