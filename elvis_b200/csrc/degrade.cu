@@ -315,21 +315,23 @@ __device__ __forceinline__ void blur_imma_rounds(uint32_t& w0, uint32_t& w1, con
 }
 
 // The same tile arithmetic with TMA doing the moving (default when the plane can be described by a tensor map).  Every
-// warp runs its own pipeline -- no CTA-wide barrier, because the tiles of a CTA need anything from 0 to 10 rounds: a
-// ring of four 16 x 16-byte boxes in flight per warp (one mbarrier each, lane 0 issues), the tile's words read from
-// and written to shared memory, and a box store per finished tile (two output slots, reused once the bulk group
-// that read them has drained).  The direct version above loads each tile when it is needed -- 16 rows of 16 bytes,
-// sixteen 128-byte lines per instruction -- and so exposes the full memory latency once per tile, which is what bounds
-// the few-rounds case (presley: 0..4 rounds, ~400 cycles per tile and scheduler for ~270 of work).
+// WARP runs its own pipeline -- no CTA-wide barrier, because the tiles of a CTA need anything from 0 to 10 rounds.  A warp
+// takes strips of eight horizontally adjacent tiles: one 16-row x 128-byte box (128-byte swizzle) loaded onto an mbarrier,
+// the eight tiles blurred in place (words read from and written back to shared memory), one box store; three strip
+// buffers per warp, so the strip after next is already in flight while a strip is being worked on.  The direct
+// version below loads each tile when it is needed -- 16 rows of 16 bytes, sixteen 128-byte lines per instruction -- and so
+// exposes the memory latency once per tile, which is what bounds the few-rounds case (presley: 0..4 rounds, ~400 cycles
+// per tile and scheduler for ~270 of work).  (Boxes of a single tile, 16 x 16 bytes, were measured slower than the direct
+// loads: the TMA unit's cost is per box row, not per byte.)
 template <int PB>
-__global__ void __launch_bounds__(256) blur_imma_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+__global__ void __launch_bounds__(128) blur_imma_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                                                             const int T, const int By, const int Bx, const int32_t* __restrict__ rounds) {
-    constexpr int kWarps = 8, kStages = 4;
+    constexpr int kWarps = 4, kBufs = 3;
     constexpr int kPerTile = 16 / PB;
-    constexpr uint32_t kTile = 256;
-    __shared__ __align__(128) uint8_t s_in[kWarps][kStages][kTile];
-    __shared__ __align__(128) uint8_t s_out[kWarps][2][kTile];
-    __shared__ __align__(8) uint64_t s_full[kWarps][kStages];
+    constexpr uint32_t kStrip = 2048;
+    __shared__ __align__(1024) uint8_t s_buf[kWarps][kBufs][kStrip];
+    __shared__ __align__(8) uint64_t s_full[kWarps][kBufs];
+    __shared__ int32_t s_nr[kWarps][8][32];                              // rounds per tile of the current strip, one column per lane
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int gq = lane >> 2, tq = lane & 3;
     const int r0 = imma_tile_row(gq), r1 = imma_tile_row(gq + 8), c0 = 4 * tq;
@@ -340,61 +342,82 @@ __global__ void __launch_bounds__(256) blur_imma_tma_kernel(const __grid_constan
         a1 |= blur_operator_entry(PB, r1, c0 + i) << (8 * i);
     }
     const int tiles_x = (Bx + kPerTile - 1) / kPerTile, tiles_y = (By + kPerTile - 1) / kPerTile;
-    const int64_t n_tiles = (int64_t)T * tiles_y * tiles_x;
+    const int strips_x = (tiles_x + 7) / 8;
+    const int64_t n_strips = (int64_t)T * tiles_y * strips_x;
     const int64_t stride = (int64_t)gridDim.x * kWarps, first = (int64_t)blockIdx.x * kWarps + w;
-    const uint32_t in_base = tma::smem_u32(&s_in[w][0][0]), out_base = tma::smem_u32(&s_out[w][0][0]), bar = tma::smem_u32(&s_full[w][0]);
-    const uint32_t off0 = (uint32_t)(r0 * 16 + c0), off1 = (uint32_t)(r1 * 16 + c0);
+    const uint32_t buf_base = tma::smem_u32(&s_buf[w][0][0]), bar = tma::smem_u32(&s_full[w][0]);
+    const uint32_t row0 = (uint32_t)(r0 * 128 + c0), row1 = (uint32_t)(r1 * 128 + c0);
+    const int x0 = r0 & 7, x1 = r1 & 7;                                  // swizzle: 16-byte chunk j of row r sits at chunk j ^ (r & 7)
 
-    auto issue = [&](int64_t tile, int slot) {                       // lane 0 only
-        const int tx = (int)(tile % tiles_x);
-        const int64_t q = tile / tiles_x;
-        tma::mbar_arrive_expect_tx(bar + 8u * slot, kTile);
-        tma::load_3d(in_base + (uint32_t)slot * kTile, &tm_in, tx * 16, (int)(q % tiles_y) * 16, (int)(q / tiles_y), bar + 8u * slot);
+    struct Strip { int sx, ty, t; };
+    auto strip_of = [&](int64_t s) {
+        const int64_t q = s / strips_x;
+        return Strip{(int)(s - q * strips_x), (int)(q % tiles_y), (int)(q / tiles_y)};
     };
-    // rounds of the block my 8 pixels belong to (they lie in ONE block of the tile: rows r0, r1 share a half, columns 4q..4q+3 too)
-    auto rounds_of = [&](int64_t tile) -> int {
-        if (tile >= n_tiles) return 0;
-        const int tx = (int)(tile % tiles_x);
-        const int64_t q = tile / tiles_x;
-        const int ty = (int)(q % tiles_y), t = (int)(q / tiles_y);
-        const int byq = ty * kPerTile + (PB == 8 ? (gq >= 4) : 0), bxq = tx * kPerTile + (PB == 8 ? (tq >= 2) : 0);
-        return byq < By && bxq < Bx ? rounds[((int64_t)t * By + byq) * Bx + bxq] : 0;
+    auto issue = [&](int64_t s, int b) {                                 // lane 0 only
+        const Strip p = strip_of(s);
+        tma::mbar_arrive_expect_tx(bar + 8u * b, kStrip);
+        tma::load_3d(buf_base + (uint32_t)b * kStrip, &tm_in, p.sx * 128, p.ty * 16, p.t, bar + 8u * b);
+    };
+    // rounds of the blocks my 8 pixels belong to in the eight tiles of a strip (in every tile they lie in ONE block:
+    // rows r0, r1 share a half, columns 4q..4q+3 too)
+    auto load_rounds = [&](int64_t s, int (&nr)[8]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nr[j] = 0;
+        if (s >= n_strips) return;
+        const Strip p = strip_of(s);
+        const int byq = p.ty * kPerTile + (PB == 8 ? (gq >= 4) : 0);
+        if (byq >= By) return;
+        const int32_t* row = rounds + ((int64_t)p.t * By + byq) * Bx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int bxq = (p.sx * 8 + j) * kPerTile + (PB == 8 ? (tq >= 2) : 0);
+            if (bxq < Bx) nr[j] = row[bxq];
+        }
     };
     if (lane == 0) {
 #pragma unroll
-        for (int sgi = 0; sgi < kStages; ++sgi) tma::mbar_init(bar + 8u * sgi, 1);
+        for (int b = 0; b < kBufs; ++b) tma::mbar_init(bar + 8u * b, 1);
         tma::mbar_init_fence();
-#pragma unroll
-        for (int sgi = 0; sgi < kStages; ++sgi)
-            if (first + sgi * stride < n_tiles) issue(first + sgi * stride, sgi);
+        if (first < n_strips) issue(first, 0);
+        if (first + stride < n_strips) issue(first + stride, 1);
     }
     __syncwarp();
-    int nr_next = rounds_of(first);
+    int nr_next[8];
+    load_rounds(first, nr_next);
     int it = 0;
-    for (int64_t tile = first; tile < n_tiles; tile += stride, ++it) {
-        const int slot = it % kStages;
-        const int nr = nr_next;
-        nr_next = rounds_of(tile + stride);
-        tma::mbar_wait(bar + 8u * slot, (uint32_t)(it / kStages) & 1u);
-        uint32_t w0 = *reinterpret_cast<const uint32_t*>(&s_in[w][slot][off0]);
-        uint32_t w1 = *reinterpret_cast<const uint32_t*>(&s_in[w][slot][off1]);
-        blur_imma_rounds(w0, w1, a0, a1, nr);
-        if (lane == 0) tma::store_wait_read<1>();                    // the box store that read this output slot two tiles ago is done
+    for (int64_t s = first; s < n_strips; s += stride, ++it) {
+        const int b = it % kBufs;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_nr[w][j][lane] = nr_next[j];       // read back by this lane only
+        load_rounds(s + stride, nr_next);                                // in flight while this strip is worked on
+        tma::mbar_wait(bar + 8u * b, (uint32_t)(it / kBufs) & 1u);
+        uint8_t* buf = &s_buf[w][b][0];
+        const int n_here = min(8, tiles_x - strip_of(s).sx * 8);         // tiles of this strip inside the plane (warp-uniform)
+#pragma unroll 1
+        for (int j = 0; j < n_here; ++j) {
+            uint32_t* p0 = reinterpret_cast<uint32_t*>(buf + row0 + ((j ^ x0) << 4));
+            uint32_t* p1 = reinterpret_cast<uint32_t*>(buf + row1 + ((j ^ x1) << 4));
+            uint32_t w0 = *p0, w1 = *p1;
+            blur_imma_rounds(w0, w1, a0, a1, s_nr[w][j][lane]);
+            *p0 = w0;
+            *p1 = w1;
+        }
+        tma::fence_proxy_async();                                        // my in-place writes, before the box store reads them
         __syncwarp();
-        uint8_t* o = &s_out[w][it & 1][0];
-        *reinterpret_cast<uint32_t*>(o + off0) = w0;
-        *reinterpret_cast<uint32_t*>(o + off1) = w1;
-        tma::fence_proxy_async();
-        __syncwarp();                                                // the tile is complete; everyone has consumed the input slot
         if (lane == 0) {
-            const int tx = (int)(tile % tiles_x);
-            const int64_t q = tile / tiles_x;
-            tma::store_3d(&tm_out, tx * 16, (int)(q % tiles_y) * 16, (int)(q / tiles_y), out_base + (uint32_t)(it & 1) * kTile);
+            const Strip p = strip_of(s);
+            tma::store_3d(&tm_out, p.sx * 128, p.ty * 16, p.t, buf_base + (uint32_t)b * kStrip);
             tma::store_commit();
-            if (tile + kStages * stride < n_tiles) issue(tile + kStages * stride, slot);
+            // buffer (it + 2) % 3 == (it - 1) % 3 was stored from at the end of the previous strip: once that store has
+            // read it, it takes the strip after next
+            if (s + 2 * stride < n_strips) {
+                tma::store_wait_read<1>();
+                issue(s + 2 * stride, (it + 2) % kBufs);
+            }
         }
     }
-    if (lane == 0) tma::store_wait<0>();                             // shared memory must outlive the last stores' reads
+    if (lane == 0) tma::store_wait<0>();                                 // shared memory must outlive the last stores' reads
 }
 
 template <int PB, bool ALIGNED>
@@ -1435,10 +1458,13 @@ extern "C" int elvis_degrade_blur(const elvis_plane* src, const elvis_plane* dst
         const char* use_tma = getenv("ELVIS_BLUR_TMA");            // 0: direct loads and stores
         CUtensorMap tm_in, tm_out;
         if (!(use_tma && use_tma[0] == '0') &&
-            tma::make_plane_map(&tm_in, g.src, bx * block_px, by * block_px, n_frames, g.src_row, g.src_frame, 16, 16, CU_TENSOR_MAP_SWIZZLE_NONE) &&
-            tma::make_plane_map(&tm_out, g.dst, bx * block_px, by * block_px, n_frames, g.dst_row, g.dst_frame, 16, 16, CU_TENSOR_MAP_SWIZZLE_NONE)) {
-            if (block_px == 16) blur_imma_tma_kernel<16><<<grid, 256, 0, st>>>(tm_in, tm_out, n_frames, by, bx, rounds);
-            else blur_imma_tma_kernel<8><<<grid, 256, 0, st>>>(tm_in, tm_out, n_frames, by, bx, rounds);
+            tma::make_plane_map(&tm_in, g.src, bx * block_px, by * block_px, n_frames, g.src_row, g.src_frame, 128, 16, CU_TENSOR_MAP_SWIZZLE_128B) &&
+            tma::make_plane_map(&tm_out, g.dst, bx * block_px, by * block_px, n_frames, g.dst_row, g.dst_frame, 128, 16, CU_TENSOR_MAP_SWIZZLE_128B)) {
+            const int tiles_x = (bx + per - 1) / per;
+            const int64_t strips = (int64_t)n_frames * ((by + per - 1) / per) * ((tiles_x + 7) / 8);
+            const int sgrid = grid_for_units(strips, 4);           // 4 warps per CTA, up to 16 CTAs per SM's worth of strips
+            if (block_px == 16) blur_imma_tma_kernel<16><<<sgrid, 128, 0, st>>>(tm_in, tm_out, n_frames, by, bx, rounds);
+            else blur_imma_tma_kernel<8><<<sgrid, 128, 0, st>>>(tm_in, tm_out, n_frames, by, bx, rounds);
             ELVIS_CHECK_LAUNCH();
             return ELVIS_OK;
         }
