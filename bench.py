@@ -657,12 +657,12 @@ def measure_v2(ctx, workload, steps, warmup, with_e2e, with_cpu, with_parity):
     elif kind == "downsample":
         lv = ops.levels_from_scores(scores[0], ops.LEVELS_ROUND, 4)
         fn, name, key = (lambda: v2.downsample_pow2(clips[0], lv, 3, outs[0])), \
-            "downsample_pow2_yuv420_kernel (elvis_degrade_downsample_pow2_yuv420, Y+U+V in one launch)", "downsample_pow2_yuv420"
+            "downsample_pow2_yuv420_tma_kernel (elvis_degrade_downsample_pow2_yuv420, Y+U+V in one launch, TMA tiles)", "downsample_pow2_yuv420"
         k_bytes = 3 * W * H * T
     else:
         rounds = ops.levels_from_scores(scores[0], ops.LEVELS_ROUND, 10)
         fn, name, key = (lambda: ops.degrade_blur(clips[0].y, rounds, BLOCK, out=y_out)), \
-            "blur_imma_kernel<16> (elvis_degrade_blur, luma launch; mma.sync u8)", "blur_imma"
+            "blur_imma_tma_kernel<16> (elvis_degrade_blur, luma launch; mma.sync u8, TMA strips)", "blur_imma"
     k_ms = ctx.time_kernel(fn, max(3, min(steps, 20)))
     roof = roofline_dict(ctx, name, k_bytes, k_ms, T, key)
     alg = v2_bytes_per_frame(W, H, kind == "dampen") * T

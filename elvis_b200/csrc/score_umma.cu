@@ -475,13 +475,20 @@ template <int R, bool XBAR>
 int launch_umma(const ScoreParams& p, const CUtensorMap& tm_clip, const CUtensorMap& tm_halo, cudaStream_t st) {
     // no carve-out preference: a kernel that forces its own L1 / shared split cannot overlap with the
     // shrink / stretch kernels of the other stream (measured: pipelined step 1.32 instead of 1.07 ms)
+    // ELVIS_UMMA_SMEM_PAD (bytes, experiment): extra dynamic shared memory per CTA -- 50 000 leaves room for ONE scoring
+    // CTA per SM, so that half of the register file stays free for the kernels of the other streams
+    static const int pad = [] {
+        const char* e = getenv("ELVIS_UMMA_SMEM_PAD");
+        const int v = e ? atoi(e) : 0;
+        return v < 0 ? 0 : (v > 150000 ? 150000 : v);
+    }();
     static PerDeviceOnce configured;   // the attribute is per (kernel, device)
     const cudaError_t e = configured.run([] {
-        return cudaFuncSetAttribute(score_umma_kernel<R, XBAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem);
+        return cudaFuncSetAttribute(score_umma_kernel<R, XBAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem + pad);
     });
     if (e != cudaSuccess) return cuda_fail(e);
     const int ctas_per_chunk = (p.By * p.tiles_x + kUnitsPerCta - 1) / kUnitsPerCta;
-    score_umma_kernel<R, XBAR><<<ctas_per_chunk * p.n_chunks, kUmmaThreads, kUmmaSmem, st>>>(tm_clip, tm_halo, p);
+    score_umma_kernel<R, XBAR><<<ctas_per_chunk * p.n_chunks, kUmmaThreads, kUmmaSmem + pad, st>>>(tm_clip, tm_halo, p);
     ELVIS_CHECK_LAUNCH();
     return ELVIS_OK;
 }
