@@ -485,12 +485,21 @@ def test_fused_downsample_movers(dev, monkeypatch, movers, W):
         big[:, 1:-1, 16:16 + a.shape[2]] = to_dev(a, dev)
         return big[:, 1:-1, 16:16 + a.shape[2]]
 
-    for clip in (Yuv420(to_dev(y, dev), to_dev(u, dev), to_dev(v, dev)), Yuv420(windowed(y, 48), windowed(u, 32), windowed(v, 32))):
-        d = v2.downsample_pow2(clip, to_dev(levels, dev), 4)
+    def check(d):
         for name, plane, pb, cap in (("y", y, bs, 4), ("u", u, bs // 2, 3), ("v", v, bs // 2, 3)):
             for t in range(T):
                 small = np.maximum(1, pb >> np.minimum(levels[t], cap))
                 assert np.array_equal(getattr(d, name)[t].cpu().numpy(), P.downsample_plane(plane[t], small, pb)), (name, t)
+
+    check(v2.downsample_pow2(Yuv420(to_dev(y, dev), to_dev(u, dev), to_dev(v, dev)), to_dev(levels, dev), 4))
+    # source AND destination as windows of wider buffers: the result is right and nothing outside the windows is written
+    src = Yuv420(windowed(y, 48), windowed(u, 32), windowed(v, 32))
+    dst = Yuv420(windowed(np.zeros_like(y), 48), windowed(np.zeros_like(u), 32), windowed(np.zeros_like(v), 32))
+    check(v2.downsample_pow2(src, to_dev(levels, dev), 4, dst))
+    for plane in dst.planes:
+        big = plane._base if plane._base is not None else plane
+        plane.fill_(7)
+        assert bool((big == 7).all())
 
 
 @pytest.mark.parametrize("movers", ["tma", "direct"])
