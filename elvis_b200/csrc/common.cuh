@@ -100,14 +100,6 @@ template <int K> __device__ __forceinline__ float byte_as_biased_float(uint32_t 
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(magic), "n"(0x7540 + K));
     return __uint_as_float(r);
 }
-// float(2^15 + b) for byte K of w: the byte lands in mantissa bits 8..15 of the pattern 0x4700bb00 (`magic15` = 0x47000000
-// in a register).  Sums of up to 64 such values stay exact integers in fp32 (64 * 32768 + 64 * 255 < 2^24), so a block
-// transform can run on the biased pixels and drop the bias from its DC term afterwards -- no per-pixel subtraction.
-template <int K> __device__ __forceinline__ float byte_as_float_plus_32768(uint32_t w, uint32_t magic15) {
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(magic15), "n"(0x7504 + 16 * K));
-    return __uint_as_float(r);
-}
 
 // Correctly rounded fp64 division by a divisor that is the same for every element of a launch (the min-max spans
 // of elvis.py:864-867 and utils.py:686): a / d == __ddiv_rn(a, d) bit for bit, at 5 fused operations instead of the

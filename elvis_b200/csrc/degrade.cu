@@ -1114,24 +1114,21 @@ __global__ void __launch_bounds__(128) dampen_packed_kernel(const BlockGeom g, c
     const uint8_t* sp = g.src + (int64_t)t * g.src_frame + (int64_t)tyi * 8 * g.src_row + (int64_t)txi * 8;
     uint8_t* dp = g.dst + (int64_t)t * g.dst_frame + (int64_t)tyi * 8 * g.dst_row + (int64_t)txi * 8;
 
-    // Pixels enter as 32768 + b, one PRMT each and no subtraction: a constant offset reaches only the DC term of a
-    // transform (every other output is built from differences, in which it cancels exactly), all sums involved are
-    // integers below 2^24 and therefore exact, and the 64 * 32768 that arrives in the DC coefficient is removed there.
     float2 x[8][4];
+    const float2 bias = make_float2(-8388608.f, -8388608.f);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const uint2 v = __ldcs(reinterpret_cast<const uint2*>(sp + (int64_t)r * g.src_row));
-        x[r][0] = make_float2(byte_as_float_plus_32768<0>(v.x, magic), byte_as_float_plus_32768<1>(v.x, magic));
-        x[r][1] = make_float2(byte_as_float_plus_32768<2>(v.x, magic), byte_as_float_plus_32768<3>(v.x, magic));
-        x[r][2] = make_float2(byte_as_float_plus_32768<0>(v.y, magic), byte_as_float_plus_32768<1>(v.y, magic));
-        x[r][3] = make_float2(byte_as_float_plus_32768<2>(v.y, magic), byte_as_float_plus_32768<3>(v.y, magic));
+        x[r][0] = __fadd2_rn(make_float2(byte_as_biased_float<0>(v.x, magic), byte_as_biased_float<1>(v.x, magic)), bias);
+        x[r][1] = __fadd2_rn(make_float2(byte_as_biased_float<2>(v.x, magic), byte_as_biased_float<3>(v.x, magic)), bias);
+        x[r][2] = __fadd2_rn(make_float2(byte_as_biased_float<0>(v.y, magic), byte_as_biased_float<1>(v.y, magic)), bias);
+        x[r][3] = __fadd2_rn(make_float2(byte_as_biased_float<2>(v.y, magic), byte_as_biased_float<3>(v.y, magic)), bias);
     }
     // forward: along the rows (scalar), then down the columns (packed)
 #pragma unroll
     for (int r = 0; r < 8; ++r) ELVIS_FDCT8(x[r][0].x, x[r][0].y, x[r][1].x, x[r][1].y, x[r][2].x, x[r][2].y, x[r][3].x, x[r][3].y);
 #pragma unroll
     for (int j = 0; j < 4; ++j) ELVIS_FDCT8_X2(x[0][j], x[1][j], x[2][j], x[3][j], x[4][j], x[5][j], x[6][j], x[7][j]);
-    x[0][0].x -= 2097152.f;                                     // 64 * 32768
     // gain 2^(-4 s (u+v)/14) / 64: powers of q = 2^(-4 s / 14); the 1/64 undoes the AAN scaling
     float gk[15];
     const float q = exp2f(-4.0f * s / 14.0f);
@@ -1587,7 +1584,7 @@ extern "C" int elvis_dct_dampen(const elvis_plane* src, const elvis_plane* dst, 
         const int64_t pairs = total / 2;
         dampen_pair_kernel<<<(unsigned)((pairs + 127) / 128), 128, 0, st>>>(g, strength, 0x4B000000u);
     } else if (fast && !(dampen_impl && !strcmp(dampen_impl, "scalar")))      // packed-fp32 kernel (default); ELVIS_DAMPEN_IMPL=scalar: the round-1 kernel
-        dampen_packed_kernel<<<grid, 128, 0, st>>>(g, strength, 0x47000000u);
+        dampen_packed_kernel<<<grid, 128, 0, st>>>(g, strength, 0x4B000000u);
     else if (fast)
         dampen_kernel<true><<<grid, 128, 0, st>>>(g, strength);
     else
