@@ -313,15 +313,23 @@ class Ctx:
         return self.max_over_ranks(start.elapsed_time(stop)), clocks
 
     def time_kernel(self, fn, reps):
+        """Average duration of `reps` back-to-back launches of one kernel, timed ALONE (CUDA events on its stream)
+        after a short idle gap, so that it is a burst figure like the measured peak it is divided by -- not the tail of
+        the power-capped sustained region that ran just before.  The SM clock during the launches is kept in
+        self.kernel_clocks and reported beside the figure."""
         torch = self.torch
         torch.cuda.synchronize()
+        time.sleep(0.3)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         fn()
+        if self.sampler:
+            self.sampler.reset()
         a.record()
         for _ in range(reps):
             fn()
         b.record()
         torch.cuda.synchronize()
+        self.kernel_clocks = self.sampler.snapshot() if self.sampler else None
         return a.elapsed_time(b) / reps
 
 
@@ -333,7 +341,9 @@ def roofline_dict(ctx, kernel, alg_bytes, ms, frames, traffic_key):
         traffic = tr["bytes"] * frames / tr["frames"]
     return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak,
             "traffic": traffic, "traffic_source": tr["source"] if tr else None, "peak_source": ctx.peak_src,
-            "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": ms}
+            "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": ms,
+            "launch_timing": "kernel alone, back-to-back launches after a 0.3 s idle gap (burst conditions, like the peak)",
+            "launch_clocks": getattr(ctx, "kernel_clocks", None)}
 
 
 # ------------------------------------------------------------------------------ GPU arm: v1 / 8k600
