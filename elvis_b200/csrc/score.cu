@@ -332,6 +332,16 @@ extern "C" int elvis_score_sc_tc(const elvis_plane* y, int32_t n_frames, const u
             score_minmax_init<<<1, 32, 0, st>>>(p.mm);
             ELVIS_CHECK_LAUNCH();
         }
+        // 16 x 16: tensor-core kernel (score_dct16.cu) when the planes are TMA-capable; ELVIS_SCORE_DCT16=simt forces the CUDA cores
+        const char* e16 = getenv("ELVIS_SCORE_DCT16");
+        if (block_size == 16 && al(16) && !(e16 && !strcmp(e16, "simt"))) {
+            ScoreParams q = p;
+            q.n_chunks = pick_chunks(n_frames, (long)By * ((Bx + 7) / 8), (long)kNumSMs * 3, getenv("ELVIS_SCORE_CHUNK") ? atoi(getenv("ELVIS_SCORE_CHUNK")) : 0);
+            q.chunk_len = (n_frames + q.n_chunks - 1) / q.n_chunks;
+            q.n_chunks = (n_frames + q.chunk_len - 1) / q.chunk_len;
+            const int rc = launch_score_dct16(q, y->height, y->width, st);
+            if (rc != ELVIS_ERR_UNSUPPORTED) return rc;
+        }
         return launch_score_dctn(p, block_size, st);
     }
     enum { SIMT, MMA_DIRECT, MMA_TMA, UMMA } impl = SIMT;

@@ -28,6 +28,8 @@ int launch_score_mma(ScoreParams p, int plane_h, int plane_w, bool use_tma, cuda
 int launch_score_umma(ScoreParams p, int block_size, int plane_h, int plane_w, cudaStream_t st);
 // score_dctn.cu: dct_size == block_size in {16, 32}, CUDA cores, one warp per block
 int launch_score_dctn(ScoreParams p, int block_size, cudaStream_t st);
+// score_dct16.cu: dct_size == block_size == 16 on the tensor cores (mma.sync f16 hi/lo split), TMA ring (16-byte aligned planes)
+int launch_score_dct16(ScoreParams p, int plane_h, int plane_w, cudaStream_t st);
 int score_umma_units_per_cta();
 int score_umma_ctas_per_sm();
 

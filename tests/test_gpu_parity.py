@@ -1019,11 +1019,17 @@ def test_pack_levels_2bit_saturates(dev):
 
 @pytest.mark.parametrize("bs,H,W,T", [(16, 64, 96, 7), (32, 64, 128, 4), (16, 48, 272, 30), (16, 1080, 1920, 3), (32, 96, 528, 13),
                                       (16, 50, 75, 5)])
-def test_sc_tc_dct_size_equals_block_size(dev, monkeypatch, bs, H, W, T):
+@pytest.mark.parametrize("impl", ["tensor", "simt"])
+def test_sc_tc_dct_size_equals_block_size(dev, monkeypatch, bs, H, W, T, impl):
     """dct_size = block_size (one 16 x 16 / 32 x 32 transform per block: the size the reference passes to
     EVCA, elvis.py:1022-1023) against the spec with n = block_size; chunked runs and halos give the
-    same bits; unaligned planes take the byte-load path."""
+    same bits; unaligned planes take the byte-load path.  16 x 16 runs on the tensor cores (score_dct16.cu:
+    partial groups of blocks, several groups per row) and, forced, on the CUDA cores (score_dctn.cu)."""
     from elvis_b200 import ops
+    if impl == "simt":
+        if bs != 16:
+            pytest.skip("32 x 32 has one implementation")
+        monkeypatch.setenv("ELVIS_SCORE_DCT16", "simt")
     y = synth_luma(T + 1, H, W, seed=bs + T)
     yd = to_dev(y, dev)
     rsc, rtc = spec_scoring.sc_tc(y[1:], bs, bs)
