@@ -153,18 +153,9 @@ __global__ void __launch_bounds__(kThreads) score_dct16_kernel(const __grid_cons
     const uint32_t bias = p.magic16;                               // 0x64006400: bytes become fp16 1024 + b under PRMT
     const __half2 off = __floats2half2_rn(1152.f, 1152.f);          // 1024 (PRMT bias) + 128 (centering)
 
-    float cprev[2][4];
-#pragma unroll
-    for (int h2 = 0; h2 < 2; ++h2)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) cprev[h2][i] = 0.f;
-    float smin = __int_as_float(0x7f800000), smax = 0.f, tmin = __int_as_float(0x7f800000), tmax = 0.f;
-    const int64_t out_step = (int64_t)p.By * p.Bx;
-    float* out_sc = p.sc + ((int64_t)t_start * p.By + by) * p.Bx + bx;
-    float* out_tc = p.tc + ((int64_t)t_start * p.By + by) * p.Bx + bx;
-
-    for (int f = 0; f < n_iter; ++f) {
-        const int s = f % kRing, t = t_start + f;
+    // One frame: coefficients of my 8 positions into `cur`, partial sums of w |C| and w |C - prev| over them.
+    auto frame = [&](const int f, const float (&prev)[2][4], float (&cur)[2][4], float& sacc, float& dacc) {
+        const int s = f % kRing;
         tma::mbar_wait(bar_full + 8u * s, (uint32_t)(f / kRing) & 1u);
         uint32_t px[2];
         px[0] = *reinterpret_cast<const uint32_t*>(&s_ring[s][off0]);
@@ -193,48 +184,71 @@ __global__ void __launch_bounds__(kThreads) score_dct16_kernel(const __grid_cons
             hmma_16816(tt[h], a1l, xb[h][0], xb[h][1]);
         }
         // step 2: C = D T^T, n-tile h2 = coefficient columns 8 h2 .. 8 h2 + 7
-        float sacc = 0.f, dacc = 0.f;
+        sacc = 0.f;
+        dacc = 0.f;
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
             uint32_t b0h, b0l, b1h, b1l;
             split_pair(tt[0][2 * h2], tt[0][2 * h2 + 1], b0h, b0l);
             split_pair(tt[1][2 * h2], tt[1][2 * h2 + 1], b1h, b1l);
-            float c[4] = {0.f, 0.f, 0.f, 0.f};
-            hmma_16816(c, a2h, b0h, b1h);
-            hmma_16816(c, a2h, b0l, b1l);
-            hmma_16816(c, a2l, b0h, b1h);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cur[h2][i] = 0.f;
+            hmma_16816(cur[h2], a2h, b0h, b1h);
+            hmma_16816(cur[h2], a2h, b0l, b1l);
+            hmma_16816(cur[h2], a2l, b0h, b1h);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                sacc = fmaf(fabsf(c[i]), wt[h2][i], sacc);
-                dacc = fmaf(fabsf(c[i] - cprev[h2][i]), wt[h2][i], dacc);
-                cprev[h2][i] = c[i];
+                sacc = fmaf(fabsf(cur[h2][i]), wt[h2][i], sacc);
+                dacc = fmaf(fabsf(cur[h2][i] - prev[h2][i]), wt[h2][i], dacc);
             }
         }
+    };
+
+    // Frames are taken two at a time: the coefficient sets ping-pong between two register arrays, and the four partial
+    // sums (SC, TC of both frames) are reduced over the warp TOGETHER -- a transposing butterfly, 6 shuffles instead
+    // of 20: after it the lanes with (lane & 24) == 0 / 8 / 16 / 24 hold SC(f), TC(f), SC(f+1), TC(f+1).
+    float ca[2][4], cb[2][4];
 #pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
-            sacc += __shfl_xor_sync(0xffffffffu, sacc, m);
-            dacc += __shfl_xor_sync(0xffffffffu, dacc, m);
-        }
-        if (t >= t0 && lane == 0 && valid) {
-            const float scv = sacc * p.inv_area;
-            const float tcv = (t == 0 && p.halo == nullptr) ? 0.f : dacc * p.inv_area;
-            *out_sc = scv;
-            *out_tc = tcv;
+    for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cb[h2][i] = 0.f;
+    float vmin = __int_as_float(0x7f800000), vmax = 0.f;            // of the value kind this lane ends up holding
+    const int kind = (lane >> 3) & 3;                                // 0: SC(f)  1: TC(f)  2: SC(f+1)  3: TC(f+1)
+    const bool is_tc = kind & 1;
+    const int64_t out_step = (int64_t)p.By * p.Bx;
+    float* out = (is_tc ? p.tc : p.sc) + ((int64_t)(t_start + (kind >> 1)) * p.By + by) * p.Bx + bx;
+    const bool writer = valid && (lane & 7) == 0;
+
+    for (int f = 0; f < n_iter; f += 2) {
+        float s0, d0, s1 = 0.f, d1 = 0.f;
+        frame(f, cb, ca, s0, d0);
+        if (f + 1 < n_iter) frame(f + 1, ca, cb, s1, d1);           // warp-uniform
+        // level 1 (xor 16): lanes 0..15 keep frame f, lanes 16..31 frame f + 1
+        const bool up = lane & 16;
+        float ks = up ? s1 : s0, kd = up ? d1 : d0;
+        ks += __shfl_xor_sync(0xffffffffu, up ? s0 : s1, 16);
+        kd += __shfl_xor_sync(0xffffffffu, up ? d0 : d1, 16);
+        // level 2 (xor 8): lanes with bit 3 clear keep SC, the others TC
+        const bool tcl = lane & 8;
+        float v = tcl ? kd : ks;
+        v += __shfl_xor_sync(0xffffffffu, tcl ? ks : kd, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        const int t = t_start + f + (kind >> 1);
+        if (writer && t >= t0 && t < t1) {
+            const float val = (is_tc && t == 0 && p.halo == nullptr) ? 0.f : v * p.inv_area;
+            *out = val;
             if (t >= p.mm_begin && t < p.mm_end) {
-                smin = fminf(smin, scv);
-                smax = fmaxf(smax, scv);
-                tmin = fminf(tmin, tcv);
-                tmax = fmaxf(tmax, tcv);
+                vmin = fminf(vmin, val);
+                vmax = fmaxf(vmax, val);
             }
         }
-        out_sc += out_step;
-        out_tc += out_step;
+        out += 2 * out_step;
     }
-    if (p.mm != nullptr && lane == 0 && smin <= smax) {
-        atomicMin(p.mm + 0, __float_as_uint(smin));   // non-negative floats order like their bit patterns
-        atomicMax(p.mm + 1, __float_as_uint(smax));
-        atomicMin(p.mm + 2, __float_as_uint(tmin));
-        atomicMax(p.mm + 3, __float_as_uint(tmax));
+    if (p.mm != nullptr && writer && vmin <= vmax) {
+        atomicMin(p.mm + (is_tc ? 2 : 0), __float_as_uint(vmin));   // non-negative floats order like their bit patterns
+        atomicMax(p.mm + (is_tc ? 3 : 1), __float_as_uint(vmax));
     }
 }
 
