@@ -102,8 +102,9 @@ def allreduce_minmax(mm: torch.Tensor, world: int, group=None) -> torch.Tensor:
 
 def sharded_removability(clip: HaloClip, n_frames_total: int, block_size: int, alpha: float, beta: float,
                          rank: int, world: int, background: Optional[torch.Tensor] = None, kernels=None,
-                         group=None, exchange: bool = True, transport=None) -> torch.Tensor:
+                         group=None, exchange: bool = True, transport=None, dct_size: int = 8) -> torch.Tensor:
     """elvis-mode removability (elvis.py:1160-1220) of the owned frames -> (n, By, Bx) float64.
+    dct_size: 8 (8 x 8 tiles) or block_size (one transform per block, the reference's EVCA call).
     background: optional uint8 (n+2, By, Bx) laid out like clip.buf (halo slots filled by the
     caller when it has the neighbours' masks; only slot 0 is ever read).  exchange=False: the
     caller has already run exchange_halo (e.g. ahead of time on a communication stream).
@@ -120,7 +121,8 @@ def sharded_removability(clip: HaloClip, n_frames_total: int, block_size: int, a
     elif exchange:
         exchange_halo(clip, rank, world, group)
     ext, first = clip.extended(rank, world)
-    sc, tc, norm = kernels.score_sc_tc(ext, block_size, minmax_range=(first, first + clip.n))
+    size_kw = {} if dct_size == 8 else {"dct_size": dct_size}
+    sc, tc, norm = kernels.score_sc_tc(ext, block_size, minmax_range=(first, first + clip.n), **size_kw)
     if peer is not None:
         peer.release_halo(clip)          # stream ordered: the scoring kernel has read the halo slots
         reduce_ = peer.allreduce_minmax_
@@ -139,7 +141,8 @@ def sharded_removability(clip: HaloClip, n_frames_total: int, block_size: int, a
 
 
 def sharded_importance(clip: HaloClip, block_size: int, alpha: float, beta: float, rank: int, world: int,
-                       foreground: Optional[torch.Tensor] = None, kernels=None, group=None, transport=None) -> torch.Tensor:
+                       foreground: Optional[torch.Tensor] = None, kernels=None, group=None, transport=None,
+                       dct_size: int = 8) -> torch.Tensor:
     """utils-mode importance (utils.py:665-688) of the owned frames: per-frame normalisation,
     so the halo exchange is the only communication (transport: see sharded_removability)."""
     if kernels is None:
@@ -151,7 +154,7 @@ def sharded_importance(clip: HaloClip, block_size: int, alpha: float, beta: floa
     else:
         exchange_halo(clip, rank, world, group)
     ext, first = clip.extended(rank, world)
-    sc, tc, _ = kernels.score_sc_tc(ext, block_size)
+    sc, tc, _ = kernels.score_sc_tc(ext, block_size, **({} if dct_size == 8 else {"dct_size": dct_size}))
     if peer is not None:
         peer.release_halo(clip)
     fg = None

@@ -804,6 +804,13 @@ def test_sharding_world_one_equals_local(dev):
     imp = sharding.sharded_importance(halo, bs, 0.5, 0.5, 0, 1).cpu().numpy()
     rsc, rtc = spec_scoring.sc_tc(y, bs)
     np.testing.assert_allclose(imp, P.importance_scores(rsc, rtc, 0.5, 0.5, np.ones_like(rsc)), rtol=RTOL, atol=1e-7)
+    # the block-sized transform (the reference's EVCA call) through the sharded scorers
+    got16 = sharding.sharded_removability(halo, T, bs, 0.5, 0.5, 0, 1, dct_size=bs)
+    assert torch.equal(got16, ElvisV1(bs, 0.5, 0.5, 0.5, dct_size=bs).score(Yuv420(to_dev(y, dev), to_dev(u, dev), to_dev(v, dev))))
+    assert not torch.equal(got16, got)
+    imp16 = sharding.sharded_importance(halo, bs, 0.5, 0.5, 0, 1, dct_size=bs).cpu().numpy()
+    rsc, rtc = spec_scoring.sc_tc(y, bs, bs)
+    np.testing.assert_allclose(imp16, P.importance_scores(rsc, rtc, 0.5, 0.5, np.ones_like(rsc)), rtol=RTOL, atol=1e-7)
 
 
 def test_api_errors_and_strided_inputs(dev):
