@@ -143,7 +143,7 @@ __device__ __forceinline__ uint64_t b_descriptor(uint32_t smem_addr) {
 // XBAR: how the upper-half warp of a unit hands its partial sums to the lower-half warp.  false: a 64-thread named
 // barrier per frame (round 1; both warps wait for each other).  true: a one-way mbarrier per exchange slot -- the
 // upper half arrives and moves on, only the lower half ever waits.
-template <int R, bool XBAR>
+template <int R, bool XBAR, bool ROLLED>
 __global__ void __launch_bounds__(kUmmaThreads, kCtasPerSm)
 score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_constant__ CUtensorMap tm_halo, const ScoreParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -329,13 +329,13 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
         // = sum w |C_t|, TC part = sum w |C_t - C_{t-1}| with C_{t-1} = the D buffer written one
         // frame earlier.  2 x 4 independent FMA chains, fixed order => deterministic.
         const uint32_t bar_x = base + kOffXbar + 16 * unit_local;
-        auto consume = [&](const int t, const int dbuf, const uint32_t d_parity, const int xslot, const uint32_t x_parity, auto role_c) {
+        auto consume = [&](const int t, const int dbuf, const int dprev, const uint32_t d_parity, const int xslot, const uint32_t x_parity, auto role_c) {
             constexpr int ROLE = decltype(role_c)::value;
             mbar_wait(bar_d + 8 * dbuf, d_parity);
             tc_fence_after();
             uint32_t v[32], q[32];
             tmem_ld32(tmem + lane_base + kColD + 64 * dbuf + 32 * ROLE, v);
-            tmem_ld32(tmem + lane_base + kColD + 64 * ((dbuf + 2) % 3) + 32 * ROLE, q);
+            tmem_ld32(tmem + lane_base + kColD + 64 * dprev + 32 * ROLE, q);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             float sa[4] = {0.f, 0.f, 0.f, 0.f}, da[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -402,18 +402,46 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
         static_assert(kUmmaRing == 6, "the unrolled frame loop assumes a ring of 6");
         auto run = [&](auto role_c) {
             produce(0, 0, 0u);
-            uint32_t round_parity = 0;
+            if (!ROLLED) {
+                uint32_t round_parity = 0;
 #pragma unroll 1
-            for (int it0 = 0; it0 < n_iter; it0 += 6) {
+                for (int it0 = 0; it0 < n_iter; it0 += 6) {
 #pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    const int it = it0 + i;
-                    if (it >= n_iter) break;
-                    if (it + 1 < n_iter) produce((i + 1) % 6, (i + 1) & 1, i == 5 ? round_parity ^ 1u : round_parity);
-                    // exchange slot i & 1 has been used (it >> 1) times before: its phase parity is round ^ (i >> 1)
-                    consume(t_start + it, i % 3, (uint32_t)(i / 3) & 1u, i & 1, round_parity ^ ((uint32_t)(i >> 1) & 1u), role_c);
+                    for (int i = 0; i < 6; ++i) {
+                        const int it = it0 + i;
+                        if (it >= n_iter) break;
+                        if (it + 1 < n_iter) produce((i + 1) % 6, (i + 1) & 1, i == 5 ? round_parity ^ 1u : round_parity);
+                        // exchange slot i & 1 has been used (it >> 1) times before: its phase parity is round ^ (i >> 1)
+                        consume(t_start + it, i % 3, (i + 2) % 3, (uint32_t)(i / 3) & 1u, i & 1, round_parity ^ ((uint32_t)(i >> 1) & 1u), role_c);
+                    }
+                    round_parity ^= 1u;
                 }
-                round_parity ^= 1u;
+            } else {
+                // The same schedule with the ring slot, the D buffer and their parities carried in registers and the
+                // loop unrolled by two only (A buffer and exchange slot stay compile-time): a third of the code, so
+                // that the two roles' loops fit the instruction caches (ncu: `no_instruction` was the top stall reason).
+                int slot = 1, dbuf = 0, dprev = 2;          // next frame to produce: 1; frame 0 lands in D buffer 0
+                uint32_t ring_parity = 0, d_parity = 0, x_parity = 0;
+#pragma unroll 1
+                for (int it0 = 0; it0 < n_iter; it0 += 2) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int it = it0 + i;
+                        if (it >= n_iter) break;
+                        if (it + 1 < n_iter) produce(slot, (i + 1) & 1, ring_parity);
+                        if (++slot == kUmmaRing) {
+                            slot = 0;
+                            ring_parity ^= 1u;
+                        }
+                        consume(t_start + it, dbuf, dprev, d_parity, i, x_parity, role_c);
+                        dprev = dbuf;
+                        if (++dbuf == 3) {
+                            dbuf = 0;
+                            d_parity ^= 1u;
+                        }
+                    }
+                    x_parity ^= 1u;
+                }
             }
         };
         if (role == 0) run(std::integral_constant<int, 0>{});
@@ -471,7 +499,7 @@ bool make_unit_map(CUtensorMap* m, const uint8_t* ptr, int W, int H, int T, int6
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int R, bool XBAR>
+template <int R, bool XBAR, bool ROLLED>
 int launch_umma(const ScoreParams& p, const CUtensorMap& tm_clip, const CUtensorMap& tm_halo, cudaStream_t st) {
     // no carve-out preference: a kernel that forces its own L1 / shared split cannot overlap with the
     // shrink / stretch kernels of the other stream (measured: pipelined step 1.32 instead of 1.07 ms)
@@ -484,11 +512,11 @@ int launch_umma(const ScoreParams& p, const CUtensorMap& tm_clip, const CUtensor
     }();
     static PerDeviceOnce configured;   // the attribute is per (kernel, device)
     const cudaError_t e = configured.run([] {
-        return cudaFuncSetAttribute(score_umma_kernel<R, XBAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem + pad);
+        return cudaFuncSetAttribute(score_umma_kernel<R, XBAR, ROLLED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem + pad);
     });
     if (e != cudaSuccess) return cuda_fail(e);
     const int ctas_per_chunk = (p.By * p.tiles_x + kUnitsPerCta - 1) / kUnitsPerCta;
-    score_umma_kernel<R, XBAR><<<ctas_per_chunk * p.n_chunks, kUmmaThreads, kUmmaSmem + pad, st>>>(tm_clip, tm_halo, p);
+    score_umma_kernel<R, XBAR, ROLLED><<<ctas_per_chunk * p.n_chunks, kUmmaThreads, kUmmaSmem + pad, st>>>(tm_clip, tm_halo, p);
     ELVIS_CHECK_LAUNCH();
     return ELVIS_OK;
 }
@@ -513,10 +541,17 @@ int launch_score_umma(ScoreParams p, int block_size, int plane_h, int plane_w, c
     if (!make_unit_map(&tm_halo, p.halo ? p.halo : p.y, plane_w, plane_h, 1, p.row_stride, p.frame_stride, R)) return ELVIS_ERR_UNSUPPORTED;
     const char* xe = getenv("ELVIS_UMMA_XBAR");        // 1 (default): one-way mbarrier exchange; 0: the round-1 named barrier
     const bool xbar = !(xe && xe[0] == '0');
+    const char* re = getenv("ELVIS_UMMA_ROLLED");      // 1: frame loop unrolled by 2 with run-time ring indices; 0: unrolled by 6
+    const bool rolled = re && re[0] == '1';
+    auto go = [&](auto r_c) {
+        constexpr int RR = decltype(r_c)::value;
+        if (rolled) return xbar ? launch_umma<RR, true, true>(p, tm_clip, tm_halo, st) : launch_umma<RR, false, true>(p, tm_clip, tm_halo, st);
+        return xbar ? launch_umma<RR, true, false>(p, tm_clip, tm_halo, st) : launch_umma<RR, false, false>(p, tm_clip, tm_halo, st);
+    };
     switch (R) {
-        case 1: return xbar ? launch_umma<1, true>(p, tm_clip, tm_halo, st) : launch_umma<1, false>(p, tm_clip, tm_halo, st);
-        case 2: return xbar ? launch_umma<2, true>(p, tm_clip, tm_halo, st) : launch_umma<2, false>(p, tm_clip, tm_halo, st);
-        default: return xbar ? launch_umma<4, true>(p, tm_clip, tm_halo, st) : launch_umma<4, false>(p, tm_clip, tm_halo, st);
+        case 1: return go(std::integral_constant<int, 1>{});
+        case 2: return go(std::integral_constant<int, 2>{});
+        default: return go(std::integral_constant<int, 4>{});
     }
 }
 
