@@ -143,7 +143,7 @@ __device__ __forceinline__ uint64_t b_descriptor(uint32_t smem_addr) {
 // XBAR: how the upper-half warp of a unit hands its partial sums to the lower-half warp.  false: a 64-thread named
 // barrier per frame (round 1; both warps wait for each other).  true: a one-way mbarrier per exchange slot -- the
 // upper half arrives and moves on, only the lower half ever waits.
-template <int R, bool XBAR, bool ROLLED>
+template <int R, bool XBAR, int ROLLED>
 __global__ void __launch_bounds__(kUmmaThreads, kCtasPerSm)
 score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_constant__ CUtensorMap tm_halo, const ScoreParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -416,7 +416,7 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
                     }
                     round_parity ^= 1u;
                 }
-            } else {
+            } else if (ROLLED == 2) {
                 // The same schedule with the ring slot, the D buffer and their parities carried in registers and the
                 // loop unrolled by two only (A buffer and exchange slot stay compile-time): a third of the code, so
                 // that the two roles' loops fit the instruction caches (ncu: `no_instruction` was the top stall reason).
@@ -441,6 +441,27 @@ score_umma_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_cons
                         }
                     }
                     x_parity ^= 1u;
+                }
+            } else {
+                // fully rolled: every index in registers
+                int slot = 1, dbuf = 0, dprev = 2, abuf = 1, xslot = 0;
+                uint32_t ring_parity = 0, d_parity = 0, x_parity = 0;
+#pragma unroll 1
+                for (int it = 0; it < n_iter; ++it) {
+                    if (it + 1 < n_iter) produce(slot, abuf, ring_parity);
+                    abuf ^= 1;
+                    if (++slot == kUmmaRing) {
+                        slot = 0;
+                        ring_parity ^= 1u;
+                    }
+                    consume(t_start + it, dbuf, dprev, d_parity, xslot, x_parity, role_c);
+                    dprev = dbuf;
+                    if (++dbuf == 3) {
+                        dbuf = 0;
+                        d_parity ^= 1u;
+                    }
+                    x_parity ^= (uint32_t)xslot;            // flips after the frame that used slot 1
+                    xslot ^= 1;
                 }
             }
         };
@@ -499,7 +520,7 @@ bool make_unit_map(CUtensorMap* m, const uint8_t* ptr, int W, int H, int T, int6
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int R, bool XBAR, bool ROLLED>
+template <int R, bool XBAR, int ROLLED>
 int launch_umma(const ScoreParams& p, const CUtensorMap& tm_clip, const CUtensorMap& tm_halo, cudaStream_t st) {
     // no carve-out preference: a kernel that forces its own L1 / shared split cannot overlap with the
     // shrink / stretch kernels of the other stream (measured: pipelined step 1.32 instead of 1.07 ms)
@@ -541,12 +562,13 @@ int launch_score_umma(ScoreParams p, int block_size, int plane_h, int plane_w, c
     if (!make_unit_map(&tm_halo, p.halo ? p.halo : p.y, plane_w, plane_h, 1, p.row_stride, p.frame_stride, R)) return ELVIS_ERR_UNSUPPORTED;
     const char* xe = getenv("ELVIS_UMMA_XBAR");        // 1 (default): one-way mbarrier exchange; 0: the round-1 named barrier
     const bool xbar = !(xe && xe[0] == '0');
-    const char* re = getenv("ELVIS_UMMA_ROLLED");      // 1: frame loop unrolled by 2 with run-time ring indices; 0: unrolled by 6
-    const bool rolled = re && re[0] == '1';
+    const char* re = getenv("ELVIS_UMMA_ROLLED");      // frame loop: 0 = unrolled by 6 (compile-time ring indices), 2 = by two, 1 = not unrolled
+    const int rolled = re ? atoi(re) : 0;
     auto go = [&](auto r_c) {
         constexpr int RR = decltype(r_c)::value;
-        if (rolled) return xbar ? launch_umma<RR, true, true>(p, tm_clip, tm_halo, st) : launch_umma<RR, false, true>(p, tm_clip, tm_halo, st);
-        return xbar ? launch_umma<RR, true, false>(p, tm_clip, tm_halo, st) : launch_umma<RR, false, false>(p, tm_clip, tm_halo, st);
+        if (rolled == 2) return xbar ? launch_umma<RR, true, 2>(p, tm_clip, tm_halo, st) : launch_umma<RR, false, 2>(p, tm_clip, tm_halo, st);
+        if (rolled == 1) return xbar ? launch_umma<RR, true, 1>(p, tm_clip, tm_halo, st) : launch_umma<RR, false, 1>(p, tm_clip, tm_halo, st);
+        return xbar ? launch_umma<RR, true, 0>(p, tm_clip, tm_halo, st) : launch_umma<RR, false, 0>(p, tm_clip, tm_halo, st);
     };
     switch (R) {
         case 1: return go(std::integral_constant<int, 1>{});
