@@ -1,5 +1,6 @@
-import torch, time, sys
-sys.path.insert(0, "/root/repo")
+"""Time elvis_score_sc_tc on 120 4K frames with the 8 x 8 transform (tcgen05 kernel) and the block-sized 16 x 16 one."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from elvis_b200 import ops
 from elvis_b200.synth import synth_yuv420
 dev = torch.device("cuda")
