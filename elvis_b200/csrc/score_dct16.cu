@@ -75,7 +75,7 @@ __device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint3
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-__global__ void __launch_bounds__(kThreads) score_dct16_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_constant__ CUtensorMap tm_halo,
+__global__ void __launch_bounds__(kThreads, 3) score_dct16_kernel(const __grid_constant__ CUtensorMap tm_clip, const __grid_constant__ CUtensorMap tm_halo,
                                                               const __grid_constant__ Dct16Tables tab, const ScoreParams p) {
     __shared__ __align__(1024) uint8_t s_ring[kRing][kBox];
     __shared__ __align__(8) uint64_t s_full[kRing], s_empty[kRing];
