@@ -290,23 +290,26 @@ __device__ __forceinline__ void blur_imma_rounds(uint32_t& w0, uint32_t& w1, con
         int m1a[4], m1b[4];                               // M1 = G X^T: n-tile 0 (from my first row) and 1 (second row)
         imma_16816(m1a, a0, a1, w0, zero4);
         imma_16816(m1b, a0, a1, w1, zero4);
-        uint32_t z[2];
+        uint32_t za[2], zb[2];                             // byte pairs of my first / second row from n-tile `half`
 #pragma unroll
         for (int half = 0; half < 2; ++half) {            // layout rows g / g + 8 of M1 feed n-tile `half` of step 2
             const uint32_t q0 = (uint32_t)m1a[2 * half], q1 = (uint32_t)m1a[2 * half + 1];
             const uint32_t q2 = (uint32_t)m1b[2 * half], q3 = (uint32_t)m1b[2 * half + 1];
-            const uint32_t hi = __byte_perm(__byte_perm(q0, q1, 0x0051), __byte_perm(q2, q3, 0x0051), 0x5410);
-            const uint32_t lo = __byte_perm(__byte_perm(q0, q1, 0x0040), __byte_perm(q2, q3, 0x0040), 0x5410);
+            // the four 16-bit values as two registers of halves, then their high / low bytes: 4 PRMT (6 when each is built apart)
+            const uint32_t p01 = __byte_perm(q0, q1, 0x5410), p23 = __byte_perm(q2, q3, 0x5410);
+            const uint32_t hi = __byte_perm(p01, p23, 0x7531);
+            const uint32_t lo = __byte_perm(p01, p23, 0x6420);
             int acc[4], acl[4];                            // two independent products: shorter dependent chain per round
             imma_16816(acc, a0, a1, hi, half4);
             imma_16816(acl, a0, a1, lo, zero4);
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[i] = acc[i] * 256 + acl[i];
-            // my first row's word comes from acc[0..1] of both halves, my second row's from acc[2..3]: keep all four
-            z[half] = __byte_perm(__byte_perm((uint32_t)acc[0], (uint32_t)acc[1], 0x0062), __byte_perm((uint32_t)acc[2], (uint32_t)acc[3], 0x0062), 0x5410);
+            // byte 2 of every accumulator is the pixel: acc[0..1] belong to my first row, acc[2..3] to my second
+            za[half] = __byte_perm((uint32_t)acc[0], (uint32_t)acc[1], 0x0062);
+            zb[half] = __byte_perm((uint32_t)acc[2], (uint32_t)acc[3], 0x0062);
         }
-        // z[half] = (row g: cols 2q,2q+1 of n-tile half | row g+8: the same) -> words of my two rows
-        const uint32_t n0 = __byte_perm(z[0], z[1], 0x5410), n1 = __byte_perm(z[0], z[1], 0x7632);
+        // words of my two rows: columns 2q, 2q+1 of n-tile 0, then of n-tile 1
+        const uint32_t n0 = __byte_perm(za[0], za[1], 0x5410), n1 = __byte_perm(zb[0], zb[1], 0x5410);
         if (k < nr) {
             w0 = n0;
             w1 = n1;
