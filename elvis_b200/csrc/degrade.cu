@@ -281,11 +281,16 @@ __device__ __forceinline__ int imma_tile_row(int i) { return 4 * ((i & 7) >> 1) 
 
 // `nr` blur rounds (per thread: the rounds of the block its 8 pixels belong to) on the warp's tile, held as the words
 // w0 / w1 of the thread's two rows; every lane of the warp must call it (the IMMAs are warp-wide).
+template <int PB>
 __device__ __forceinline__ void blur_imma_rounds(uint32_t& w0, uint32_t& w1, const uint32_t a0, const uint32_t a1, const int nr) {
     const int zero4[4] = {0, 0, 0, 0}, half4[4] = {128, 128, 128, 128};
+    // rounds the warp has to run: the tile's own count (one block), or the maximum over its four blocks -- the block of a
+    // lane is given by bit 4 (rows) and bit 1 (columns) of the lane index
     int max_r = nr;
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) max_r = max(max_r, __shfl_xor_sync(0xffffffffu, max_r, m));
+    if (PB == 8) {
+        max_r = max(max_r, __shfl_xor_sync(0xffffffffu, max_r, 16));
+        max_r = max(max_r, __shfl_xor_sync(0xffffffffu, max_r, 2));
+    }
     for (int k = 0; k < max_r; ++k) {
         int m1a[4], m1b[4];                               // M1 = G X^T: n-tile 0 (from my first row) and 1 (second row)
         imma_16816(m1a, a0, a1, w0, zero4);
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__(128) blur_imma_tma_kernel(const __grid_constan
             uint32_t* p0 = reinterpret_cast<uint32_t*>(buf + row0 + ((j ^ x0) << 4));
             uint32_t* p1 = reinterpret_cast<uint32_t*>(buf + row1 + ((j ^ x1) << 4));
             uint32_t w0 = *p0, w1 = *p1;
-            blur_imma_rounds(w0, w1, a0, a1, s_nr[w][j][lane]);
+            blur_imma_rounds<PB>(w0, w1, a0, a1, s_nr[w][j][lane]);
             *p0 = w0;
             *p1 = w1;
         }
@@ -465,7 +470,7 @@ __global__ void __launch_bounds__(256) blur_imma_kernel(const BlockGeom g, const
                 w1 = p1[0] | (p1[1] << 8) | (p1[2] << 16) | ((uint32_t)p1[3] << 24);
             }
         }
-        blur_imma_rounds(w0, w1, a0, a1, nr);
+        blur_imma_rounds<PB>(w0, w1, a0, a1, nr);
         if (live) {
             uint8_t *p0 = dp + (int64_t)r0 * g.dst_row, *p1 = dp + (int64_t)r1 * g.dst_row;
             if (ALIGNED) {
