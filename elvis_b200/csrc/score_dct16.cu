@@ -70,8 +70,7 @@ __device__ __forceinline__ void hmma_16816(float (&d)[4], const uint32_t (&a)[4]
 __device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
     const __half2 h = __floats2half2_rn(x, y);
     const float2 hf = __half22float2(h);
-    const float2 r = __fadd2_rn(make_float2(x, y), make_float2(-hf.x, -hf.y));      // one packed subtraction
-    const __half2 l = __floats2half2_rn(r.x, r.y);
+    const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
@@ -198,12 +197,9 @@ __global__ void __launch_bounds__(kThreads, 3) score_dct16_kernel(const __grid_c
             hmma_16816(cur[h2], a2h, b0l, b1l);
             hmma_16816(cur[h2], a2l, b0h, b1h);
 #pragma unroll
-            for (int i = 0; i < 4; i += 2) {
-                const float2 df = __fadd2_rn(make_float2(cur[h2][i], cur[h2][i + 1]), make_float2(-prev[h2][i], -prev[h2][i + 1]));
+            for (int i = 0; i < 4; ++i) {
                 sacc = fmaf(fabsf(cur[h2][i]), wt[h2][i], sacc);
-                dacc = fmaf(fabsf(df.x), wt[h2][i], dacc);
-                sacc = fmaf(fabsf(cur[h2][i + 1]), wt[h2][i + 1], sacc);
-                dacc = fmaf(fabsf(df.y), wt[h2][i + 1], dacc);
+                dacc = fmaf(fabsf(cur[h2][i] - prev[h2][i]), wt[h2][i], dacc);
             }
         }
     };
