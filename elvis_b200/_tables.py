@@ -1,5 +1,5 @@
 """Host-side coefficient tables for elvis_degrade_downsample (layout documented in
-csrc/degrade.cu).  The arithmetic follows OpenCV's resize setup code for 8-bit images:
+csrc/downsample.cu).  The arithmetic follows OpenCV's resize setup code for 8-bit images:
 the bilinear taps are float32 positions quantised to 11 bits, the fractional INTER_AREA
 weights are float32 overlaps.  tests/test_tables.py compares these against the
 independent restatement in oracle/spec_cv.py."""

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "csrc", "build")
 LIB_PATH = os.path.join(HERE, "libelvis_b200.so")
-SOURCES = ["common.cu", "score.cu", "score_mma.cu", "score_umma.cu", "score_dctn.cu", "score_dct16.cu", "combine.cu", "select.cu", "shrink.cu", "degrade.cu", "restore.cu", "rowcol.cu", "roi.cu", "pyramid.cu", "peer.cu"]
+SOURCES = ["common.cu", "score.cu", "score_mma.cu", "score_umma.cu", "score_dctn.cu", "score_dct16.cu", "combine.cu", "select.cu", "shrink.cu", "degrade.cu", "blur.cu", "downsample.cu", "dampen.cu", "restore.cu", "rowcol.cu", "roi.cu", "pyramid.cu", "peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
