@@ -1,4 +1,4 @@
-"""CPU check of the tensor-core formulation of the per-block Gaussian blur (blur_imma in degrade.cu),
+"""CPU check of the tensor-core formulation of the per-block Gaussian blur (blur_imma in blur.cu),
 transliterated: Z = G X G^T per round as three groups of mma.sync.m16n8k16 (u8 x u8 -> s32) whose
 operands chain without data movement, against oracle/spec_cv.gaussian_blur5_rounds."""
 import os

@@ -1,4 +1,4 @@
-"""CPU check of the tensor-core formulation of the DCT dampening (dampen_hmma in degrade.cu): the gain
+"""CPU check of the tensor-core formulation of the DCT dampening (dampen_hmma in dampen.cu): the gain
 g(u, v) = q^(u+v) is separable, so dampening an 8 x 8 tile is X' = M X M^T with M = A^T diag(q^u) A
 (A = orthonormal DCT-II) -- two small matrix products per tile with a per-block operator.  Emulates
 mma.sync.m16n8k16 (f16 x f16 -> f32) with the PTX fragment layouts, the hi + lo f16 splits and the
