@@ -161,6 +161,21 @@ def build(pb: int, small_sizes: tuple, lanczos: bool = False) -> np.ndarray:
     return np.concatenate([generic, np.zeros(pad, np.int32), fast.reshape(-1)])
 
 
+def fast_levels_flag(pb: int, small_sizes: tuple) -> int:
+    """The `fast_tables_ok` argument of elvis_degrade_downsample: 1 = every level has fast-path tables, 0 = none (or too
+    many levels to describe), otherwise an even value with bit l + 1 set for every level l WITHOUT them."""
+    blob = build(pb, tuple(small_sizes))
+    st = level_stride(pb)
+    if pb not in (8, 16):
+        return 0
+    fast = [int(blob[i * st + 5]) == 1 for i in range(len(small_sizes))]
+    if all(fast):
+        return 1
+    if not any(fast) or len(fast) > 30:
+        return 0
+    return sum(1 << (i + 1) for i, f in enumerate(fast) if not f)
+
+
 def all_fast(pb: int, small_sizes: tuple) -> bool:
     """True when every level of the blob has fast-path (byte-weight) tables."""
     blob = build(pb, tuple(small_sizes))

@@ -24,7 +24,8 @@ __host__ __device__ inline int level_stride(int pb, bool lanczos = false) { retu
 
 template <bool LANCZOS>
 __global__ void __launch_bounds__(256) downsample_kernel(const BlockGeom g, const int32_t* __restrict__ levels,
-                                                         const int32_t* __restrict__ tables, int n_levels, int warps_per_cta) {
+                                                         const int32_t* __restrict__ tables, int n_levels, int warps_per_cta,
+                                                         const uint32_t only_mask = 0u) {   // non-zero: only blocks whose level bit is set
     extern __shared__ __align__(16) uint8_t smem[];
     const int pb = g.pb, n = pb * pb;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(256) downsample_kernel(const BlockGeom g, cons
         decode_unit(g, unit, t, by, bx, c);
         int lv = levels[((int64_t)t * g.By + by) * g.Bx + bx];
         lv = lv < 0 ? 0 : (lv >= n_levels ? n_levels - 1 : lv);
+        if (only_mask && !((only_mask >> lv) & 1u)) continue;      // the closed-form kernel handles this block (warp-uniform)
         const int32_t* tab = tables + (size_t)lv * level_stride(pb, LANCZOS);
         const int small = tab[0], kind = tab[1];
         const uint8_t* sp = g.src + (int64_t)t * g.src_frame + (int64_t)by * pb * g.src_row + ((int64_t)bx * pb) * g.C + c;
@@ -284,7 +286,8 @@ __global__ void __launch_bounds__(256) downsample_fast_kernel(const BlockGeom g,
 // (about 11 instructions per pixel against 30 of the table-driven kernel above).
 template <int PB, bool ALIGNED>
 __global__ void __launch_bounds__(256) downsample_pow2_kernel(const BlockGeom g, const int32_t* __restrict__ levels,
-                                                              const int32_t* __restrict__ tables, int n_levels) {
+                                                              const int32_t* __restrict__ tables, int n_levels,
+                                                              const uint32_t skip_mask = 0u) {   // levels left to the generic kernel
     constexpr int kWarps = 8;
     constexpr int kGroup = 2 * PB;
     constexpr int kBlocks = 32 / kGroup;
@@ -297,18 +300,21 @@ __global__ void __launch_bounds__(256) downsample_pow2_kernel(const BlockGeom g,
     const int64_t stride = (int64_t)gridDim.x * kWarps * kBlocks;
     for (int64_t b0 = ((int64_t)blockIdx.x * kWarps + w) * kBlocks; b0 < n_blocks; b0 += stride) {
         const int64_t b = b0 + blk;
-        const bool live = b < n_blocks;
+        bool live = b < n_blocks;
         int L = 0;
         const uint8_t* sp = g.src;
         uint8_t* dp = g.dst;
         if (live) {
+            int lv = levels[b];
+            lv = lv < 0 ? 0 : (lv >= n_levels ? n_levels - 1 : lv);
+            live = !((skip_mask >> lv) & 1u);
+            const int small = __ldg(tables + (size_t)lv * kLevelStride);
+            L = (!live || small >= PB) ? 0 : 31 - __clz(PB / small);
+        }
+        if (live) {
             const int bx = (int)(b % g.Bx);
             const int64_t q = b / g.Bx;
             const int by = (int)(q % g.By), t = (int)(q / g.By);
-            int lv = levels[b];
-            lv = lv < 0 ? 0 : (lv >= n_levels ? n_levels - 1 : lv);
-            const int small = __ldg(tables + (size_t)lv * kLevelStride);
-            L = small >= PB ? 0 : 31 - __clz(PB / small);
             sp += (int64_t)t * g.src_frame + ((int64_t)by * PB + r) * g.src_row + (int64_t)bx * PB + kBytes * h;
             dp += (int64_t)t * g.dst_frame + ((int64_t)by * PB + r) * g.dst_row + (int64_t)bx * PB + kBytes * h;
         }
@@ -563,7 +569,29 @@ extern "C" int elvis_degrade_downsample(const elvis_plane* src, const elvis_plan
     cudaStream_t st = as_stream(stream);
     if (int rc = copy_edges(g, st)) return rc;
     const int n = block_px * block_px;
-    if (g.C == 1 && (block_px == 16 || block_px == 8) && fast_tables_ok && !getenv("ELVIS_DOWNSAMPLE_GENERIC")) {
+    // fast_tables_ok: 1 = every level is a power-of-two reduction; an even value > 1 = MIXED, bit l + 1 set for every level l
+    // WITHOUT fast tables (e.g. utils' 16 -> 5): those blocks go through the generic kernel, all others through the closed form
+    const uint32_t slow_mask = (fast_tables_ok > 1 && !(fast_tables_ok & 1)) ? ((uint32_t)fast_tables_ok >> 1) : 0u;
+    if (g.C == 1 && (block_px == 16 || block_px == 8) && slow_mask && !getenv("ELVIS_DOWNSAMPLE_GENERIC") && !getenv("ELVIS_DOWNSAMPLE_TABLE")) {
+        const bool al4 = aligned_to(g.src, block_px / 2) && aligned_to(g.dst, block_px / 2) && g.src_frame % (block_px / 2) == 0 &&
+                         g.dst_frame % (block_px / 2) == 0 && g.src_row % (block_px / 2) == 0 && g.dst_row % (block_px / 2) == 0;
+        const int64_t blocks = (int64_t)n_frames * by * bx;
+        const int grid2 = grid_for_units(blocks, 8 * (block_px == 16 ? 1 : 2));
+        if (block_px == 16) {
+            if (al4) downsample_pow2_kernel<16, true><<<grid2, 256, 0, st>>>(g, levels, tables, n_levels, slow_mask);
+            else downsample_pow2_kernel<16, false><<<grid2, 256, 0, st>>>(g, levels, tables, n_levels, slow_mask);
+        } else {
+            if (al4) downsample_pow2_kernel<8, true><<<grid2, 256, 0, st>>>(g, levels, tables, n_levels, slow_mask);
+            else downsample_pow2_kernel<8, false><<<grid2, 256, 0, st>>>(g, levels, tables, n_levels, slow_mask);
+        }
+        ELVIS_CHECK_LAUNCH();
+        int wpc = 8;
+        while (wpc > 1 && (size_t)wpc * n * 6 > 48 * 1024) wpc >>= 1;
+        downsample_kernel<false><<<grid_for_units(blocks, wpc), wpc * 32, (size_t)wpc * n * 6, st>>>(g, levels, tables, n_levels, wpc, slow_mask);
+        ELVIS_CHECK_LAUNCH();
+        return ELVIS_OK;
+    }
+    if (g.C == 1 && (block_px == 16 || block_px == 8) && fast_tables_ok == 1 && !getenv("ELVIS_DOWNSAMPLE_GENERIC")) {
         const bool al = aligned_to(g.src, 8) && aligned_to(g.dst, 8) && g.src_frame % 8 == 0 && g.dst_frame % 8 == 0 &&
                         g.src_row % 8 == 0 && g.dst_row % 8 == 0;
         const int64_t blocks = (int64_t)n_frames * by * bx;

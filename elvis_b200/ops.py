@@ -338,7 +338,7 @@ def degrade_downsample(clip: torch.Tensor, levels: torch.Tensor, block_px: int, 
     T, by, bx, out = _degrade_args(clip, levels, block_px, torch.int32, out)
     small_sizes = tuple(int(s) for s in small_sizes)
     tab = _device_tables(block_px, small_sizes, clip.device)
-    fast_ok = int(_tables.all_fast(block_px, small_sizes))
+    fast_ok = _tables.fast_levels_flag(block_px, small_sizes)
     src, dst = plane_of(clip), plane_of(out, "out")
     call("elvis_degrade_downsample", C.byref(src), C.byref(dst), T, block_px, by, bx, _ptr(levels), _ptr(tab),
          len(small_sizes), fast_ok, _stream())

@@ -183,9 +183,11 @@ ELVIS_API int elvis_degrade_blur(const elvis_plane* src, const elvis_plane* dst,
  * utils.py:1151-1161, presley.py:978-983).  levels: int32 (T, By, Bx) indexing
  * `tables`, the device copy of the blob built by elvis_b200/_tables.py
  * (n_levels entries; layout documented there); a level whose small size equals block_px
- * copies the block.  block_px <= 64.  fast_tables_ok: non-zero when the builder marked every
- * level as a power-of-two reduction with byte-weight tables (enables the DP4A kernel for planar
- * 8/16-pixel blocks; the generic table-driven kernel is used otherwise). */
+ * copies the block.  block_px <= 64.  fast_tables_ok: 1 when the builder marked every level as a
+ * power-of-two reduction (closed-form integer kernel for planar 8/16-pixel blocks); 0: the generic
+ * table-driven kernel; an even value > 1: MIXED -- bit l + 1 is set for every level l that is NOT a
+ * power-of-two reduction (n_levels <= 30): those blocks take the generic kernel, the others the closed
+ * form (utils.py:1142-1148: 16 -> 8, 5, 4). */
 ELVIS_API int elvis_degrade_downsample(const elvis_plane* src, const elvis_plane* dst, int32_t n_frames,
                              int32_t block_px, int32_t by, int32_t bx, const int32_t* levels,
                              const int32_t* tables, int32_t n_levels, int32_t fast_tables_ok,

@@ -528,6 +528,22 @@ def test_blur_tensor_core_movers(dev, monkeypatch, movers, pb, by, bx):
     assert int(out.count_nonzero()) == 0                                          # nothing written outside the window
 
 
+@pytest.mark.parametrize("pb,smalls", [(16, (16, 8, 5, 4)), (16, (16, 3, 8, 7, 2, 1)), (8, (8, 5, 3, 2)), (8, (8, 4, 2, 2))])
+def test_downsample_mixed_levels(dev, pb, smalls):
+    """utils' level set (utils.py:1142-1148: block -> 8, 5, 4 pixels) mixes power-of-two reductions with fractional ones:
+    the former run through the closed-form kernel, the latter through the table-driven one, in the same call."""
+    from elvis_b200 import ops
+    T, by, bx = 2, 5, 9
+    rng = np.random.default_rng(pb + len(smalls))
+    plane = rng.integers(0, 256, (T, by * pb, bx * pb), dtype=np.uint8)
+    plane[0] = synth_luma(1, by * pb, bx * pb, seed=3)[0]
+    levels = rng.integers(0, len(smalls), (T, by, bx)).astype(np.int32)
+    got = ops.degrade_downsample(to_dev(plane, dev), to_dev(levels, dev), pb, smalls).cpu().numpy()
+    small_map = np.asarray(smalls)[levels]
+    for t in range(T):
+        assert np.array_equal(got[t], P.downsample_plane(plane[t], small_map[t], pb)), t
+
+
 def test_planar_degrade(dev):
     from elvis_b200 import ops
     from elvis_b200.pipeline import PresleyV2, Yuv420
