@@ -138,6 +138,119 @@ __global__ void __launch_bounds__(256) downsample_kernel(const BlockGeom g, cons
     }
 }
 
+// ------------------------------------------- downsample, table driven, planar 16 / 8 blocks
+// The arithmetic of downsample_kernel<false> above (same tables, same operation order: bit-identical) for single-channel
+// planes with aligned rows and 16- or 8-pixel blocks -- the shape in which fractional reductions actually occur (utils'
+// 16 -> 5, presley's bs // 3 and bs // 5): the block comes in and goes out as 8- / 4-byte row pieces through shared
+// memory instead of byte by byte, the block size is a compile-time constant, and the (row, column) pairs of the
+// reduced image advance incrementally instead of being divided out of a linear index.
+template <int PB>
+__global__ void __launch_bounds__(256) downsample_planar_kernel(const BlockGeom g, const int32_t* __restrict__ levels,
+                                                                const int32_t* __restrict__ tables, int n_levels, const uint32_t only_mask) {
+    constexpr int kWarps = 8, N = PB * PB;
+    __shared__ __align__(16) int32_t s_b[kWarps][N];          // horizontal passes: float (area) / int (bilinear)
+    __shared__ __align__(16) uint8_t s_a[kWarps][N];          // the block, then the result
+    __shared__ __align__(16) uint8_t s_s[kWarps][N];          // the reduced image
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int32_t* Bi = s_b[w];
+    float* Bf = reinterpret_cast<float*>(Bi);
+    uint8_t* A = s_a[w];
+    uint8_t* S = s_s[w];
+    // row piece of this lane: 16-pixel blocks: 8 bytes of row lane / 2; 8-pixel blocks: 4 bytes of row lane / 2 (lanes 0..15)
+    constexpr int kPiece = PB / 2;
+    const bool mover = PB == 16 || lane < 16;
+    const int mrow = lane >> 1, mcol = (lane & 1) * kPiece;
+
+    const int64_t n_blocks = (int64_t)g.T * g.By * g.Bx;
+    for (int64_t b = (int64_t)blockIdx.x * kWarps + w; b < n_blocks; b += (int64_t)gridDim.x * kWarps) {
+        int lv = levels[b];
+        lv = lv < 0 ? 0 : (lv >= n_levels ? n_levels - 1 : lv);
+        if (only_mask && !((only_mask >> lv) & 1u)) continue;      // the closed-form kernel handles this block (warp-uniform)
+        const int bx = (int)(b % g.Bx);
+        const int64_t q = b / g.Bx;
+        const int by = (int)(q % g.By), t = (int)(q / g.By);
+        const int32_t* tab = tables + (size_t)lv * level_stride(PB);
+        const int small = tab[0], kind = tab[1];
+        const uint8_t* sp = g.src + (int64_t)t * g.src_frame + ((int64_t)by * PB + mrow) * g.src_row + (int64_t)bx * PB + mcol;
+        uint8_t* dp = g.dst + (int64_t)t * g.dst_frame + ((int64_t)by * PB + mrow) * g.dst_row + (int64_t)bx * PB + mcol;
+        if (mover) {
+            if (PB == 16) *reinterpret_cast<uint2*>(A + mrow * PB + mcol) = __ldcs(reinterpret_cast<const uint2*>(sp));
+            else *reinterpret_cast<uint32_t*>(A + mrow * PB + mcol) = __ldcs(reinterpret_cast<const uint32_t*>(sp));
+        }
+        __syncwarp();
+        if (kind != 0 && small < PB) {
+            const int ns = small * small;
+            const int q32 = 32 / small, r32 = 32 - q32 * small;         // how (row, column) of the reduced image advance per 32 lanes
+            if (kind == 1) {
+                int dy = lane / small, dx = lane - dy * small;
+                for (int i = lane; i < ns; i += 32) {
+                    const uint8_t* p = A + (2 * dy) * PB + 2 * dx;
+                    S[i] = (uint8_t)((p[0] + p[1] + p[PB] + p[PB + 1] + 2) >> 2);
+                    dx += r32; dy += q32;
+                    if (dx >= small) { dx -= small; ++dy; }
+                }
+            } else if (kind == 2) {
+                const int f = tab[2];
+                const float scale = __int_as_float(tab[3]);
+                int dy = lane / small, dx = lane - dy * small;
+                for (int i = lane; i < ns; i += 32) {
+                    int sum = 0;
+                    for (int yy = 0; yy < f; ++yy)
+                        for (int xx = 0; xx < f; ++xx) sum += A[(dy * f + yy) * PB + dx * f + xx];
+                    S[i] = (uint8_t)__float2int_rn(__fmul_rn((float)sum, scale));
+                    dx += r32; dy += q32;
+                    if (dx >= small) { dx -= small; ++dy; }
+                }
+            } else {
+                const int32_t* start = tab + 8;
+                const int32_t* ent = tab + 8 + (PB + 1);
+                int y = lane / small, dx = lane - y * small;
+                for (int i = lane; i < PB * small; i += 32) {       // rows: (y, dx)
+                    float acc = 0.f;
+                    for (int e = start[dx]; e < start[dx + 1]; ++e)
+                        acc = __fadd_rn(acc, __fmul_rn((float)A[y * PB + ent[2 * e]], __int_as_float(ent[2 * e + 1])));
+                    Bf[i] = acc;                                    // i == y * small + dx
+                    dx += r32; y += q32;
+                    if (dx >= small) { dx -= small; ++y; }
+                }
+                __syncwarp();
+                int dy = lane / small;
+                dx = lane - dy * small;
+                for (int i = lane; i < ns; i += 32) {               // columns: (dy, dx)
+                    float acc = 0.f;
+                    for (int e = start[dy]; e < start[dy + 1]; ++e)
+                        acc = __fadd_rn(acc, __fmul_rn(Bf[ent[2 * e] * small + dx], __int_as_float(ent[2 * e + 1])));
+                    const int v = __float2int_rn(acc);
+                    S[i] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+                    dx += r32; dy += q32;
+                    if (dx >= small) { dx -= small; ++dy; }
+                }
+            }
+            __syncwarp();
+            // bilinear back up: horizontal pass into Bi[small][PB] (11-bit coefficients), then the vertical one into A
+            const int32_t* lh = tab + 8 + (PB + 1) + 4 * PB;
+            const int32_t* lvt = lh + 4 * PB;
+            for (int i = lane; i < small * PB; i += 32) {
+                const int y = i / PB, d = i % PB;
+                Bi[i] = S[y * small + lh[d]] * lh[2 * PB + d] + S[y * small + lh[PB + d]] * lh[3 * PB + d];
+            }
+            __syncwarp();
+            for (int i = lane; i < N; i += 32) {
+                const int d2 = i / PB, d = i % PB;
+                const int r0 = Bi[lvt[d2] * PB + d] >> 4, r1 = Bi[lvt[PB + d2] * PB + d] >> 4;
+                int v = (((lvt[2 * PB + d2] * r0) >> 16) + ((lvt[3 * PB + d2] * r1) >> 16) + 2) >> 2;
+                A[i] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+            }
+            __syncwarp();
+        }
+        if (mover) {
+            if (PB == 16) __stcs(reinterpret_cast<uint2*>(dp), *reinterpret_cast<const uint2*>(A + mrow * PB + mcol));
+            else __stcs(reinterpret_cast<uint32_t*>(dp), *reinterpret_cast<const uint32_t*>(A + mrow * PB + mcol));
+        }
+        __syncwarp();
+    }
+}
+
 // ----------------------------------------------------------------- downsample, fast path
 // Planar planes, 16- or 8-pixel blocks, power-of-two reductions (the elvis 1x/2x/4x/8x(/16x)
 // pyramid).  Same lane geometry as blur_fast_kernel (8 pixels of one row per lane).
@@ -585,9 +698,14 @@ extern "C" int elvis_degrade_downsample(const elvis_plane* src, const elvis_plan
             else downsample_pow2_kernel<8, false><<<grid2, 256, 0, st>>>(g, levels, tables, n_levels, slow_mask);
         }
         ELVIS_CHECK_LAUNCH();
-        int wpc = 8;
-        while (wpc > 1 && (size_t)wpc * n * 6 > 48 * 1024) wpc >>= 1;
-        downsample_kernel<false><<<grid_for_units(blocks, wpc), wpc * 32, (size_t)wpc * n * 6, st>>>(g, levels, tables, n_levels, wpc, slow_mask);
+        if (al4) {
+            if (block_px == 16) downsample_planar_kernel<16><<<grid_for_units(blocks, 8), 256, 0, st>>>(g, levels, tables, n_levels, slow_mask);
+            else downsample_planar_kernel<8><<<grid_for_units(blocks, 8), 256, 0, st>>>(g, levels, tables, n_levels, slow_mask);
+        } else {
+            int wpc = 8;
+            while (wpc > 1 && (size_t)wpc * n * 6 > 48 * 1024) wpc >>= 1;
+            downsample_kernel<false><<<grid_for_units(blocks, wpc), wpc * 32, (size_t)wpc * n * 6, st>>>(g, levels, tables, n_levels, wpc, slow_mask);
+        }
         ELVIS_CHECK_LAUNCH();
         return ELVIS_OK;
     }
@@ -619,6 +737,16 @@ extern "C" int elvis_degrade_downsample(const elvis_plane* src, const elvis_plan
         }
         ELVIS_CHECK_LAUNCH();
         return ELVIS_OK;
+    }
+    if (g.C == 1 && (block_px == 16 || block_px == 8) && !getenv("ELVIS_DOWNSAMPLE_GENERIC")) {
+        const int a = block_px / 2;
+        if (aligned_to(g.src, a) && aligned_to(g.dst, a) && g.src_frame % a == 0 && g.dst_frame % a == 0 && g.src_row % a == 0 && g.dst_row % a == 0) {
+            const int64_t blocks = (int64_t)n_frames * by * bx;
+            if (block_px == 16) downsample_planar_kernel<16><<<grid_for_units(blocks, 8), 256, 0, st>>>(g, levels, tables, n_levels, 0u);
+            else downsample_planar_kernel<8><<<grid_for_units(blocks, 8), 256, 0, st>>>(g, levels, tables, n_levels, 0u);
+            ELVIS_CHECK_LAUNCH();
+            return ELVIS_OK;
+        }
     }
     int wpc = 8;
     while (wpc > 1 && (size_t)wpc * n * 6 > 48 * 1024) wpc >>= 1;
