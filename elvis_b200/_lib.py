@@ -13,7 +13,7 @@ OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_SHAPE = 0, -1, -2, -3, -4
 F32, F64 = 0, 1
 REMOVE_HIGH, REMOVE_LOW = 0, 1
 LEVELS_ROUND, LEVELS_INVERTED_ROUND, LEVELS_INVERTED_BINS = 0, 1, 2
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class Plane(C.Structure):
@@ -40,6 +40,8 @@ SIGNATURES = {
     "elvis_normalize": [_vp, _i64, _vp, _vp],
     "elvis_importance_scores": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f64, _f64, _vp, _vp],
     "elvis_select_rows": [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp],
+    "elvis_split_channels3": [_vp, _vp, _i32, _vp],
+    "elvis_merge_channels3": [_vp, _vp, _i32, _vp],
     "elvis_normalize_select_rows": [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp],
     "elvis_shrink": [_PP, _PP, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
     "elvis_stretch": [_PP, _PP, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],

@@ -250,6 +250,57 @@ __global__ void __launch_bounds__(256) rgb_to_gray_kernel(const GrayParams p) {
     }
 }
 
+// Packed 3-channel frames <-> three planes.  The reference's frames are packed (H x W x 3); the fast per-block kernels
+// (tensor-core blur, closed-form downsample) work on planes, so the operators split a packed clip, run the plane
+// kernels per channel and merge the result -- two HBM-bound passes instead of the generic packed kernels, which are 4-15x
+// slower than that (tools/time_packed_degrade.py).  Four pixels per thread: 3 words in, one word per plane out (and back).
+struct ChannelParams {
+    uint8_t* packed;
+    uint8_t* plane[3];
+    int64_t packed_frame, packed_row, plane_frame[3], plane_row[3];
+    int32_t T, H, W, words;
+};
+
+template <bool MERGE>
+__global__ void __launch_bounds__(256) channels3_kernel(const ChannelParams p) {
+    const int qw = (p.W + 3) / 4;
+    const int64_t total = (int64_t)p.T * p.H * qw;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int qx = (int)(i % qw);
+        const int yy = (int)((i / qw) % p.H);
+        const int t = (int)(i / ((int64_t)qw * p.H));
+        const int x0 = qx * 4, n = min(4, p.W - x0);
+        uint8_t* pk = p.packed + (int64_t)t * p.packed_frame + (int64_t)yy * p.packed_row + (int64_t)x0 * 3;
+        uint8_t* pl[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) pl[c] = p.plane[c] + (int64_t)t * p.plane_frame[c] + (int64_t)yy * p.plane_row[c] + x0;
+        if (p.words && n == 4) {
+            // packed words of pixels 0..3 with channels (a, b, c):  w0 = a0 b0 c0 a1,  w1 = b1 c1 a2 b2,  w2 = c2 a3 b3 c3
+            if (!MERGE) {
+                const uint32_t w0 = __ldcs(reinterpret_cast<const uint32_t*>(pk)), w1 = __ldcs(reinterpret_cast<const uint32_t*>(pk) + 1),
+                               w2 = __ldcs(reinterpret_cast<const uint32_t*>(pk) + 2);
+                __stcs(reinterpret_cast<uint32_t*>(pl[0]), __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210));
+                __stcs(reinterpret_cast<uint32_t*>(pl[1]), __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210));
+                __stcs(reinterpret_cast<uint32_t*>(pl[2]), __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410));
+            } else {
+                const uint32_t a = __ldcs(reinterpret_cast<const uint32_t*>(pl[0])), b = __ldcs(reinterpret_cast<const uint32_t*>(pl[1])),
+                               c = __ldcs(reinterpret_cast<const uint32_t*>(pl[2]));
+                const uint32_t ab = __byte_perm(a, b, 0x5140), ab2 = __byte_perm(a, b, 0x7362);   // a0 b0 a1 b1 | a2 b2 a3 b3
+                __stcs(reinterpret_cast<uint32_t*>(pk), __byte_perm(ab, c, 0x2410));                                   // a0 b0 c0 a1
+                __stcs(reinterpret_cast<uint32_t*>(pk) + 1, __byte_perm(__byte_perm(ab, ab2, 0x0543), c, 0x2150));     // b1 c1 a2 b2
+                __stcs(reinterpret_cast<uint32_t*>(pk) + 2, __byte_perm(ab2, c, 0x7326));                              // c2 a3 b3 c3
+            }
+        } else {
+            for (int k = 0; k < n; ++k)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (MERGE) pk[3 * k + c] = pl[c][k];
+                    else pl[c][k] = pk[3 * k + c];
+                }
+        }
+    }
+}
+
 // cv2.resize(map, INTER_LINEAR) for float32 / float64 maps (pinned against cv2 4.13 in
 // tests/test_oracle.py: oracle/spec_cv.py resize_linear_float).  cv2 interpolates as a fused
 // lerp, horizontally then vertically: h = fma(S[x1] - S[x0], fx, S[x0]); out = fma(h1 - h0, fy, h0),
@@ -420,4 +471,40 @@ extern "C" int elvis_resize_linear_float(const void* src, int32_t dtype, int32_t
         return ELVIS_ERR_INVALID_ARG;
     ELVIS_CHECK_LAUNCH();
     return ELVIS_OK;
+}
+
+namespace {
+int channels3(const elvis_plane* packed, const elvis_plane* planes, int32_t n_frames, bool merge, elvis_stream_t stream) {
+    if (!plane_ok(packed) || !planes || n_frames <= 0 || packed->channels != 3) return ELVIS_ERR_INVALID_ARG;
+    ChannelParams p;
+    p.packed = static_cast<uint8_t*>(packed->data);
+    p.packed_frame = packed->frame_stride;
+    p.packed_row = packed->row_stride;
+    p.T = n_frames;
+    p.H = packed->height;
+    p.W = packed->width;
+    bool words = aligned_to(p.packed, 4) && packed->frame_stride % 4 == 0 && packed->row_stride % 4 == 0;
+    for (int c = 0; c < 3; ++c) {
+        if (!plane_ok(&planes[c]) || planes[c].channels != 1) return ELVIS_ERR_INVALID_ARG;
+        if (planes[c].height != packed->height || planes[c].width != packed->width) return ELVIS_ERR_SHAPE;
+        p.plane[c] = static_cast<uint8_t*>(planes[c].data);
+        p.plane_frame[c] = planes[c].frame_stride;
+        p.plane_row[c] = planes[c].row_stride;
+        words = words && aligned_to(p.plane[c], 4) && planes[c].frame_stride % 4 == 0 && planes[c].row_stride % 4 == 0;
+    }
+    p.words = words;
+    const unsigned grid = grid_for((int64_t)n_frames * p.H * ((p.W + 3) / 4));
+    if (merge) channels3_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(p);
+    else channels3_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(p);
+    ELVIS_CHECK_LAUNCH();
+    return ELVIS_OK;
+}
+}  // namespace
+
+extern "C" int elvis_split_channels3(const elvis_plane* packed, const elvis_plane* planes, int32_t n_frames, elvis_stream_t stream) {
+    return channels3(packed, planes, n_frames, false, stream);
+}
+
+extern "C" int elvis_merge_channels3(const elvis_plane* planes, const elvis_plane* packed, int32_t n_frames, elvis_stream_t stream) {
+    return channels3(packed, planes, n_frames, true, stream);
 }

@@ -313,8 +313,54 @@ def _degrade_args(clip: torch.Tensor, block_map: torch.Tensor, block_px: int, dt
     return T, by, bx, out
 
 
+def split_channels3(clip: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(T, H, W, 3) uint8 packed frames -> (3, T, H, W) planes."""
+    _check_cuda(clip, torch.uint8, "clip")
+    if clip.dim() != 4 or clip.shape[3] != 3:
+        raise ValueError("clip must be (T, H, W, 3)")
+    T, H, W, _ = clip.shape
+    if out is None:
+        out = torch.empty((3, T, H, W), dtype=torch.uint8, device=clip.device)
+    if clip.numel():
+        planes = (Plane * 3)(*[plane_of(out[c], "planes") for c in range(3)])
+        src = plane_of(clip)
+        call("elvis_split_channels3", C.byref(src), planes, T, _stream())
+    return out
+
+
+def merge_channels3(planes: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(3, T, H, W) uint8 planes -> (T, H, W, 3) packed frames."""
+    _check_cuda(planes, torch.uint8, "planes")
+    if planes.dim() != 4 or planes.shape[0] != 3:
+        raise ValueError("planes must be (3, T, H, W)")
+    _, T, H, W = planes.shape
+    if out is None:
+        out = torch.empty((T, H, W, 3), dtype=torch.uint8, device=planes.device)
+    if planes.numel():
+        pl = (Plane * 3)(*[plane_of(planes[c], "planes") for c in range(3)])
+        dst = plane_of(out, "out")
+        call("elvis_merge_channels3", pl, C.byref(dst), T, _stream())
+    return out
+
+
+def _per_channel(clip: torch.Tensor, out: torch.Tensor, block_px: int, by: int, bx: int, plane_op) -> bool:
+    """Packed 3-channel clips with 8- / 16-pixel blocks: split into planes, run the planar (fast) kernel per channel,
+    merge -- the channels are independent in every per-block degradation (planar Y/U/V == packed per channel).
+    Partial blocks at the right / bottom edge ride along (the planar kernels copy them through)."""
+    if clip.dim() != 4 or clip.shape[3] != 3 or block_px not in (8, 16) or not clip.numel():
+        return False
+    planes = split_channels3(clip)
+    result = torch.empty_like(planes)
+    for c in range(3):
+        plane_op(planes[c], result[c])
+    merge_channels3(result, out)
+    return True
+
+
 def degrade_blur(clip: torch.Tensor, rounds: torch.Tensor, block_px: int, out: torch.Tensor | None = None) -> torch.Tensor:
     T, by, bx, out = _degrade_args(clip, rounds, block_px, torch.int32, out)
+    if _per_channel(clip, out, block_px, by, bx, lambda p, o: degrade_blur(p, rounds, block_px, out=o)):
+        return out
     src, dst = plane_of(clip), plane_of(out, "out")
     call("elvis_degrade_blur", C.byref(src), C.byref(dst), T, block_px, by, bx, _ptr(rounds), _stream())
     return out
@@ -337,6 +383,8 @@ def degrade_downsample(clip: torch.Tensor, levels: torch.Tensor, block_px: int, 
     """small_sizes[level] = side the block is reduced to before being scaled back."""
     T, by, bx, out = _degrade_args(clip, levels, block_px, torch.int32, out)
     small_sizes = tuple(int(s) for s in small_sizes)
+    if _per_channel(clip, out, block_px, by, bx, lambda p, o: degrade_downsample(p, levels, block_px, small_sizes, out=o)):
+        return out
     tab = _device_tables(block_px, small_sizes, clip.device)
     fast_ok = _tables.fast_levels_flag(block_px, small_sizes)
     src, dst = plane_of(clip), plane_of(out, "out")

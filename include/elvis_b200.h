@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ELVIS_B200_ABI_VERSION 6
+#define ELVIS_B200_ABI_VERSION 7
 
 #define ELVIS_OK               0
 #define ELVIS_ERR_INVALID_ARG (-1)   /* NULL pointer, non-positive size, out-of-range parameter   */
@@ -357,6 +357,12 @@ ELVIS_API int elvis_resize_linear_float(const void* src, int32_t dtype, int32_t 
  * (presley.py:184-202: `analyze_frames(np.array(frames), ...)`): cv2.COLOR_RGB2GRAY's 15-bit
  * fixed point, (9798 R + 19235 G + 3735 B + 2^14) >> 15.  rgb: channels = 3; y: channels = 1. */
 ELVIS_API int elvis_rgb_to_gray(const elvis_plane* rgb, const elvis_plane* y, int32_t n_frames, elvis_stream_t stream);
+
+/* Packed 3-channel frames (the reference's H x W x 3 layout) <-> three single-channel planes of the same size.
+ * packed: channels = 3; planes: array of 3 planes with channels = 1 (any strides).  The operators use the pair to run the
+ * fast planar per-block kernels on packed clips (elvis.py:2141-2196 / utils.py:1101-1217 take packed frames). */
+ELVIS_API int elvis_split_channels3(const elvis_plane* packed, const elvis_plane* planes, int32_t n_frames, elvis_stream_t stream);
+ELVIS_API int elvis_merge_channels3(const elvis_plane* planes, const elvis_plane* packed, int32_t n_frames, elvis_stream_t stream);
 
 /* Row-major refill map of stretch_video_frames (presley.py:806-819): map[t][i] = rank of block i
  * among the kept blocks (mask == 0) of frame t in row-major order, or -1 for removed blocks and for

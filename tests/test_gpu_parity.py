@@ -544,6 +544,26 @@ def test_downsample_mixed_levels(dev, pb, smalls):
         assert np.array_equal(got[t], P.downsample_plane(plane[t], small_map[t], pb)), t
 
 
+@pytest.mark.parametrize("H,W", [(5, 7), (16, 64), (33, 130), (8, 4)])
+def test_split_and_merge_channels(dev, H, W):
+    """Packed (T, H, W, 3) <-> three planes: the word path (aligned, width % 4 == 0), the byte path, and windows."""
+    import torch
+    from elvis_b200 import ops
+    rng = np.random.default_rng(H * W)
+    clip = rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8)
+    planes = ops.split_channels3(to_dev(clip, dev))
+    assert np.array_equal(planes.cpu().numpy(), np.moveaxis(clip, 3, 0))
+    assert np.array_equal(ops.merge_channels3(planes).cpu().numpy(), clip)
+    big = torch.zeros((2, H + 2, W + 5, 3), dtype=torch.uint8, device=dev)
+    big[:, 1:-1, 2:2 + W] = to_dev(clip, dev)
+    assert np.array_equal(ops.split_channels3(big[:, 1:-1, 2:2 + W]).cpu().numpy(), np.moveaxis(clip, 3, 0))
+    out = torch.full_like(big, 9)
+    ops.merge_channels3(planes, out=out[:, 1:-1, 2:2 + W])
+    assert np.array_equal(out[:, 1:-1, 2:2 + W].cpu().numpy(), clip)
+    out[:, 1:-1, 2:2 + W] = 9
+    assert bool((out == 9).all())
+
+
 def test_planar_degrade(dev):
     from elvis_b200 import ops
     from elvis_b200.pipeline import PresleyV2, Yuv420
