@@ -22,6 +22,24 @@ def _to_dev(a: np.ndarray, dtype=None) -> torch.Tensor:
     return torch.from_numpy(a).to(_DEV, non_blocking=False)
 
 
+def _frames_to_dev(frames, dtype=np.uint8) -> torch.Tensor:
+    """List of equally shaped host frames -> one (T, ...) device tensor, copied frame by frame: no np.stack of the whole
+    clip on the host (a second full-size pageable buffer whose first touch costs more than the transfers)."""
+    first = np.asarray(frames[0], dtype=dtype)
+    out = torch.empty((len(frames),) + first.shape, dtype=torch.from_numpy(first[:0].ravel()).dtype, device=_DEV)
+    for i, f in enumerate(frames):
+        a = np.ascontiguousarray(np.asarray(f, dtype=dtype))
+        if a.shape != first.shape:
+            raise ValueError("all frames must share a shape")
+        out[i].copy_(torch.from_numpy(a))
+    return out
+
+
+def _frames_to_host(clip: torch.Tensor) -> list:
+    """(T, ...) device tensor -> list of host arrays, one download per frame."""
+    return [clip[i].cpu().numpy() for i in range(clip.shape[0])]
+
+
 def _packed_clip(image: np.ndarray) -> torch.Tensor:
     """(H, W, C) or (H, W) uint8 host image -> (1, H, W[, C]) device clip."""
     if image.dtype != np.uint8:

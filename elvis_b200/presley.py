@@ -12,7 +12,7 @@ import torch
 
 from . import ops
 from . import utils as _utils
-from .elvis import _to_dev, reference_dct_size
+from .elvis import _frames_to_dev, _frames_to_host, _to_dev, reference_dct_size
 
 
 # ------------------------------------------------------------------ EVCA stand-in
@@ -58,15 +58,15 @@ def shrink_video_frames(frames: List[np.ndarray], importance_scores: List[np.nda
     if method is not shrink_frame_row_only or len(frames) == 0:
         out = [method(f, s, block_size, shrink_amount) for f, s in zip(frames, importance_scores)]
         return [o[0] for o in out], [o[1] for o in out]
-    clip = _to_dev(np.stack(frames), np.uint8)
+    clip = _frames_to_dev(frames)
     h, w = clip.shape[1:3]
     by, bx = h // block_size, w // block_size
     k, out_bx = _utils.row_only_plan(by, bx, shrink_amount)
     scores = _to_dev(np.stack([np.asarray(s, np.float64)[:by, :bx] for s in importance_scores]))
     mask = ops.select_rows(scores, _to_dev(k), ops.REMOVE_LOW)
-    shrunk = ops.shrink(clip[:, :by * block_size, :bx * block_size], mask, block_size, out_bx).cpu().numpy()
+    shrunk = _frames_to_host(ops.shrink(clip[:, :by * block_size, :bx * block_size], mask, block_size, out_bx))
     mask_h = mask.cpu().numpy().astype(bool)
-    return [shrunk[i] for i in range(len(frames))], [mask_h[i] for i in range(len(frames))]
+    return shrunk, [mask_h[i] for i in range(len(frames))]
 
 
 def stretch_video_frames(shrunken_frames: List[np.ndarray], removal_masks: List[np.ndarray], block_size: int) -> List[np.ndarray]:
@@ -78,15 +78,14 @@ def stretch_video_frames(shrunken_frames: List[np.ndarray], removal_masks: List[
     if len(shrunken_frames) == 0:
         return []
     masks = _to_dev(np.stack([np.asarray(m) != 0 for m in removal_masks]), np.uint8)
-    clip = _to_dev(np.stack(shrunken_frames), np.uint8)
+    clip = _frames_to_dev(shrunken_frames)
     by, bx = masks.shape[1:]
     sby, sbx = clip.shape[1] // block_size, clip.shape[2] // block_size
     if sbx == 0 or sby == 0:
         z = np.zeros((by * block_size, bx * block_size) + tuple(clip.shape[3:]), np.uint8)
         return [z.copy() for _ in shrunken_frames]
     refill = ops.refill_map(masks, sby * sbx)
-    out = ops.gather_blocks(clip[:, :sby * block_size, :sbx * block_size], refill, block_size, by, bx).cpu().numpy()
-    return [out[i] for i in range(len(shrunken_frames))]
+    return _frames_to_host(ops.gather_blocks(clip[:, :sby * block_size, :sbx * block_size], refill, block_size, by, bx))
 
 
 # ------------------------------------------------------------------ adaptive degradation
@@ -132,9 +131,9 @@ def degrade_video_adaptive(frames: List[np.ndarray], importance_scores: List[np.
     """presley.py:1016-1039, the whole clip in one batch."""
     if len(frames) == 0:
         return [], []
-    clip = _to_dev(np.stack(frames), np.uint8)
+    clip = _frames_to_dev(frames)
     imp = _to_dev(np.stack(importance_scores), np.float64)
     levels = ops.levels_from_scores(imp, ops.LEVELS_INVERTED_ROUND, max_value)
-    out = _degrade_clip(clip, levels, block_size, method).cpu().numpy()
+    out = _frames_to_host(_degrade_clip(clip, levels, block_size, method))
     lv = levels.cpu().numpy()
-    return [out[i] for i in range(len(frames))], [lv[i] for i in range(len(frames))]
+    return out, [lv[i] for i in range(len(frames))]

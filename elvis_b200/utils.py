@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .elvis import _packed_clip, _to_dev
+from .elvis import _frames_to_dev, _frames_to_host, _packed_clip, _to_dev
 
 
 def calculate_importance_scores(frames, block_size: int, alpha: float, beta: float, complexities,
@@ -177,7 +177,7 @@ def restore_with_opencv_unsharp(frames: List[np.ndarray], degradation_maps: np.n
     and temporal blending; the whole clip in one batch."""
     if len(frames) == 0:
         return []
-    clip = _to_dev(np.stack(frames), np.uint8)
+    clip = _frames_to_dev(frames)
     by, bx = clip.shape[1] // block_size, clip.shape[2] // block_size
     maps = np.zeros((len(frames), by, bx), np.int32)
     for i in range(min(len(frames), len(degradation_maps))):
@@ -188,8 +188,7 @@ def restore_with_opencv_unsharp(frames: List[np.ndarray], degradation_maps: np.n
     out = ops.restore_unsharp(clip, _to_dev(maps), block_size, halo=halo, max_level=max(1, int(maps.max())))
     if temporal_blend > 0:
         ops.temporal_blend_(out, temporal_blend)
-    out = out.cpu().numpy()
-    return [out[i] for i in range(len(frames))]
+    return _frames_to_host(out)
 
 
 # utils.py:1253-1317: despite its name the reference's "lanczos" restorer runs the same unsharp mask
@@ -201,7 +200,7 @@ def write_y4m(frames: List[np.ndarray], y4m_path: str, framerate: float) -> None
     """utils.py:453-462: YUV4MPEG2 file, 4:2:0, frames converted like cv2.COLOR_RGB2YUV_I420."""
     height, width = frames[0].shape[:2]
     fps_num = int(round(framerate * 1000))
-    clip = _to_dev(np.stack([np.asarray(f) for f in frames]), np.uint8)
+    clip = _frames_to_dev(frames)
     i420 = ops.rgb_to_i420(clip).cpu().numpy()
     with open(y4m_path, "wb") as f:
         f.write(f"YUV4MPEG2 W{width} H{height} F{fps_num}:1000 Ip A1:1 C420\n".encode())
