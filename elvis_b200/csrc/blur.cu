@@ -292,14 +292,14 @@ __device__ __forceinline__ void blur_imma_rounds(uint32_t& w0, uint32_t& w1, con
 // per tile and scheduler for ~270 of work).  (Boxes of a single tile, 16 x 16 bytes, were measured slower than the direct
 // loads: the TMA unit's cost is per box row, not per byte.)
 template <int PB>
-__global__ void __launch_bounds__(128) blur_imma_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+__global__ void __launch_bounds__(128, 8) blur_imma_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                                                             const int T, const int By, const int Bx, const int32_t* __restrict__ rounds) {
     constexpr int kWarps = 4, kBufs = 3;
     constexpr int kPerTile = 16 / PB;
     constexpr uint32_t kStrip = 2048;
     __shared__ __align__(1024) uint8_t s_buf[kWarps][kBufs][kStrip];
     __shared__ __align__(8) uint64_t s_full[kWarps][kBufs];
-    __shared__ int32_t s_nr[kWarps][8][32];                              // rounds per tile of the current strip, one column per lane
+    __shared__ int32_t s_nr[kWarps][8][4];                               // rounds per tile of the current strip and block of the tile (quadrant)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int gq = lane >> 2, tq = lane & 3;
     const int r0 = imma_tile_row(gq), r1 = imma_tile_row(gq + 8), c0 = 4 * tq;
@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(128) blur_imma_tma_kernel(const __grid_constan
     const uint32_t buf_base = tma::smem_u32(&s_buf[w][0][0]), bar = tma::smem_u32(&s_full[w][0]);
     const uint32_t row0 = (uint32_t)(r0 * 128 + c0), row1 = (uint32_t)(r1 * 128 + c0);
     const int x0 = r0 & 7, x1 = r1 & 7;                                  // swizzle: 16-byte chunk j of row r sits at chunk j ^ (r & 7)
+    const int quad = PB == 8 ? ((gq >= 4) * 2 + (tq >= 2)) : 0;          // which block of the tile my 8 pixels belong to
 
     struct Strip { int sx, ty, t; };
     auto strip_of = [&](int64_t s) {
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(128) blur_imma_tma_kernel(const __grid_constan
     for (int64_t s = first; s < n_strips; s += stride, ++it) {
         const int b = it % kBufs;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s_nr[w][j][lane] = nr_next[j];       // read back by this lane only
+        for (int j = 0; j < 8; ++j) s_nr[w][j][quad] = nr_next[j];       // every lane of a quadrant writes the same value
         load_rounds(s + stride, nr_next);                                // in flight while this strip is worked on
         tma::mbar_wait(bar + 8u * b, (uint32_t)(it / kBufs) & 1u);
         uint8_t* buf = &s_buf[w][b][0];
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(128) blur_imma_tma_kernel(const __grid_constan
             uint32_t* p0 = reinterpret_cast<uint32_t*>(buf + row0 + ((j ^ x0) << 4));
             uint32_t* p1 = reinterpret_cast<uint32_t*>(buf + row1 + ((j ^ x1) << 4));
             uint32_t w0 = *p0, w1 = *p1;
-            blur_imma_rounds<PB>(w0, w1, a0, a1, s_nr[w][j][lane]);
+            blur_imma_rounds<PB>(w0, w1, a0, a1, s_nr[w][j][quad]);
             *p0 = w0;
             *p1 = w1;
         }
