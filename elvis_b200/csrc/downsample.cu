@@ -666,6 +666,92 @@ __global__ void __launch_bounds__(256) downsample_pow2_yuv420_tma_kernel(const _
     if (tid == 0) tma::store_wait<0>();                               // shared memory must outlive the last store's reads
 }
 
+// Experimental variant (ELVIS_DOWNSAMPLE_TMA=2): the same tiles, but one pipeline PER WARP as in the blur kernel -- a warp
+// takes a whole tile of eight blocks (three box loads onto its own mbarrier, eight blocks in place, three box stores, three
+// tile buffers) and no CTA-wide barrier couples warps whose blocks need different amounts of work.
+__global__ void __launch_bounds__(128) downsample_pow2_yuv420_warp_kernel(const __grid_constant__ DownMaps m, const int T, const int By, const int Bx,
+                                                                          const int32_t* __restrict__ levels, const int max_level) {
+    constexpr int kWarps = 4, kBufs = 3;
+    constexpr uint32_t kTile = 3072, kOffU = 2048, kOffV = 2560;
+    __shared__ __align__(1024) uint8_t s_buf[kWarps][kBufs][kTile];
+    __shared__ __align__(8) uint64_t s_full[kWarps][kBufs];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int groups = (Bx + 7) / 8;
+    const int64_t n_strips = (int64_t)T * By * groups;
+    const int64_t stride = (int64_t)gridDim.x * kWarps, first = (int64_t)blockIdx.x * kWarps + w;
+    const uint32_t buf_base = tma::smem_u32(&s_buf[w][0][0]), bar = tma::smem_u32(&s_full[w][0]);
+    auto issue = [&](int64_t s, int b) {                              // lane 0 only
+        const int gx = (int)(s % groups);
+        const int64_t row = s / groups;                              // t * By + by
+        const int by = (int)(row % By), t = (int)(row / By);
+        const uint32_t dst = buf_base + (uint32_t)b * kTile, bb = bar + 8u * b;
+        tma::mbar_arrive_expect_tx(bb, kTile);
+        tma::load_3d(dst, &m.in[0], gx * 128, by * 16, t, bb);
+        tma::load_3d(dst + kOffU, &m.in[1], gx * 64, by * 8, t, bb);
+        tma::load_3d(dst + kOffV, &m.in[2], gx * 64, by * 8, t, bb);
+    };
+    auto level_of = [&](int64_t s) -> int {                          // lane j < 8: level of block j of strip s
+        if (s >= n_strips || lane >= 8) return 0;
+        const int gx = (int)(s % groups);
+        const int bx = gx * 8 + lane;
+        return bx < Bx ? levels[(s / groups) * Bx + bx] : 0;
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < kBufs; ++b) tma::mbar_init(bar + 8u * b, 1);
+        tma::mbar_init_fence();
+        if (first < n_strips) issue(first, 0);
+        if (first + stride < n_strips) issue(first + stride, 1);
+    }
+    __syncwarp();
+    const int yr = lane >> 1, yh = lane & 1;
+    const int cpl = lane >> 4, gl = lane & 15, cr = gl >> 1, ch = gl & 1;
+    const uint32_t y_row = (uint32_t)(yr * 128 + (yh << 3)), y_x = (uint32_t)(yr & 7);
+    const uint32_t c_row = (cpl ? kOffV : kOffU) + (uint32_t)(cr * 64 + (ch << 2)), c_x = (uint32_t)((cr >> 1) & 3);
+    int lv_next = level_of(first);
+    int it = 0;
+    for (int64_t s = first; s < n_strips; s += stride, ++it) {
+        const int b = it % kBufs;
+        const int lv_mine = lv_next;
+        lv_next = level_of(s + stride);
+        tma::mbar_wait(bar + 8u * b, (uint32_t)(it / kBufs) & 1u);
+        uint8_t* buf = &s_buf[w][b][0];
+        const int gx = (int)(s % groups);
+        const int n_here = min(8, Bx - gx * 8);
+#pragma unroll 1
+        for (int j = 0; j < n_here; ++j) {
+            int L = __shfl_sync(0xffffffffu, lv_mine, j);
+            L = L < 0 ? 0 : (L > max_level ? max_level : L);
+            if (L > 0) {                                              // warp-uniform
+                uint2* py = reinterpret_cast<uint2*>(buf + y_row + (((uint32_t)j ^ y_x) << 4));
+                uint32_t* pc = reinterpret_cast<uint32_t*>(buf + c_row + ((((uint32_t)j >> 1) ^ c_x) << 4) + (((uint32_t)j & 1u) << 3));
+                const uint2 y = *py;
+                uint32_t p0 = y.x, p1 = y.y, c0 = *pc, c1 = 0u;
+                down_up_pow2_level<16>(p0, p1, L > 4 ? 4 : L, lane, 0);
+                down_up_pow2_level<8>(c0, c1, L > 3 ? 3 : L, gl, lane & 16);
+                *py = make_uint2(p0, p1);
+                *pc = c0;
+            }
+        }
+        tma::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            const int64_t row = s / groups;
+            const int by = (int)(row % By), t = (int)(row / By);
+            const uint32_t src = buf_base + (uint32_t)b * kTile;
+            tma::store_3d(&m.out[0], gx * 128, by * 16, t, src);
+            tma::store_3d(&m.out[1], gx * 64, by * 8, t, src + kOffU);
+            tma::store_3d(&m.out[2], gx * 64, by * 8, t, src + kOffV);
+            tma::store_commit();
+            if (s + 2 * stride < n_strips) {
+                tma::store_wait_read<1>();
+                issue(s + 2 * stride, (it + 2) % kBufs);
+            }
+        }
+    }
+    if (lane == 0) tma::store_wait<0>();
+}
+
 }  // namespace
 }  // namespace elvis
 
@@ -815,6 +901,12 @@ extern "C" int elvis_degrade_downsample_pow2_yuv420(const elvis_plane* src_yuv, 
             const CUtensorMapSwizzle sw = i == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
             ok = tma::make_plane_map(&m.in[i], g.src[i], bx * pb, by * pb, n_frames, g.src_row[i], g.src_frame[i], box_w, pb, sw) &&
                  tma::make_plane_map(&m.out[i], g.dst[i], bx * pb, by * pb, n_frames, g.dst_row[i], g.dst_frame[i], box_w, pb, sw);
+        }
+        if (ok && use_tma && use_tma[0] == '2') {
+            const int64_t strips = (int64_t)n_frames * by * ((bx + 7) / 8);
+            downsample_pow2_yuv420_warp_kernel<<<grid_for_units(strips, 4), 128, 0, as_stream(stream)>>>(m, n_frames, by, bx, levels, max_level);
+            ELVIS_CHECK_LAUNCH();
+            return ELVIS_OK;
         }
         if (ok) {
             downsample_pow2_yuv420_tma_kernel<<<grid, 256, 0, as_stream(stream)>>>(m, by, bx, levels, max_level);

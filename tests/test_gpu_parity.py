@@ -465,14 +465,14 @@ def test_presley_degrade_video(dev):
     assert np.array_equal(Pr.blur_block(blk, 2), P.presley_degrade_frame(blk, np.array([[2]]), 16, "blur"))
 
 
-@pytest.mark.parametrize("movers", ["tma", "cp.async"])
+@pytest.mark.parametrize("movers", ["tma", "cp.async", "tma-per-warp"])
 @pytest.mark.parametrize("W", [48, 96, 128, 272, 400])       # 3 / 6 / 8 / 17 / 25 blocks per row: partial tiles, several tiles, odd chroma pitch
 def test_fused_downsample_movers(dev, monkeypatch, movers, W):
     """The fused Y+U+V power-of-two downsample through both tile movers (TMA boxes with swizzle; cp.async pieces),
     levels 0..4, on contiguous planes and on planes that are windows of wider buffers."""
     import torch
     from elvis_b200.pipeline import PresleyV2, Yuv420
-    monkeypatch.setenv("ELVIS_DOWNSAMPLE_TMA", "1" if movers == "tma" else "0")
+    monkeypatch.setenv("ELVIS_DOWNSAMPLE_TMA", {"tma": "1", "cp.async": "0", "tma-per-warp": "2"}[movers])
     T, H, bs = 2, 48, 16
     y, u, v = synth_yuv420(T, H, W, seed=W)
     rng = np.random.default_rng(W)
