@@ -103,3 +103,16 @@ def test_nearest_index_matches_cv2():
         row = np.arange(ssize, dtype=np.float32)[None]
         ref = cv2.resize(row, (dsize, 1), interpolation=cv2.INTER_NEAREST)[0].astype(np.int64)
         assert np.array_equal(T.nearest_index(ssize, dsize), ref), (ssize, dsize)
+
+
+def test_fast_levels_flag():
+    """The `fast_tables_ok` argument of elvis_degrade_downsample: 1 = every level is a power-of-two reduction, 0 = none (or
+    not describable), otherwise an even value whose bit l + 1 marks level l as one for the table-driven kernel."""
+    from elvis_b200 import _tables as T
+    assert T.fast_levels_flag(16, (16, 8, 4, 2, 1)) == 1
+    assert T.fast_levels_flag(8, (8, 4, 2, 2)) == 1
+    assert T.fast_levels_flag(16, (16, 8, 5, 4)) == 1 << 3            # utils.py:1142-1148: only 16 -> 5 is fractional
+    assert T.fast_levels_flag(16, (16, 3, 8, 7, 2, 1)) == (1 << 2) | (1 << 4)
+    assert T.fast_levels_flag(16, (5, 3)) == 0                        # nothing for the closed form
+    assert T.fast_levels_flag(32, (32, 16)) == 0                      # only 8- and 16-pixel blocks have the fast kernels
+    assert T.fast_levels_flag(16, (16, 8, 5, 4)) % 2 == 0 and T.all_fast(16, (16, 8, 4)) and not T.all_fast(16, (16, 5))
