@@ -26,7 +26,7 @@ def _frames_to_dev(frames, dtype=np.uint8) -> torch.Tensor:
     """List of equally shaped host frames -> one (T, ...) device tensor, copied frame by frame: no np.stack of the whole
     clip on the host (a second full-size pageable buffer whose first touch costs more than the transfers)."""
     first = np.asarray(frames[0], dtype=dtype)
-    out = torch.empty((len(frames),) + first.shape, dtype=torch.from_numpy(first[:0].ravel()).dtype, device=_DEV)
+    out = torch.empty((len(frames),) + first.shape, dtype=torch.from_numpy(np.empty(0, dtype=first.dtype)).dtype, device=_DEV)
     for i, f in enumerate(frames):
         a = np.ascontiguousarray(np.asarray(f, dtype=dtype))
         if a.shape != first.shape:
